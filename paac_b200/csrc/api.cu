@@ -1,0 +1,311 @@
+// extern "C" entry points of libpaacb.so (see include/paacb.h for the contract of each).
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace paacb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// Pillow NEAREST column table for 160 -> 84 (floor((x + 0.5) * 160 / 84) except x = 52 -> 99, x = 73 -> 139).
+static const uint8_t kDefaultCol[PAACB_OBS] = {
+    0,   2,   4,   6,   8,   10,  12,  14,  16,  18,  20,  21,  23,  25,  27,  29,  31,  33,  35,  37,  39,
+    40,  42,  44,  46,  48,  50,  52,  54,  56,  58,  60,  61,  63,  65,  67,  69,  71,  73,  75,  77,  79,
+    80,  82,  84,  86,  88,  90,  92,  94,  96,  98,  99,  101, 103, 105, 107, 109, 111, 113, 115, 117, 119,
+    120, 122, 124, 126, 128, 130, 132, 134, 136, 138, 139, 141, 143, 145, 147, 149, 151, 153, 155, 157, 159};
+
+static void add_tensor(paacb_ctx* c, const char* name, int64_t& off, int ndim, int64_t s0, int64_t s1, int64_t s2,
+                       int64_t s3, int64_t fan_in) {
+  TensorInfo& t = c->tensor[c->n_tensors++];
+  snprintf(t.name, sizeof(t.name), "%s", name);
+  t.offset = off;
+  t.ndim = ndim;
+  t.shape[0] = s0; t.shape[1] = s1; t.shape[2] = s2; t.shape[3] = s3;
+  t.fan_in = fan_in;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= t.shape[i];
+  off += n;
+}
+
+static void add_conv(paacb_ctx* c, const char* name, int k, int cout, int stride, int& h, int& w, int& ch,
+                     int64_t& poff, int64_t& aoff) {
+  LayerGeom& g = c->layer[c->n_layers];
+  g.H = h; g.W = w; g.C = ch; g.R = k; g.S = k; g.stride = stride;
+  g.OH = (h - k) / stride + 1; g.OW = (w - k) / stride + 1; g.N = cout;
+  g.K = k * k * ch;
+  g.in_u8 = (c->n_layers == 0);
+  g.in_act_off = (c->n_layers == 0) ? -1 : c->layer[c->n_layers - 1].out_act_off;
+  g.out_act_off = aoff;
+  aoff += (int64_t)g.OH * g.OW * g.N;
+  char nm[40];
+  g.w_off = poff;
+  snprintf(nm, sizeof(nm), "%s_weights", name);
+  add_tensor(c, nm, poff, 4, k, k, ch, cout, g.K);
+  g.b_off = poff;
+  snprintf(nm, sizeof(nm), "%s_biases", name);
+  add_tensor(c, nm, poff, 1, cout, 0, 0, 0, g.K);
+  h = g.OH; w = g.OW; ch = cout;
+  c->n_layers++;
+}
+
+}  // namespace paacb
+
+using namespace paacb;
+
+extern "C" {
+
+int paacb_version(void) { return PAACB_VERSION; }
+const char* paacb_last_error(void) { return g_err; }
+
+int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
+  PAACB_CHECK_ARG(out != nullptr, "out is NULL");
+  PAACB_CHECK_ARG(arch == PAACB_ARCH_NIPS || arch == PAACB_ARCH_NATURE, "arch must be PAACB_ARCH_NIPS or PAACB_ARCH_NATURE");
+  PAACB_CHECK_ARG(num_actions >= 2 && num_actions <= PAACB_MAX_ACTIONS, "num_actions out of range [2, 18]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("paacb_create: no CUDA device (this library has no CPU path)");
+    return PAACB_ECUDA;
+  }
+  PAACB_CHECK_ARG(device >= 0 && device < ndev, "device index out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return PAACB_ECUDA; }
+  if (prop.major != 10) {
+    set_error("paacb_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return PAACB_EUNSUPPORTED;
+  }
+  paacb_ctx* c = new paacb_ctx();
+  memset(c, 0, sizeof(*c));
+  c->arch = arch; c->num_actions = num_actions; c->device = device; c->math = PAACB_MATH_FP32;
+  c->num_sms = prop.multiProcessorCount;
+  int h = PAACB_OBS, w = PAACB_OBS, ch = PAACB_STACK;
+  int64_t poff = 0, aoff = 0;
+  if (arch == PAACB_ARCH_NIPS) {                       // networks.py:145-149
+    add_conv(c, "conv1", 8, 16, 4, h, w, ch, poff, aoff);
+    add_conv(c, "conv2", 4, 32, 2, h, w, ch, poff, aoff);
+  } else {                                             // networks.py:161-167
+    add_conv(c, "conv1", 8, 32, 4, h, w, ch, poff, aoff);
+    add_conv(c, "conv2", 4, 64, 2, h, w, ch, poff, aoff);
+    add_conv(c, "conv3", 3, 64, 1, h, w, ch, poff, aoff);
+  }
+  {  // hidden fc over the (h, w, c)-flattened activation (networks.py:6-9)
+    const int fin = h * w * ch;
+    const int fout = (arch == PAACB_ARCH_NIPS) ? 256 : 512;
+    LayerGeom& g = c->layer[c->n_layers];
+    g.H = 1; g.W = 1; g.C = fin; g.R = 1; g.S = 1; g.stride = 1; g.OH = 1; g.OW = 1; g.N = fout; g.K = fin;
+    g.in_u8 = 0;
+    g.in_act_off = c->layer[c->n_layers - 1].out_act_off;
+    g.out_act_off = aoff;
+    aoff += fout;
+    const char* nm = (arch == PAACB_ARCH_NIPS) ? "fc3" : "fc4";
+    char buf[40];
+    g.w_off = poff;
+    snprintf(buf, sizeof(buf), "%s_weights", nm);
+    add_tensor(c, buf, poff, 2, fin, fout, 0, 0, fin);
+    g.b_off = poff;
+    snprintf(buf, sizeof(buf), "%s_biases", nm);
+    add_tensor(c, buf, poff, 1, fout, 0, 0, 0, fin);
+    c->n_layers++;
+    c->feat = fout;
+  }
+  c->act_floats_per_sample = aoff;
+  c->actor_w_off = poff;  add_tensor(c, "actor_output_weights", poff, 2, c->feat, num_actions, 0, 0, c->feat);
+  c->actor_b_off = poff;  add_tensor(c, "actor_output_biases", poff, 1, num_actions, 0, 0, 0, c->feat);
+  c->critic_w_off = poff; add_tensor(c, "critic_output_weights", poff, 2, c->feat, 1, 0, 0, c->feat);
+  c->critic_b_off = poff; add_tensor(c, "critic_output_biases", poff, 1, 1, 0, 0, 0, c->feat);
+  c->param_count = poff;
+  for (int y = 0; y < PAACB_OBS; ++y) {
+    c->tabs.row[y] = (uint8_t)(((2 * y + 1) * 5) / 4);   // floor((y + 0.5) * 2.5)
+    c->tabs.col[y] = kDefaultCol[y];
+  }
+  *out = c;
+  return PAACB_OK;
+}
+
+int paacb_destroy(paacb_ctx* ctx) {
+  delete ctx;
+  return PAACB_OK;
+}
+
+int paacb_set_math(paacb_ctx* ctx, int math_mode) {
+  PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  PAACB_CHECK_ARG(math_mode == PAACB_MATH_FP32 || math_mode == PAACB_MATH_TF32X3 || math_mode == PAACB_MATH_TF32,
+                  "unknown math mode");
+  ctx->math = math_mode;
+  return PAACB_OK;
+}
+
+int paacb_get_math(const paacb_ctx* ctx) { return ctx ? ctx->math : PAACB_EINVAL; }
+
+int paacb_set_resize_tables(paacb_ctx* ctx, const int32_t* row84, const int32_t* col84) {
+  PAACB_CHECK_ARG(ctx && row84 && col84, "NULL argument");
+  for (int i = 0; i < PAACB_OBS; ++i) {
+    PAACB_CHECK_ARG(row84[i] >= 0 && row84[i] < PAACB_FRAME_H && col84[i] >= 0 && col84[i] < PAACB_FRAME_W,
+                    "table entry out of range");
+    ctx->tabs.row[i] = (uint8_t)row84[i];
+    ctx->tabs.col[i] = (uint8_t)col84[i];
+  }
+  return PAACB_OK;
+}
+
+int64_t paacb_param_count(const paacb_ctx* ctx) { return ctx ? ctx->param_count : PAACB_EINVAL; }
+int paacb_num_tensors(const paacb_ctx* ctx) { return ctx ? ctx->n_tensors : PAACB_EINVAL; }
+
+int paacb_tensor_info(const paacb_ctx* ctx, int index, char* name, int name_cap, int64_t* offset, int* ndim,
+                      int64_t shape[4], int64_t* fan_in) {
+  PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  PAACB_CHECK_ARG(index >= 0 && index < ctx->n_tensors, "tensor index out of range");
+  const TensorInfo& t = ctx->tensor[index];
+  if (name && name_cap > 0) snprintf(name, (size_t)name_cap, "%s", t.name);
+  if (offset) *offset = t.offset;
+  if (ndim) *ndim = t.ndim;
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = t.shape[i];
+  if (fan_in) *fan_in = t.fan_in;
+  return PAACB_OK;
+}
+
+int64_t paacb_forward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
+  return ctx ? ctx->act_floats_per_sample * batch : PAACB_EINVAL;
+}
+int64_t paacb_backward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
+  return ctx ? ctx->act_floats_per_sample * batch : PAACB_EINVAL;
+}
+int64_t paacb_optimizer_workspace_floats(const paacb_ctx* ctx) { return ctx ? optimizer_ws_floats(ctx) : PAACB_EINVAL; }
+int64_t paacb_launch_count(const paacb_ctx* ctx) { return ctx ? ctx->launches : PAACB_EINVAL; }
+
+int paacb_preprocess_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_per_env, const uint8_t* d_reset,
+                        const uint8_t* d_prev, uint8_t* d_next, int64_t n_envs, paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_frames && d_prev && d_next, "NULL argument");
+  PAACB_CHECK_ARG(pairs_per_env == 1 || pairs_per_env == PAACB_STACK, "pairs_per_env must be 1 or 4");
+  PAACB_CHECK_ARG(d_reset == nullptr || pairs_per_env == PAACB_STACK, "reset flags need pairs_per_env == 4");
+  PAACB_CHECK_ARG(n_envs >= 0 && n_envs < (1LL << 31), "n_envs out of range");
+  PAACB_CHECK_ARG(((uintptr_t)d_frames & 15) == 0 && ((uintptr_t)d_prev & 15) == 0 && ((uintptr_t)d_next & 15) == 0,
+                  "buffers must be 16-byte aligned");
+  return launch_preprocess(ctx, d_frames, pairs_per_env, d_reset, d_prev, d_next, n_envs, (cudaStream_t)stream);
+}
+
+static int run_layer_fwd(const paacb_ctx* ctx, int l, const float* d_params, const uint8_t* d_states, int64_t batch,
+                         float* ws, cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[l];
+  const void* x = (l == 0) ? (const void*)d_states : (const void*)(ws + g.in_act_off * batch);
+  float* y = ws + g.out_act_off * batch;
+  if (ctx->math != PAACB_MATH_FP32) {
+    const int rc = launch_conv_fwd_tc(ctx, g, x, d_params + g.w_off, d_params + g.b_off, y, batch,
+                                      ctx->math == PAACB_MATH_TF32X3, st);
+    if (rc != PAACB_EUNSUPPORTED) return rc;
+  }
+  return launch_conv_fwd_simt(ctx, g, x, d_params + g.w_off, d_params + g.b_off, y, batch, st);
+}
+
+int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                         float* d_fwd_ws, float* d_pi, float* d_v, const float* d_uniforms, int32_t* d_actions,
+                         float* d_onehot, paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_params && d_states && d_fwd_ws && d_pi && d_v, "NULL argument");
+  PAACB_CHECK_ARG(batch >= 0 && batch * (int64_t)ctx->layer[0].OH * ctx->layer[0].OW < (1LL << 40), "batch out of range");
+  PAACB_CHECK_ARG(((uintptr_t)d_params & 15) == 0 && ((uintptr_t)d_states & 15) == 0 && ((uintptr_t)d_fwd_ws & 15) == 0,
+                  "params / states / workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = 0; l < ctx->n_layers; ++l) {
+    const int rc = run_layer_fwd(ctx, l, d_params, d_states, batch, d_fwd_ws, st);
+    if (rc != PAACB_OK) return rc;
+  }
+  const float* h = d_fwd_ws + ctx->layer[ctx->n_layers - 1].out_act_off * batch;
+  return launch_heads_fwd(ctx, h, d_params + ctx->actor_w_off, d_params + ctx->actor_b_off,
+                          d_params + ctx->critic_w_off, d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms,
+                          d_actions, d_onehot, st);
+}
+
+int paacb_returns_loss_grad(const paacb_ctx* ctx, const float* d_rewards, const float* d_episode_over,
+                            const float* d_values, const float* d_bootstrap_v, const int32_t* d_actions,
+                            const float* d_pi, const float* d_v, int t_max, int64_t n_envs, double gamma,
+                            float entropy_beta, float* d_y, float* d_adv, float* d_dlogits, float* d_dv,
+                            float* d_loss, paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_rewards && d_episode_over && d_values && d_bootstrap_v && d_actions && d_pi && d_v &&
+                  d_y && d_adv && d_dlogits && d_dv && d_loss, "NULL argument");
+  PAACB_CHECK_ARG(t_max >= 1 && n_envs >= 0, "t_max / n_envs out of range");
+  return launch_returns_loss_grad(ctx, d_rewards, d_episode_over, d_values, d_bootstrap_v, d_actions, d_pi, d_v,
+                                  t_max, n_envs, gamma, entropy_beta, d_y, d_adv, d_dlogits, d_dv, d_loss,
+                                  (cudaStream_t)stream);
+}
+
+int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                   const float* d_fwd_ws, const float* d_dlogits, const float* d_dv, float* d_bwd_ws, float* d_grads,
+                   paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_params && d_states && d_fwd_ws && d_dlogits && d_dv && d_bwd_ws && d_grads, "NULL argument");
+  PAACB_CHECK_ARG(((uintptr_t)d_bwd_ws & 15) == 0 && ((uintptr_t)d_grads & 15) == 0, "workspace / grads must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(d_grads, 0, (size_t)ctx->param_count * sizeof(float), st) != cudaSuccess) {
+    set_error("paacb_backward: memset failed");
+    return PAACB_ECUDA;
+  }
+  const int L = ctx->n_layers;
+  const float* h = d_fwd_ws + ctx->layer[L - 1].out_act_off * batch;
+  float* dh = d_bwd_ws + ctx->layer[L - 1].out_act_off * batch;
+  int rc = launch_heads_bwd(ctx, h, d_params + ctx->actor_w_off, d_params + ctx->critic_w_off, d_dlogits, d_dv, batch,
+                            dh, d_grads + ctx->actor_w_off, d_grads + ctx->actor_b_off, d_grads + ctx->critic_w_off,
+                            d_grads + ctx->critic_b_off, st);
+  if (rc != PAACB_OK) return rc;
+  for (int l = L - 1; l >= 0; --l) {
+    const LayerGeom& g = ctx->layer[l];
+    const void* x = (l == 0) ? (const void*)d_states : (const void*)(d_fwd_ws + g.in_act_off * batch);
+    const float* dz = d_bwd_ws + g.out_act_off * batch;
+    rc = launch_conv_wgrad_simt(ctx, g, x, dz, d_grads + g.w_off, d_grads + g.b_off, batch, st);
+    if (rc != PAACB_OK) return rc;
+    if (l > 0) {
+      rc = launch_conv_dgrad_simt(ctx, g, dz, d_params + g.w_off, (const float*)x, d_bwd_ws + g.in_act_off * batch,
+                                  batch, st);
+      if (rc != PAACB_OK) return rc;
+    }
+  }
+  return PAACB_OK;
+}
+
+int paacb_clip_rmsprop(const paacb_ctx* ctx, float* d_params, float* d_ms, float* d_mom, const float* d_grads,
+                       float grad_scale, float lr, float rho, float eps, float momentum, float clip_norm,
+                       int clip_type, float* d_norm_out, float* d_opt_ws, paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_params && d_ms && d_mom && d_grads && d_opt_ws, "NULL argument");
+  PAACB_CHECK_ARG(clip_type == PAACB_CLIP_IGNORE || clip_type == PAACB_CLIP_GLOBAL,
+                  "clip_type must be ignore or global ('local' is broken in the reference, actor_learner.py:62-63)");
+  PAACB_CHECK_ARG(clip_type == PAACB_CLIP_IGNORE || clip_norm > 0.f, "clip_norm must be positive");
+  PAACB_CHECK_ARG((((uintptr_t)d_params | (uintptr_t)d_ms | (uintptr_t)d_mom | (uintptr_t)d_grads | (uintptr_t)d_opt_ws) & 15) == 0,
+                  "buffers must be 16-byte aligned");
+  return launch_clip_rmsprop(ctx, d_params, d_ms, d_mom, d_grads, grad_scale, lr, rho, eps, momentum, clip_norm,
+                             clip_type, d_norm_out, d_opt_ws, (cudaStream_t)stream);
+}
+
+int paacb_host_register(void* host_ptr, size_t bytes, void** d_ptr) {
+  PAACB_CHECK_ARG(host_ptr && d_ptr && bytes > 0, "NULL argument");
+  cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaHostRegister(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return PAACB_ECUDA;
+  }
+  e = cudaHostGetDevicePointer(d_ptr, host_ptr, 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaHostUnregister(host_ptr);
+    set_error("cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e));
+    return PAACB_ECUDA;
+  }
+  return PAACB_OK;
+}
+
+int paacb_host_unregister(void* host_ptr) {
+  PAACB_CHECK_ARG(host_ptr != nullptr, "NULL argument");
+  const cudaError_t e = cudaHostUnregister(host_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaHostUnregister failed: %s", cudaGetErrorString(e));
+    return PAACB_ECUDA;
+  }
+  return PAACB_OK;
+}
+
+}  // extern "C"

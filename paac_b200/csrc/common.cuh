@@ -1,0 +1,122 @@
+// Shared declarations for the paacb kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/paacb.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "paacb is written for sm_100a (B200) only"
+#endif
+
+namespace paacb {
+
+// One conv / fc layer viewed as an implicit GEMM: Y[M, N] = im2col(X)[M, K] * W[K, N].
+// X is NHWC [b, H, W, C]; W is HWIO = row-major [K = R*S*C, N = Cout]; Y is NHWC [b, OH, OW, Cout].
+// An fc layer is H = W = R = S = 1, C = in, N = out.
+struct LayerGeom {
+  int H, W, C;        // input
+  int R, S, stride;   // filter
+  int OH, OW, N;      // output (N = Cout)
+  int K;              // R*S*C
+  int in_u8;          // input is the uint8 state tensor (scaled by 1/255 on load)
+  int64_t w_off, b_off;   // offsets into the flat parameter buffer
+  int64_t in_act_off;     // offset of the input activation in the forward workspace, per sample (floats); -1: states
+  int64_t out_act_off;    // offset of the output activation, per sample
+};
+
+struct ResizeTables {
+  uint8_t row[PAACB_OBS];
+  uint8_t col[PAACB_OBS];
+};
+
+struct TensorInfo {
+  char name[40];
+  int64_t offset;
+  int ndim;
+  int64_t shape[4];
+  int64_t fan_in;
+};
+
+}  // namespace paacb
+
+struct paacb_ctx {
+  int arch;
+  int num_actions;
+  int device;
+  int math;
+  int num_sms;
+  int n_layers;                 // conv layers + the hidden fc
+  paacb::LayerGeom layer[4];
+  int feat;                     // hidden fc width F
+  int64_t act_floats_per_sample;   // sum of activation sizes of all layers
+  int64_t actor_w_off, actor_b_off, critic_w_off, critic_b_off;
+  int64_t param_count;
+  int n_tensors;
+  paacb::TensorInfo tensor[PAACB_MAX_TENSORS];
+  paacb::ResizeTables tabs;
+  mutable int64_t launches;
+};
+
+namespace paacb {
+
+void set_error(const char* fmt, ...);
+
+#define PAACB_CHECK_ARG(cond, msg)                         \
+  do {                                                     \
+    if (!(cond)) {                                         \
+      paacb::set_error("%s: %s", __func__, msg);           \
+      return PAACB_EINVAL;                                 \
+    }                                                      \
+  } while (0)
+
+#define PAACB_CHECK_LAUNCH(ctx)                                                        \
+  do {                                                                                 \
+    cudaError_t e__ = cudaPeekAtLastError();                                           \
+    if (e__ != cudaSuccess) {                                                          \
+      paacb::set_error("%s: launch failed: %s", __func__, cudaGetErrorString(e__));    \
+      return PAACB_ECUDA;                                                              \
+    }                                                                                  \
+    (ctx)->launches++;                                                                 \
+  } while (0)
+
+// ---- launchers implemented in the .cu files (all asynchronous on `st`) --------------------------
+int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
+                      const uint8_t* prev, uint8_t* next, int64_t n, cudaStream_t st);
+
+// SIMT fp32 implicit GEMMs (gemm_simt.cu)
+int launch_conv_fwd_simt(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* w, const float* bias,
+                         float* y, int64_t batch, cudaStream_t st);
+// dx[b,H,W,C] = (dz (*) W^T) * (x_act > 0)   (x_act == nullptr: no mask)
+int launch_conv_dgrad_simt(const paacb_ctx* ctx, const LayerGeom& g, const float* dz, const float* w, const float* x_act,
+                           float* dx, int64_t batch, cudaStream_t st);
+// dw[K,N] += im2col(x)^T dz ; db[N] += colsum(dz)    (dw, db must be zeroed by the caller)
+int launch_conv_wgrad_simt(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* dz, float* dw, float* db,
+                           int64_t batch, cudaStream_t st);
+
+// heads (heads.cu)
+int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const float* wa, const float* ba, const float* wc,
+                     const float* bc, int64_t batch, float* pi, float* v, const float* uniforms, int32_t* actions,
+                     float* onehot, cudaStream_t st);
+int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const float* wa, const float* wc, const float* dlogits,
+                     const float* dv, int64_t batch, float* dh, float* dwa, float* dba, float* dwc, float* dbc,
+                     cudaStream_t st);
+
+// loss (loss.cu)
+int launch_returns_loss_grad(const paacb_ctx* ctx, const float* rewards, const float* over, const float* values,
+                             const float* boot, const int32_t* actions, const float* pi, const float* v, int T,
+                             int64_t N, double gamma, float beta, float* y, float* adv, float* dlogits, float* dv,
+                             float* loss, cudaStream_t st);
+
+// optimizer (optim.cu)
+int64_t optimizer_ws_floats(const paacb_ctx* ctx);
+int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* mom, const float* grads, float gscale,
+                        float lr, float rho, float eps, float momentum, float clip, int clip_type, float* norm_out,
+                        float* ws, cudaStream_t st);
+
+// tcgen05 path (gemm_tc.cu); returns PAACB_EUNSUPPORTED when a layer/mode is not covered
+int launch_conv_fwd_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* w, const float* bias,
+                       float* y, int64_t batch, int split3, cudaStream_t st);
+
+}  // namespace paacb

@@ -1,0 +1,182 @@
+// K5 + K6: actor / critic heads, softmax, categorical sampling; and the heads' backward.
+//
+// Forward replaces networks.py:84-89 (softmax layer), policy_v_network.py:24-26,37 (critic, reshape)
+// and paac.py:34-45 / :27 (sampling, one-hot).  One warp per sample: lanes stride the F hidden
+// features, accumulate the A+1 dot products against head weights staged in shared memory, butterfly
+// reduce, then every lane holds the logits; softmax is exp(z - max) / sum as TF's Softmax op.
+// Sampling is inverse-CDF on a caller-supplied uniform (fp32 running sum, last bucket open-ended).
+//
+// Backward: dWa = h^T dlogits, dba = colsum(dlogits), dWc = h^T dv, dbc = sum(dv),
+//           dh = (dlogits Wa^T + dv Wc^T) * [h > 0]   (ReLU mask of the hidden layer fused).
+#include "common.cuh"
+
+namespace paacb {
+
+constexpr int kMaxA = PAACB_MAX_ACTIONS;
+constexpr int kHeadWarps = 8;
+
+__global__ void __launch_bounds__(kHeadWarps * 32)
+heads_fwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, const float* __restrict__ ba,
+                 const float* __restrict__ wc, const float* __restrict__ bc, int64_t batch, int F, int A,
+                 float* __restrict__ pi, float* __restrict__ v, const float* __restrict__ uniforms,
+                 int32_t* __restrict__ actions, float* __restrict__ onehot) {
+  extern __shared__ float sw[];              // [F][A+1]: actor columns then the critic column
+  const int A1 = A + 1;
+  for (int i = threadIdx.x; i < F * A1; i += blockDim.x) {
+    const int f = i / A1, a = i - f * A1;
+    sw[i] = (a < A) ? __ldg(wa + (int64_t)f * A + a) : __ldg(wc + f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t b = (int64_t)blockIdx.x * kHeadWarps + warp; b < batch; b += (int64_t)gridDim.x * kHeadWarps) {
+    float acc[kMaxA + 1];
+#pragma unroll
+    for (int a = 0; a <= kMaxA; ++a) acc[a] = 0.f;
+    const float* hr = h + b * F;
+    for (int f = lane; f < F; f += 32) {
+      const float hv = __ldg(hr + f);
+      const float* wr = sw + f * A1;
+#pragma unroll
+      for (int a = 0; a <= kMaxA; ++a)
+        if (a < A1) acc[a] = fmaf(hv, wr[a], acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a <= kMaxA; ++a) {
+      if (a < A1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+      }
+    }
+    // every lane now holds all A+1 sums; lanes 0..A-1 keep their own logit
+    float z = -INFINITY, val = 0.f;
+#pragma unroll
+    for (int a = 0; a <= kMaxA; ++a) {
+      if (a < A && lane == a) z = acc[a] + __ldg(ba + a);
+      if (a == A) val = acc[a] + __ldg(bc);
+    }
+    float mx = z;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = (lane < A) ? expf(z - mx) : 0.f;
+    float sum = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float p = e / sum;
+    if (lane < A) pi[b * A + lane] = p;
+    if (lane == 0) v[b] = val;
+    if (uniforms != nullptr) {
+      const float u = __ldg(uniforms + b);
+      // fp32 running sum in index order: c_j = c_{j-1} + p_j; action = first j < A-1 with u < c_j
+      int act = A - 1;
+      float c = 0.f;
+      bool done = false;
+      for (int j = 0; j < A - 1; ++j) {
+        c += __shfl_sync(0xffffffffu, p, j);
+        if (!done && u < c) { act = j; done = true; }
+      }
+      if (actions != nullptr && lane == 0) actions[b] = act;
+      if (onehot != nullptr && lane < A) onehot[b * A + lane] = (lane == act) ? 1.f : 0.f;
+    }
+  }
+}
+
+constexpr int kHbThreads = 256;
+constexpr int kHbChunk = 64;     // samples per CTA
+
+template <int FPT>   // features per thread: F = FPT * 256
+__global__ void __launch_bounds__(kHbThreads)
+heads_bwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, const float* __restrict__ wc,
+                 const float* __restrict__ dlogits, const float* __restrict__ dv, int64_t batch, int F, int A,
+                 float* __restrict__ dh, float* __restrict__ dwa, float* __restrict__ dba, float* __restrict__ dwc,
+                 float* __restrict__ dbc) {
+  __shared__ float sd[kHbChunk][kMaxA + 2];      // dlogits row then dv
+  const int A1 = A + 1;
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * kHbChunk;
+  const int nb = (int)((batch - b0 < kHbChunk) ? batch - b0 : kHbChunk);
+  for (int i = tid; i < nb * A1; i += kHbThreads) {
+    const int r = i / A1, a = i - r * A1;
+    sd[r][a] = (a < A) ? __ldg(dlogits + (b0 + r) * A + a) : __ldg(dv + b0 + r);
+  }
+  float wreg[FPT][kMaxA + 1];
+  float gacc[FPT][kMaxA + 1];
+#pragma unroll
+  for (int q = 0; q < FPT; ++q) {
+    const int f = tid + q * kHbThreads;
+#pragma unroll
+    for (int a = 0; a <= kMaxA; ++a) {
+      gacc[q][a] = 0.f;
+      wreg[q][a] = 0.f;
+      if (f < F && a < A) wreg[q][a] = __ldg(wa + (int64_t)f * A + a);
+      if (f < F && a == A) wreg[q][a] = __ldg(wc + f);
+    }
+  }
+  __syncthreads();
+  for (int r = 0; r < nb; ++r) {
+#pragma unroll
+    for (int q = 0; q < FPT; ++q) {
+      const int f = tid + q * kHbThreads;
+      if (f < F) {
+        const float hv = __ldg(h + (b0 + r) * F + f);
+        float g = 0.f;
+#pragma unroll
+        for (int a = 0; a <= kMaxA; ++a) {
+          if (a < A1) {
+            const float d = sd[r][a];
+            gacc[q][a] = fmaf(hv, d, gacc[q][a]);
+            g = fmaf(d, wreg[q][a], g);
+          }
+        }
+        dh[(b0 + r) * F + f] = hv > 0.f ? g : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < FPT; ++q) {
+    const int f = tid + q * kHbThreads;
+    if (f < F) {
+#pragma unroll
+      for (int a = 0; a <= kMaxA; ++a) {
+        if (a < A) atomicAdd(dwa + (int64_t)f * A + a, gacc[q][a]);
+        if (a == A) atomicAdd(dwc + f, gacc[q][a]);
+      }
+    }
+  }
+  if (tid < A1) {
+    float s = 0.f;
+    for (int r = 0; r < nb; ++r) s += sd[r][tid];
+    if (tid < A) atomicAdd(dba + tid, s); else atomicAdd(dbc, s);
+  }
+}
+
+int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const float* wa, const float* ba, const float* wc,
+                     const float* bc, int64_t batch, float* pi, float* v, const float* uniforms, int32_t* actions,
+                     float* onehot, cudaStream_t st) {
+  if (batch == 0) return PAACB_OK;
+  const int F = ctx->feat, A = ctx->num_actions;
+  int64_t blocks = (batch + kHeadWarps - 1) / kHeadWarps;
+  const int64_t cap = (int64_t)ctx->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = (size_t)F * (A + 1) * sizeof(float);
+  heads_fwd_kernel<<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h, wa, ba, wc, bc, batch, F, A, pi, v, uniforms,
+                                                                     actions, onehot);
+  PAACB_CHECK_LAUNCH(ctx);
+  return PAACB_OK;
+}
+
+int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const float* wa, const float* wc, const float* dlogits,
+                     const float* dv, int64_t batch, float* dh, float* dwa, float* dba, float* dwc, float* dbc,
+                     cudaStream_t st) {
+  if (batch == 0) return PAACB_OK;
+  const int F = ctx->feat, A = ctx->num_actions;
+  const unsigned blocks = (unsigned)((batch + kHbChunk - 1) / kHbChunk);
+  if (F <= kHbThreads)
+    heads_bwd_kernel<1><<<blocks, kHbThreads, 0, st>>>(h, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
+  else if (F <= 2 * kHbThreads)
+    heads_bwd_kernel<2><<<blocks, kHbThreads, 0, st>>>(h, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
+  else { set_error("heads_bwd: hidden width > 512 unsupported"); return PAACB_EUNSUPPORTED; }
+  PAACB_CHECK_LAUNCH(ctx);
+  return PAACB_OK;
+}
+
+}  // namespace paacb

@@ -1,0 +1,95 @@
+// K1: Atari observation pipeline as one vectorised uint8 kernel.
+//
+// Replaces, per env-step (reference file:line):
+//   np.amax(frame_pool, axis=0)                atari_emulator.py:72
+//   imresize(img, (84, 84), 'nearest')         atari_emulator.py:73  (Pillow NEAREST index tables)
+//   ObservationPool.new_observation / get_pooled_observations   environment.py:66-71
+//   reset -> fresh 4-plane stack               emulator_runner.py:26-27 + atari_emulator.py:88-96
+//
+// One CTA per env.  Phase 1 streams only the 84 source rows nearest-sampling selects (2 frames x 84 x
+// 160 B, 16-byte loads, byte-wise max with __vmaxu4) into shared memory.  Phase 2 gathers the 84
+// selected columns from shared memory and merges them into the NHWC uint8 stack: a non-reset step is
+// (prev >> 8) | (new << 24) per pixel word (drop the oldest frame, append the newest as channel 3).
+// HBM traffic per env-step: 26,880 B frames + 28,224 B previous stack read, 28,224 B written.
+#include "common.cuh"
+
+namespace paacb {
+
+constexpr int kFrameBytes = PAACB_FRAME_H * PAACB_FRAME_W;   // 33,600
+constexpr int kRowVec = PAACB_FRAME_W / 16;                   // 10 uint4 per source row
+constexpr int kStateVec = PAACB_OBS * PAACB_OBS / 4;          // 1,764 uint4 per state (4 pixels each)
+constexpr int kThreads = 256;
+constexpr int kVecPerThread = (kStateVec + kThreads - 1) / kThreads;   // 7
+
+__device__ __forceinline__ uint4 shr8(uint4 v) { return make_uint4(v.x >> 8, v.y >> 8, v.z >> 8, v.w >> 8); }
+
+__global__ void __launch_bounds__(kThreads)
+preprocess_u8_kernel(const uint8_t* __restrict__ frames, int pairs, const uint8_t* __restrict__ reset,
+                     const uint8_t* prev, uint8_t* next, ResizeTables tabs) {
+  __shared__ __align__(16) uint8_t plane[PAACB_OBS * PAACB_FRAME_W];
+  __shared__ int s_row[PAACB_OBS];
+  __shared__ int s_col[PAACB_OBS];
+  const int tid = threadIdx.x;
+  const int64_t env = blockIdx.x;
+  if (tid < PAACB_OBS) {
+    s_row[tid] = tabs.row[tid] * PAACB_FRAME_W;
+    s_col[tid] = tabs.col[tid];
+  }
+  const bool rst = (reset != nullptr) && (pairs >= PAACB_STACK) && (reset[env] != 0);
+  const uint4* prev4 = reinterpret_cast<const uint4*>(prev + env * (int64_t)(kStateVec * 16));
+  uint4* next4 = reinterpret_cast<uint4*>(next + env * (int64_t)(kStateVec * 16));
+
+  uint4 acc[kVecPerThread];
+#pragma unroll
+  for (int i = 0; i < kVecPerThread; ++i) {
+    const int idx = tid + i * kThreads;
+    acc[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (!rst && idx < kStateVec) acc[i] = shr8(prev4[idx]);
+  }
+
+  const int nplanes = rst ? PAACB_STACK : 1;
+  for (int p = 0; p < nplanes; ++p) {
+    const uint8_t* f0 = frames + ((env * pairs + p) * 2) * (int64_t)kFrameBytes;
+    const uint8_t* f1 = f0 + kFrameBytes;
+    __syncthreads();   // tables visible (p == 0) / previous plane fully consumed (p > 0)
+    for (int i = tid; i < PAACB_OBS * kRowVec; i += kThreads) {
+      const int y = i / kRowVec, c = i - y * kRowVec;
+      const int src = s_row[y] + c * 16;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(f0 + src));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(f1 + src));
+      uint4 m;
+      m.x = __vmaxu4(a.x, b.x); m.y = __vmaxu4(a.y, b.y); m.z = __vmaxu4(a.z, b.z); m.w = __vmaxu4(a.w, b.w);
+      *reinterpret_cast<uint4*>(plane + y * PAACB_FRAME_W + c * 16) = m;
+    }
+    __syncthreads();
+    const int shift = rst ? 8 * p : 24;
+#pragma unroll
+    for (int i = 0; i < kVecPerThread; ++i) {
+      const int idx = tid + i * kThreads;
+      if (idx < kStateVec) {
+        const int y = idx / (PAACB_OBS / 4);
+        const int x0 = (idx - y * (PAACB_OBS / 4)) * 4;
+        const uint8_t* prow = plane + y * PAACB_FRAME_W;
+        acc[i].x |= (uint32_t)prow[s_col[x0 + 0]] << shift;
+        acc[i].y |= (uint32_t)prow[s_col[x0 + 1]] << shift;
+        acc[i].z |= (uint32_t)prow[s_col[x0 + 2]] << shift;
+        acc[i].w |= (uint32_t)prow[s_col[x0 + 3]] << shift;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kVecPerThread; ++i) {
+    const int idx = tid + i * kThreads;
+    if (idx < kStateVec) next4[idx] = acc[i];
+  }
+}
+
+int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
+                      const uint8_t* prev, uint8_t* next, int64_t n, cudaStream_t st) {
+  if (n == 0) return PAACB_OK;
+  preprocess_u8_kernel<<<(unsigned)n, kThreads, 0, st>>>(frames, pairs, reset, prev, next, ctx->tabs);
+  PAACB_CHECK_LAUNCH(ctx);
+  return PAACB_OK;
+}
+
+}  // namespace paacb

@@ -1,0 +1,152 @@
+"""RolloutEngine: the device-resident half of PAACLearner.train() (paac.py:99-168).
+
+It owns every device buffer one learner needs for N environments and t_max steps and issues the C-ABI
+calls in the order the reference's loop implies:
+
+    for t in range(T):   act(t)      -> paacb_policy_forward(+sample)          paac.py:105-112
+                         observe(t)  -> paacb_preprocess_u8 / state upload     emulator_runner.py:24-31, paac.py:119-123
+    update(lr)           -> bootstrap forward (paac.py:140-142), training forward, paacb_returns_loss_grad
+                            (paac.py:144-149 + the loss graph), paacb_backward, [NCCL allreduce],
+                            paacb_clip_rmsprop (actor_learner.py:54-70)
+
+All launches go to the current torch stream without host synchronisation, so ``update`` (and ``act`` +
+``observe`` when frames are device-resident) can be captured in a CUDA graph (``capture_update``).
+PyTorch is used for memory, streams and torch.distributed only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+STATE_SHAPE = (84, 84, 4)
+FRAME_SLOT_SHAPE = (4, 2, 210, 160)
+
+
+class RolloutEngine(object):
+
+    def __init__(self, network, n_envs, t_max, gamma=0.99, rho=0.99, eps=0.1, momentum=0.0,
+                 clip_norm=3.0, clip_norm_type='global', seed=3, process_group=None, world_size=1):
+        self.net = network
+        self.lib = network._lib
+        self.ctx = network.ctx
+        self.dev = network.torch_device
+        self.N, self.T, self.A = int(n_envs), int(t_max), int(network.num_actions)
+        self.B = self.N * self.T
+        self.gamma, self.rho, self.eps, self.momentum = float(gamma), float(rho), float(eps), float(momentum)
+        self.clip_norm = float(clip_norm)
+        if clip_norm_type == 'global':
+            self.clip_type = _lib.CLIP_GLOBAL
+        elif clip_norm_type == 'ignore':
+            self.clip_type = _lib.CLIP_IGNORE
+        elif clip_norm_type == 'local':
+            raise Exception("clip_norm_type 'local' is broken in the reference (actor_learner.py:62-63 iterates "
+                            "(grad, var) tuples); use 'global' or 'ignore'")
+        else:
+            raise Exception('Norm type not recognized')          # actor_learner.py:67
+        self.beta = float(network.entropy_regularisation_strength)
+        self.group, self.world = process_group, int(world_size)
+
+        d, N, T, A, B = self.dev, self.N, self.T, self.A, self.B
+        f32 = dict(dtype=torch.float32, device=d)
+        self.states = torch.zeros((T + 1, N) + STATE_SHAPE, dtype=torch.uint8, device=d)
+        self.actions = torch.zeros((T, N), dtype=torch.int32, device=d)
+        self.onehot = torch.zeros((N, A), **f32)
+        self.values = torch.zeros((T, N), **f32)
+        self.rewards = torch.zeros((T, N), **f32)
+        self.over = torch.zeros((T, N), **f32)
+        self.uniforms = torch.zeros((T, N), **f32)
+        self.pi_act = torch.zeros((N, A), **f32)
+        self.boot_v = torch.zeros((N,), **f32)
+        self.boot_pi = torch.zeros((N, A), **f32)
+        self.pi = torch.zeros((B, A), **f32)
+        self.v = torch.zeros((B,), **f32)
+        self.y = torch.zeros((B,), **f32)
+        self.adv = torch.zeros((B,), **f32)
+        self.dlogits = torch.zeros((B, A), **f32)
+        self.dv = torch.zeros((B,), **f32)
+        self.loss = torch.zeros((1,), **f32)
+        self.norm = torch.zeros((1,), **f32)
+        P = network.param_count
+        self.grads = torch.zeros((P,), **f32)
+        self.ms = torch.ones((P,), **f32)            # rms slot <- ones, momentum slot <- zeros
+        self.mom = torch.zeros((P,), **f32)
+        self.act_ws = torch.empty((network.workspace_floats(N),), **f32)
+        self.fwd_ws = torch.empty((network.workspace_floats(B),), **f32)
+        self.bwd_ws = torch.empty((int(self.lib.paacb_backward_workspace_floats(self.ctx, B)),), **f32)
+        self.opt_ws = torch.empty((int(self.lib.paacb_optimizer_workspace_floats(self.ctx)),), **f32)
+        self.gen = torch.Generator(device=d)
+        self.gen.manual_seed(int(seed))
+        self._graph = None
+        self._lr_dev = None
+
+    # ---- helpers ----------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def draw_uniforms(self):
+        """One Philox draw per update for all T*N sampling decisions."""
+        self.uniforms.uniform_(0.0, 1.0, generator=self.gen)
+        # uniform_ on fp32 can return exactly 1.0 only by rounding; keep u in [0, 1)
+        self.uniforms.clamp_(max=float(np.nextafter(np.float32(1.0), np.float32(0.0))))
+
+    # ---- rollout ----------------------------------------------------------------------------------
+    def act(self, t):
+        """Forward on states[t] + categorical sampling; fills actions[t], values[t], onehot, pi_act."""
+        self.net.forward(self.states[t], self.pi_act, self.values[t], self.act_ws, uniforms=self.uniforms[t],
+                         actions=self.actions[t], onehot=self.onehot)
+
+    def observe_frames(self, t, frames_ptr, pairs_per_env, reset_u8, rewards, over):
+        """Raw-frame protocol: states[t+1] <- preprocess(frames | states[t]); rewards/over: device tensors."""
+        p = _lib.ptr
+        _lib.check(self.lib.paacb_preprocess_u8(self.ctx, C.c_void_p(frames_ptr), int(pairs_per_env), p(reset_u8),
+                                                p(self.states[t]), p(self.states[t + 1]), self.N, self._stream()),
+                   'paacb_preprocess_u8')
+        self.rewards[t].copy_(rewards, non_blocking=True)
+        self.over[t].copy_(over, non_blocking=True)
+
+    def observe_states(self, t, states, rewards, over):
+        """Classic protocol: the environments produced stacked 84x84x4 observations themselves."""
+        self.states[t + 1].copy_(states, non_blocking=True)
+        self.rewards[t].copy_(rewards, non_blocking=True)
+        self.over[t].copy_(over, non_blocking=True)
+
+    # ---- update -----------------------------------------------------------------------------------
+    def forward_backward(self):
+        """Bootstrap forward, training forward, returns + loss gradient, backward.  Leaves dL/dparams in grads."""
+        T, N, B = self.T, self.N, self.B
+        p = _lib.ptr
+        st = self._stream()
+        self.net.forward(self.states[T], self.boot_pi, self.boot_v, self.act_ws)                  # paac.py:140-142
+        flat_states = self.states[:T].view((B,) + STATE_SHAPE)                                    # paac.py:151
+        self.net.forward(flat_states, self.pi, self.v, self.fwd_ws)
+        _lib.check(self.lib.paacb_returns_loss_grad(
+            self.ctx, p(self.rewards), p(self.over), p(self.values), p(self.boot_v), p(self.actions), p(self.pi),
+            p(self.v), T, N, C.c_double(self.gamma), C.c_float(self.beta), p(self.y), p(self.adv), p(self.dlogits),
+            p(self.dv), p(self.loss), st), 'paacb_returns_loss_grad')
+        _lib.check(self.lib.paacb_backward(self.ctx, p(self.net.params), p(flat_states), B, p(self.fwd_ws),
+                                           p(self.dlogits), p(self.dv), p(self.bwd_ws), p(self.grads), st),
+                   'paacb_backward')
+
+    def allreduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    def apply(self, lr):
+        p = _lib.ptr
+        _lib.check(self.lib.paacb_clip_rmsprop(
+            self.ctx, p(self.net.params), p(self.ms), p(self.mom), p(self.grads), C.c_float(1.0 / self.world),
+            C.c_float(lr), C.c_float(self.rho), C.c_float(self.eps), C.c_float(self.momentum),
+            C.c_float(self.clip_norm), self.clip_type, p(self.norm), p(self.opt_ws), self._stream()),
+            'paacb_clip_rmsprop')
+
+    def roll(self):
+        """The last state of this rollout is the first state of the next (paac.py:99-112 reuse shared_states)."""
+        self.states[0].copy_(self.states[self.T], non_blocking=True)
+
+    def update(self, lr):
+        self.forward_backward()
+        self.allreduce()
+        self.apply(lr)
+        self.roll()

@@ -1,0 +1,151 @@
+"""PAACLearner: mirror of paac.py:13-187 -- the PAAC loop, act -> step envs -> n-step returns -> train step.
+
+Same constructor, ``train()``, ``cleanup()`` and static ``choose_next_actions(network, num_actions, states,
+session)``.  What the reference does with T+2 ``session.run`` calls, three per-env Python loops and NumPy per
+update happens here on the GPU through the C ABI (RolloutEngine); the host keeps only the worker fan-out /
+fan-in and the episode statistics.
+
+Environments that implement the raw-frame protocol (BaseEnvironment.next_raw) write their two pooled raw
+frames into shared, pinned+mapped memory and the GPU does max-pool + resize + stacking; others hand over
+stacked 84x84x4 observations exactly as in the reference.
+"""
+import logging
+import time
+
+import numpy as np
+import torch
+
+from .actor_learner import ActorLearner
+from .emulator_runner import EmulatorRunner, RawFrameEmulatorRunner
+from .engine import FRAME_SLOT_SHAPE
+from .runners import Runners
+from .session import forward_numpy
+
+
+class PAACLearner(ActorLearner):
+    def __init__(self, network_creator, environment_creator, args):
+        super(PAACLearner, self).__init__(network_creator, environment_creator, args)
+        self.workers = args.emulator_workers
+        self.raw_frames = bool(getattr(args, 'raw_frames', True))
+        self.last_loss = None
+        self.last_norm = None
+
+    @staticmethod
+    def choose_next_actions(network, num_actions, states, session):
+        """paac.py:18-29: forward + categorical sampling; returns (one_hot [N,A], v [N], pi [N,A])."""
+        uniforms = np.random.random_sample(len(states)).astype(np.float32)
+        uniforms = np.minimum(uniforms, np.nextafter(np.float32(1.0), np.float32(0.0)))
+        network_output_pi, network_output_v, action_indices = forward_numpy(network, states, uniforms)
+        new_actions = np.eye(num_actions)[action_indices]
+        return new_actions, network_output_v, network_output_pi
+
+    def __choose_next_actions(self, states):
+        return PAACLearner.choose_next_actions(self.network, self.num_actions, states, self.session)
+
+    def train(self):
+        """
+        Main actor learner loop for parallel advantage actor critic learning.
+        """
+        self.global_step = self.init_network()
+
+        logging.debug("Starting training at Step {}".format(self.global_step))
+        counter = 0
+        global_step_start = self.global_step
+        total_rewards = []
+
+        eng = self.engine
+        N, T, A = self.local_emulator_counts, self.max_local_steps, self.num_actions
+        dev = eng.dev
+        raw = self.raw_frames and all(getattr(e, 'supports_raw_frames', False) for e in self.emulators)
+
+        # state (or raw frame slots), reward, episode_over, action -- positional, as paac.py:73-77
+        if raw:
+            first = np.zeros((N,) + FRAME_SLOT_SHAPE, dtype=np.uint8)
+            for i, emulator in enumerate(self.emulators):
+                emulator.get_initial_state_raw(first[i])
+            runner_cls = RawFrameEmulatorRunner
+        else:
+            first = np.asarray([emulator.get_initial_state() for emulator in self.emulators], dtype=np.uint8)
+            runner_cls = EmulatorRunner
+        variables = [first,
+                     (np.zeros(N, dtype=np.float32)),
+                     (np.asarray([False] * N, dtype=np.float32)),
+                     (np.zeros((N, A), dtype=np.float32))]
+
+        self.runners = Runners(runner_cls, self.emulators, self.workers, variables)
+        self.runners.start()
+        shared_states, shared_rewards, shared_episode_over, shared_actions = self.runners.get_shared_variables()
+        states_dev_ptr = self.runners.pin(0)
+        rewards_t = torch.from_numpy(shared_rewards)
+        over_t = torch.from_numpy(shared_episode_over)
+
+        if raw:      # initial stack: every env is "reset" -> four fresh planes
+            all_reset = torch.ones(N, dtype=torch.uint8, device=dev)
+            self._preprocess_into(0, states_dev_ptr, all_reset)
+        else:
+            eng.states[0].copy_(torch.from_numpy(shared_states))
+        torch.cuda.synchronize(dev)
+
+        emulator_steps = np.zeros(N, dtype=np.int64)
+        total_episode_rewards = np.zeros(N, dtype=np.float64)
+        start_time = time.time()
+
+        while self.global_step < self.max_global_steps:
+            loop_start_time = time.time()
+            eng.draw_uniforms()
+            for t in range(T):
+                eng.act(t)                                              # paac.py:105
+                shared_actions[...] = eng.onehot.cpu().numpy()          # paac.py:107-108 (syncs the stream)
+
+                # Start updating all environments with next_actions
+                self.runners.update_environments()
+                self.runners.wait_updated()
+                # Done updating all environments, have new states, rewards and is_over
+
+                if raw:
+                    reset = torch.from_numpy(shared_episode_over.astype(np.uint8)).to(dev, non_blocking=True)
+                    eng.observe_frames(t, states_dev_ptr, 4, reset, rewards_t, over_t)
+                else:
+                    eng.observe_states(t, torch.from_numpy(shared_states), rewards_t, over_t)
+
+                # episode statistics (paac.py:121-138), vectorised; reward clipping happens on the GPU
+                total_episode_rewards += shared_rewards
+                emulator_steps += 1
+                self.global_step += self.emulator_counts
+                for e in np.nonzero(shared_episode_over)[0]:
+                    total_rewards.append(total_episode_rewards[e])
+                    total_episode_rewards[e] = 0
+                    emulator_steps[e] = 0
+
+            eng.update(self.get_lr())                                   # paac.py:140-165
+            self.last_loss, self.last_norm = eng.loss, eng.norm
+
+            counter += 1
+            if counter % (2048 / self.emulator_counts) == 0:
+                curr_time = time.time()
+                global_steps = self.global_step
+                last_ten = 0.0 if len(total_rewards) < 1 else np.mean(total_rewards[-10:])
+                logging.info("Ran {} steps, at {} steps/s ({} steps/s avg), last 10 rewards avg {}"
+                             .format(global_steps,
+                                     self.max_local_steps * self.emulator_counts / (curr_time - loop_start_time),
+                                     (global_steps - global_step_start) / (curr_time - start_time),
+                                     last_ten))
+            self.save_vars()
+
+        torch.cuda.synchronize(dev)
+        self.cleanup()
+
+    def _preprocess_into(self, slot, frames_ptr, reset_u8):
+        import ctypes as C
+        from . import _lib
+        eng = self.engine
+        _lib.check(eng.lib.paacb_preprocess_u8(eng.ctx, C.c_void_p(frames_ptr), 4, _lib.ptr(reset_u8),
+                                               _lib.ptr(eng.states[slot]), _lib.ptr(eng.states[slot]), eng.N,
+                                               eng._stream()), 'paacb_preprocess_u8')
+
+    def cleanup(self):
+        super(PAACLearner, self).cleanup()
+        if getattr(self, 'runners', None) is not None:
+            self.runners.stop()
+            for r in self.runners.runners:
+                r.join(5)
