@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- PAAC env-steps/sec (Nature CNN, t_max=5) on N B200s; update ms.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs E] [--math fp32|tf32x3|tf32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one PAAC update cycle of the hot path over one batch of synthetic input (BASELINE.json configs[2]:
+synthetic raw 210x160 frames, NatureNetwork, 4096 envs per GPU, t_max = 5, 6 actions):
+    5 x [ policy forward on 4096 states + categorical sampling, preprocessing of 4096 raw frame pairs ]
+    + bootstrap forward, training forward on 20,480 states, n-step returns + loss gradient, backward,
+    [NCCL allreduce of the flat gradient when N > 1], global-norm clip + RMSProp.
+One step = 20,480 env-steps per GPU.  `value` = env-steps of all ranks / max-over-ranks device time with the
+frames resident in HBM; `e2e` = the same cycle driven from HOST buffers (pinned frames uploaded and sampled
+actions read back every env step, loss read back every update).  Rank 0 prints ONE JSON line.
+
+--impl reference times the CPU restatement of the reference's path (oracle/cpu_baseline.py; TF1/ALE cannot be
+installed here) on the host cores for the same metric/config, each step a bounded sample of the workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'paac_env_steps_per_sec'
+UNIT = 'env-steps/s'
+T_MAX = 5
+NUM_ACTIONS = 6
+FRAME_PAIR_BYTES = 2 * 210 * 160
+K1_ALGO_BYTES = 33936            # 84 rows x 160 B x 2 frames read + 7,056 B written per env-step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--envs', type=int, default=4096, help='environments per GPU')
+    ap.add_argument('--arch', default='NATURE', choices=['NATURE', 'NIPS'])
+    ap.add_argument('--math', default=os.environ.get('PAACB_BENCH_MATH', 'fp32'), choices=['fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--frame_pool', type=int, default=8, help='device frame buffers rotated between env steps')
+    ap.add_argument('--no_cpu_baseline', action='store_true')
+    ap.add_argument('--no_e2e', action='store_true')
+    ap.add_argument('--ref_envs', type=int, default=64, help='--impl reference: envs per step (bounded sample)')
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {'workload': 'BASELINE.json configs[2]: synthetic raw 210x160 uint8 frame pairs, %sNetwork, %d envs/GPU, '
+                        't_max=%d, %d actions, learner-only (frames resident in HBM)' % (
+                            'Nature' if args.arch == 'NATURE' else 'NIPS', args.envs, T_MAX, NUM_ACTIONS),
+            'arch': args.arch, 'envs_per_gpu': args.envs, 't_max': T_MAX, 'num_actions': NUM_ACTIONS,
+            'env_steps_per_step': args.envs * T_MAX * n_gpus,
+            'parallelism': 'envs sharded over %d GPU(s); one flat fp32 gradient allreduce per update' % n_gpus,
+            'l2': 'inputs larger than L2: each env step reads a different %d-deep rotating frame buffer of %.0f MB and '
+                  'the update streams %.2f GB of activations (L2 = 126 MB)' % (
+                      args.frame_pool, args.envs * FRAME_PAIR_BYTES / 1e6, args.envs * T_MAX * 21632 * 4 * 2 / 1e9)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+    cores = os.cpu_count() or 1
+    sps, ms, done, cores = cpu_baseline.time_cycles(args.arch, args.ref_envs, T_MAX, NUM_ACTIONS, steps=args.steps,
+                                                    warmup=min(args.warmup, 1), cores=cores, max_seconds=240)
+    sample = ('restated reference CPU path (oracle port, not TF1): %d timed update cycles of %d envs x t_max %d '
+              '(a bounded sample of the %d-env workload), torch-CPU fp32 + NumPy preprocessing, %d threads'
+              % (done, args.ref_envs, T_MAX, args.envs, cores))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': sps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done,
+            'warmup': min(args.warmup, 1), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, args.gpus),
+            'cpu_baseline': {'value': sps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': sps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        time.sleep(0.05)
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, r[4:8]):
+                if val.strip().lower() == 'active':
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d['hbm_gbs'], d['bf16_tflops'], d.get('bf16_tflops_sustained', d['bf16_tflops']), 'measured'
+    return 6650.0, 1590.0, 1400.0, 'fallback'
+
+
+def layer_macs(arch):
+    """MACs per sample of each conv/fc layer: (name, macs, has_dgrad)."""
+    if arch == 'NATURE':
+        return [('conv1', 400 * 256 * 32, False), ('conv2', 81 * 512 * 64, True), ('conv3', 49 * 576 * 64, True),
+                ('fc4', 3136 * 512, True)]
+    return [('conv1', 400 * 256 * 16, False), ('conv2', 81 * 256 * 32, True), ('fc3', 2592 * 256, True)]
+
+
+def read_profile(net):
+    lib = net._lib
+    out = {}
+    for s in range(lib.paacb_profile_slots()):
+        name = C.create_string_buffer(64)
+        ms, cnt = C.c_double(), C.c_int64()
+        lib.paacb_profile_read(net.ctx, s, name, 64, C.byref(ms), C.byref(cnt))
+        if cnt.value > 0:
+            out[name.value.decode()] = (ms.value, cnt.value)
+    return out
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    from paac_b200 import _lib
+    from paac_b200.engine import RolloutEngine
+    from paac_b200.policy_v_network import NaturePolicyVNetwork, NIPSPolicyVNetwork
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    N, T, A = args.envs, T_MAX, NUM_ACTIONS
+    conf = dict(name='local_learning', num_actions=A, clip_norm=3.0, clip_norm_type='global', device='/gpu:%d' % local,
+                entropy_regularisation_strength=0.02, seed=3, math=args.math)
+    net = (NaturePolicyVNetwork if args.arch == 'NATURE' else NIPSPolicyVNetwork)(conf)
+    eng = RolloutEngine(net, N, T, seed=3 * (rank + 1), world_size=world)
+    P = net.param_count
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3 * (rank + 1))                                  # mirrors atari_emulator.py:18
+    pool = [torch.randint(0, 256, (N, 1, 2, 210, 160), dtype=torch.uint8, device=dev, generator=gen)
+            for _ in range(args.frame_pool)]
+    u = torch.rand((T, N), device=dev, generator=gen)
+    rewards = torch.where(u < 0.05, -1.0, torch.where(u > 0.95, 1.0, 0.0)).float()
+    over = (torch.rand((T, N), device=dev, generator=gen) < 0.01).float()
+    eng.states[0].copy_(torch.randint(0, 256, eng.states[0].shape, dtype=torch.uint8, device=dev, generator=gen))
+    lr = 0.0224
+    counter = [0]
+
+    def step_device():
+        eng.draw_uniforms()
+        for t in range(T):
+            eng.act(t)
+            buf = pool[counter[0] % len(pool)]
+            counter[0] += 1
+            eng.observe_frames(t, buf.data_ptr(), 1, None, rewards[t], over[t])
+        eng.update(lr)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm ---------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    _lib.check(net._lib.paacb_profile_enable(net.ctx, 1))
+    _lib.check(net._lib.paacb_profile_reset(net.ctx))
+    launches0 = net.launch_count()
+    clocks = ClockSampler(local)
+    ms_total = timed(step_device, args.steps)
+    clk = clocks.stop()
+    launches = net.launch_count() - launches0
+    prof = read_profile(net)
+    _lib.check(net._lib.paacb_profile_enable(net.ctx, 0))
+    loss_val = float(eng.loss.item())
+    ms_per_step = ms_total / args.steps
+    value = world * N * T * args.steps / (ms_total / 1e3)
+
+    # ---- per-kernel roofline table (device time from CUDA events on the launching stream) ---------------
+    hbm_peak, tc_burst, tc_sust, peak_kind = load_peaks()
+    tf32_peak = 0.5 * tc_sust                       # tf32 issues at half the bf16 rate; kernels are timed inside a long step
+    B = N * T
+    fwd_samples = (T * N + N + B) * args.steps       # acting + bootstrap + training forward
+    kernels = []
+    for li, (lname, macs, has_dgrad) in enumerate(layer_macs(args.arch)):
+        for kind, samples in (('fwd', fwd_samples), ('wgrad', B * args.steps), ('dgrad', B * args.steps if has_dgrad else 0)):
+            key = '%s_%s' % (lname, kind)
+            if key in prof and samples:
+                ms, cnt = prof[key]
+                ach = 2.0 * macs * samples / (ms / 1e3) / 1e12
+                kernels.append({'name': key, 'ms': ms, 'launches': cnt, 'bound': 'tensor', 'achieved': ach,
+                                'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak,
+                                'algo_per_launch': 2.0 * macs * samples / cnt})
+    def hbm_row(key, bytes_total):
+        if key in prof:
+            ms, cnt = prof[key]
+            ach = bytes_total / (ms / 1e3) / 1e9
+            kernels.append({'name': key, 'ms': ms, 'launches': cnt, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak,
+                            'unit': 'GB/s', 'frac': ach / hbm_peak, 'algo_per_launch': bytes_total / cnt})
+    hbm_row('preprocess_u8', float(K1_ALGO_BYTES) * N * T * args.steps)
+    hbm_row('returns_loss_grad', (4.0 * (2 * A + 6) * B + 4.0 * N) * args.steps)
+    hbm_row('grad_sumsq', 4.0 * P * args.steps)
+    hbm_row('clip_rmsprop', 24.0 * P * args.steps)
+    F = 512 if args.arch == 'NATURE' else 256
+    hbm_row('heads_fwd', 4.0 * F * (T * N + N + B) * args.steps)       # reads the hidden activations once
+    hbm_row('heads_bwd', 8.0 * F * B * args.steps)                     # reads h, writes dh
+    accounted = sum(k['ms'] for k in kernels)
+    for k in kernels:
+        k['share_of_step'] = k['ms'] / ms_total
+    kernels.sort(key=lambda k: -k['ms'])
+    dom = kernels[0]
+    roofline = {'kernel': dom['name'], 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'],
+                'unit': dom['unit'], 'frac': dom['frac'], 'traffic': None, 'share_of_step': dom['share_of_step'],
+                'launches': dom['launches'], 'avg_launch_ms': dom['ms'] / dom['launches'],
+                'algo_per_launch': dom['algo_per_launch'],
+                'peak_source': ('%s: MEASURED_PEAKS.json ' % peak_kind) +
+                               ('0.5 x bf16_tflops_sustained (kind::tf32 / fp32 contraction; tf32 issues at half the bf16 rate)'
+                                if dom['bound'] == 'tensor' else 'hbm_gbs')}
+    # nominal whole-step fraction: contract flops per env-step / tf32 peak
+    flops_per_env_step = 71.96e6 if args.arch == 'NATURE' else 21.65e6
+    step_frac = (value / world) * flops_per_env_step / 1e12 / tf32_peak
+
+    # ---- end-to-end arm: host buffers in, actions / loss out ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_frames = [torch.randint(0, 256, (N, 1, 2, 210, 160), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        host_rew, host_over = rewards.cpu().pin_memory(), over.cpu().pin_memory()
+        host_onehot = torch.empty((N, A), dtype=torch.float32).pin_memory()
+        host_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
+        stage = torch.empty((N, 1, 2, 210, 160), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev)
+
+        def step_host():
+            eng.draw_uniforms()
+            for t in range(T):
+                eng.act(t)
+                host_onehot.copy_(eng.onehot, non_blocking=True)          # the environments need the actions
+                stream.synchronize()
+                stage.copy_(host_frames[t & 1], non_blocking=True)        # this env step's raw frames, pinned -> HBM
+                eng.observe_frames(t, stage.data_ptr(), 1, None, host_rew[t], host_over[t])
+            eng.update(lr)
+            host_loss.copy_(eng.loss, non_blocking=True)
+            stream.synchronize()
+
+        for _ in range(2):
+            step_host()
+        e_steps = max(2, args.steps // 2)
+        e_ms = timed(step_host, e_steps)
+        e2e = {'value': world * N * T * e_steps / (e_ms / 1e3), 'unit': UNIT, 'steps': e_steps,
+               'ms_per_step': e_ms / e_steps,
+               'h2d_bytes_per_step': T * (N * FRAME_PAIR_BYTES + 2 * 4 * N), 'd2h_bytes_per_step': T * N * A * 4 + 4,
+               'api': 'RolloutEngine.act / observe_frames / update over the C ABI; pinned host frames uploaded and sampled '
+                      'one-hot actions read back every env step, loss read back every update'}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+        c_envs = 32
+        sps, cms, done, cores = cpu_baseline.time_cycles(args.arch, c_envs, T, A, steps=1000, warmup=1, max_seconds=15)
+        cpu = {'value': sps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': 'restated reference CPU path (oracle port, not TF1): %d update cycles of %d envs x t_max %d in ~15 s '
+                         '(BASELINE.json configs[0]-sized batch), torch-CPU fp32 + NumPy preprocessing, %d threads; '
+                         '%.0f ms per cycle' % (done, c_envs, T, cores, cms)}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'update_ms': ms_per_step,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': {'fp32': 'f32', 'tf32x3': 'tf32x3', 'tf32': 'tf32'}[args.math], 'data': 'synthetic',
+                'config': workload_config(args, world), 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
+                'roofline': roofline, 'cpu_baseline': cpu,
+                'step_fraction_of_tf32_peak': step_frac, 'kernel_time_accounted': accounted / ms_total,
+                'kernels': [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels],
+                'loss': loss_val}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -129,6 +129,15 @@ int paacb_clip_rmsprop(const paacb_ctx* ctx, float* d_params, float* d_ms, float
 /* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
 int64_t paacb_launch_count(const paacb_ctx* ctx);
 
+/* ---- per-kernel timing with CUDA events on the launching stream (measurement aid, off by default).
+ * While enabled every kernel launch is bracketed by two event records; paacb_profile_read(slot)
+ * synchronises on the last recorded event and returns the accumulated device time and launch count
+ * of one kernel family ("conv2_wgrad", "clip_rmsprop", ...; "unused" for absent layers). */
+int paacb_profile_enable(paacb_ctx* ctx, int on);
+int paacb_profile_reset(paacb_ctx* ctx);
+int paacb_profile_slots(void);
+int paacb_profile_read(const paacb_ctx* ctx, int slot, char* name, int name_cap, double* total_ms, int64_t* launches);
+
 /* ---- shared-buffer plumbing for the Runners protocol (runners.py:12-16 allocates RawArray buffers
  * that forked workers write).  Page-locks an existing host range and maps it into the device address
  * space so paacb_preprocess_u8 can read the frames the workers wrote without a staging copy.

@@ -37,6 +37,10 @@ PROTOTYPES = {
     'paacb_backward': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_clip_rmsprop': (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
     'paacb_launch_count': (_i64, [_vp]),
+    'paacb_profile_enable': (_i, [_vp, _i]),
+    'paacb_profile_reset': (_i, [_vp]),
+    'paacb_profile_slots': (_i, []),
+    'paacb_profile_read': (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_d), C.POINTER(_i64)]),
     'paacb_host_register': (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
     'paacb_host_unregister': (_i, [_vp]),
 }

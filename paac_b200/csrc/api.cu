@@ -40,6 +40,7 @@ static void add_conv(paacb_ctx* c, const char* name, int k, int cout, int stride
   g.OH = (h - k) / stride + 1; g.OW = (w - k) / stride + 1; g.N = cout;
   g.K = k * k * ch;
   g.in_u8 = (c->n_layers == 0);
+  g.index = c->n_layers;
   g.in_act_off = (c->n_layers == 0) ? -1 : c->layer[c->n_layers - 1].out_act_off;
   g.out_act_off = aoff;
   aoff += (int64_t)g.OH * g.OW * g.N;
@@ -52,6 +53,22 @@ static void add_conv(paacb_ctx* c, const char* name, int k, int cout, int stride
   add_tensor(c, nm, poff, 1, cout, 0, 0, 0, g.K);
   h = g.OH; w = g.OW; ch = cout;
   c->n_layers++;
+}
+
+// Fold the recorded (start, stop) event pairs into the per-kernel accumulators.  Synchronises on the
+// last recorded event, so it is only called from paacb_profile_read or when the event pool is full.
+void prof_drain(const paacb_ctx* ctx) {
+  if (ctx->prof_n == 0) return;
+  cudaEventSynchronize(ctx->prof_ev[2 * (ctx->prof_n - 1) + 1]);
+  for (int i = 0; i < ctx->prof_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) == cudaSuccess) {
+      ctx->prof_ms[ctx->prof_kid[i]] += ms;
+      ctx->prof_cnt[ctx->prof_kid[i]]++;
+    }
+  }
+  cudaGetLastError();
+  ctx->prof_n = 0;
 }
 
 }  // namespace paacb
@@ -100,6 +117,7 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     LayerGeom& g = c->layer[c->n_layers];
     g.H = 1; g.W = 1; g.C = fin; g.R = 1; g.S = 1; g.stride = 1; g.OH = 1; g.OW = 1; g.N = fout; g.K = fin;
     g.in_u8 = 0;
+    g.index = c->n_layers;
     g.in_act_off = c->layer[c->n_layers - 1].out_act_off;
     g.out_act_off = aoff;
     aoff += fout;
@@ -129,7 +147,71 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
 }
 
 int paacb_destroy(paacb_ctx* ctx) {
+  if (ctx == nullptr) return PAACB_OK;
+  if (ctx->prof_ev != nullptr) {
+    for (int i = 0; i < 2 * kMaxProfEvents; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+    delete[] ctx->prof_ev;
+    delete[] ctx->prof_kid;
+  }
   delete ctx;
+  return PAACB_OK;
+}
+
+int paacb_profile_enable(paacb_ctx* ctx, int on) {
+  PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  if (on && ctx->prof_ev == nullptr) {
+    ctx->prof_ev = new cudaEvent_t[2 * kMaxProfEvents];
+    ctx->prof_kid = new int[kMaxProfEvents];
+    for (int i = 0; i < 2 * kMaxProfEvents; ++i) {
+      if (cudaEventCreate(&ctx->prof_ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); return PAACB_ECUDA; }
+    }
+  }
+  if (!on) prof_drain(ctx);
+  ctx->prof_on = on ? 1 : 0;
+  return PAACB_OK;
+}
+
+int paacb_profile_reset(paacb_ctx* ctx) {
+  PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  prof_drain(ctx);
+  for (int i = 0; i < K_COUNT; ++i) { ctx->prof_ms[i] = 0.0; ctx->prof_cnt[i] = 0; }
+  return PAACB_OK;
+}
+
+int paacb_profile_slots(void) { return K_COUNT; }
+
+int paacb_profile_read(const paacb_ctx* ctx, int slot, char* name, int name_cap, double* total_ms, int64_t* launches) {
+  PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  PAACB_CHECK_ARG(slot >= 0 && slot < K_COUNT, "slot out of range");
+  prof_drain(ctx);
+  if (name && name_cap > 0) {
+    const char* base = "";
+    int layer = -1;
+    if (slot == K_PREPROCESS) base = "preprocess_u8";
+    else if (slot < K_HEADS_FWD) { base = "fwd"; layer = slot - K_FWD0; }
+    else if (slot == K_HEADS_FWD) base = "heads_fwd";
+    else if (slot == K_LOSS) base = "returns_loss_grad";
+    else if (slot == K_HEADS_BWD) base = "heads_bwd";
+    else if (slot < K_DGRAD0) { base = "wgrad"; layer = slot - K_WGRAD0; }
+    else if (slot < K_SUMSQ) { base = "dgrad"; layer = slot - K_DGRAD0; }
+    else if (slot == K_SUMSQ) base = "grad_sumsq";
+    else base = "clip_rmsprop";
+    if (layer >= 0) {
+      if (layer < ctx->n_layers) {
+        char lname[40];
+        snprintf(lname, sizeof(lname), "%s", ctx->tensor[2 * layer].name);      // "<layer>_weights"
+        char* us = strrchr(lname, '_');
+        if (us) *us = 0;
+        snprintf(name, (size_t)name_cap, "%s_%s", lname, base);
+      } else {
+        snprintf(name, (size_t)name_cap, "unused");
+      }
+    } else {
+      snprintf(name, (size_t)name_cap, "%s", base);
+    }
+  }
+  if (total_ms) *total_ms = ctx->prof_ms[slot];
+  if (launches) *launches = ctx->prof_cnt[slot];
   return PAACB_OK;
 }
 

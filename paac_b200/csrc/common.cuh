@@ -21,6 +21,7 @@ struct LayerGeom {
   int OH, OW, N;      // output (N = Cout)
   int K;              // R*S*C
   int in_u8;          // input is the uint8 state tensor (scaled by 1/255 on load)
+  int index;          // layer index (0 = conv1); selects the profiling slot
   int64_t w_off, b_off;   // offsets into the flat parameter buffer
   int64_t in_act_off;     // offset of the input activation in the forward workspace, per sample (floats); -1: states
   int64_t out_act_off;    // offset of the output activation, per sample
@@ -30,6 +31,13 @@ struct ResizeTables {
   uint8_t row[PAACB_OBS];
   uint8_t col[PAACB_OBS];
 };
+
+// profiling slots: one per kernel family per layer (paacb_profile_read)
+enum KernelId {
+  K_PREPROCESS = 0, K_FWD0 = 1, K_HEADS_FWD = 5, K_LOSS = 6, K_HEADS_BWD = 7, K_WGRAD0 = 8, K_DGRAD0 = 12,
+  K_SUMSQ = 16, K_RMSPROP = 17, K_COUNT = 18
+};
+constexpr int kMaxProfEvents = 8192;
 
 struct TensorInfo {
   char name[40];
@@ -57,6 +65,13 @@ struct paacb_ctx {
   paacb::TensorInfo tensor[PAACB_MAX_TENSORS];
   paacb::ResizeTables tabs;
   mutable int64_t launches;
+  // optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline numbers)
+  mutable int prof_on;
+  mutable int prof_n;
+  mutable cudaEvent_t* prof_ev;       // 2 * kMaxProfEvents events, created on first enable
+  mutable int* prof_kid;
+  mutable double prof_ms[paacb::K_COUNT];
+  mutable int64_t prof_cnt[paacb::K_COUNT];
 };
 
 namespace paacb {
@@ -71,7 +86,17 @@ void set_error(const char* fmt, ...);
     }                                                      \
   } while (0)
 
-#define PAACB_CHECK_LAUNCH(ctx)                                                        \
+void prof_drain(const paacb_ctx* ctx);
+// bracket a kernel launch: PAACB_LAUNCH_BEGIN(ctx, kid, st); kernel<<<...>>>(...); PAACB_LAUNCH_END(ctx, kid, st);
+#define PAACB_LAUNCH_BEGIN(ctx, kid, st)                                               \
+  do {                                                                                 \
+    if ((ctx)->prof_on) {                                                              \
+      if ((ctx)->prof_n >= paacb::kMaxProfEvents) paacb::prof_drain(ctx);              \
+      cudaEventRecord((ctx)->prof_ev[2 * (ctx)->prof_n], st);                          \
+    }                                                                                  \
+  } while (0)
+
+#define PAACB_LAUNCH_END(ctx, kid, st)                                                 \
   do {                                                                                 \
     cudaError_t e__ = cudaPeekAtLastError();                                           \
     if (e__ != cudaSuccess) {                                                          \
@@ -79,6 +104,10 @@ void set_error(const char* fmt, ...);
       return PAACB_ECUDA;                                                              \
     }                                                                                  \
     (ctx)->launches++;                                                                 \
+    if ((ctx)->prof_on) {                                                              \
+      cudaEventRecord((ctx)->prof_ev[2 * (ctx)->prof_n + 1], st);                      \
+      (ctx)->prof_kid[(ctx)->prof_n++] = (kid);                                        \
+    }                                                                                  \
   } while (0)
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`) --------------------------

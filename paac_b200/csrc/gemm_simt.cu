@@ -385,13 +385,14 @@ int launch_conv_fwd_simt(const paacb_ctx* ctx, const LayerGeom& g, const void* x
   const int64_t M = batch * g.OH * g.OW;
   if (M == 0) return PAACB_OK;
   const unsigned gx = (unsigned)((M + kNT - 1) / kNT);
+  PAACB_LAUNCH_BEGIN(ctx, K_FWD0 + g.index, st);
 #define FWD(BN, TM, TN, U8) \
   conv_fwd_simt_kernel<BN, TM, TN, U8><<<dim3(gx, (g.N + BN - 1) / BN), kNT, 0, st>>>(x, w, bias, y, g, M, 1)
   if (g.N % 64 == 0) { if (g.in_u8) FWD(64, 8, 8, true); else FWD(64, 8, 8, false); }
   else if (g.N % 32 == 0) { if (g.in_u8) FWD(32, 8, 4, true); else FWD(32, 8, 4, false); }
   else { if (g.in_u8) FWD(16, 4, 4, true); else FWD(16, 4, 4, false); }
 #undef FWD
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_FWD0 + g.index, st);
   return PAACB_OK;
 }
 
@@ -403,13 +404,14 @@ int launch_conv_dgrad_simt(const paacb_ctx* ctx, const LayerGeom& g, const float
   const int Hq = (g.H + s - 1) / s, Wq = (g.W + s - 1) / s;
   const int64_t Mc = batch * Hq * Wq;
   const unsigned gx = (unsigned)((Mc + kNT - 1) / kNT);
+  PAACB_LAUNCH_BEGIN(ctx, K_DGRAD0 + g.index, st);
 #define DG(BN, TM, TN) \
   conv_dgrad_simt_kernel<BN, TM, TN><<<dim3(gx, (g.C + BN - 1) / BN, s * s), kNT, 0, st>>>(dz, w, x_act, dx, g, batch)
   if (g.C >= 64) DG(64, 8, 8);
   else if (g.C >= 32) DG(32, 8, 4);
   else DG(16, 4, 4);
 #undef DG
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_DGRAD0 + g.index, st);
   return PAACB_OK;
 }
 
@@ -428,13 +430,14 @@ int launch_conv_wgrad_simt(const paacb_ctx* ctx, const LayerGeom& g, const void*
   const int64_t rows_per_split = ((row_blocks + splits - 1) / splits) * kBR;
   splits = (M + rows_per_split - 1) / rows_per_split;
   const dim3 grid((g.K + 63) / 64, (g.N + bj - 1) / bj, (unsigned)splits);
+  PAACB_LAUNCH_BEGIN(ctx, K_WGRAD0 + g.index, st);
 #define WG(BJ, TM, TN, U8) \
   conv_wgrad_simt_kernel<BJ, TM, TN, U8><<<grid, kNT, 0, st>>>(x, dz, dw, db, g, M, rows_per_split)
   if (bj == 64) { if (g.in_u8) WG(64, 4, 8, true); else WG(64, 4, 8, false); }
   else if (bj == 32) { if (g.in_u8) WG(32, 4, 4, true); else WG(32, 4, 4, false); }
   else { if (g.in_u8) WG(16, 4, 2, true); else WG(16, 4, 2, false); }
 #undef WG
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_WGRAD0 + g.index, st);
   return PAACB_OK;
 }
 

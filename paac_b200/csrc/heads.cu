@@ -158,9 +158,10 @@ int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const float* wa, cons
   const int64_t cap = (int64_t)ctx->num_sms * 8;
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)F * (A + 1) * sizeof(float);
+  PAACB_LAUNCH_BEGIN(ctx, K_HEADS_FWD, st);
   heads_fwd_kernel<<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h, wa, ba, wc, bc, batch, F, A, pi, v, uniforms,
                                                                      actions, onehot);
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_HEADS_FWD, st);
   return PAACB_OK;
 }
 
@@ -170,12 +171,13 @@ int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const float* wa, cons
   if (batch == 0) return PAACB_OK;
   const int F = ctx->feat, A = ctx->num_actions;
   const unsigned blocks = (unsigned)((batch + kHbChunk - 1) / kHbChunk);
+  if (F > 2 * kHbThreads) { set_error("heads_bwd: hidden width > 512 unsupported"); return PAACB_EUNSUPPORTED; }
+  PAACB_LAUNCH_BEGIN(ctx, K_HEADS_BWD, st);
   if (F <= kHbThreads)
     heads_bwd_kernel<1><<<blocks, kHbThreads, 0, st>>>(h, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
-  else if (F <= 2 * kHbThreads)
+  else
     heads_bwd_kernel<2><<<blocks, kHbThreads, 0, st>>>(h, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
-  else { set_error("heads_bwd: hidden width > 512 unsupported"); return PAACB_EUNSUPPORTED; }
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_HEADS_BWD, st);
   return PAACB_OK;
 }
 

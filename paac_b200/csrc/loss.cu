@@ -91,10 +91,11 @@ int launch_returns_loss_grad(const paacb_ctx* ctx, const float* rewards, const f
   if (N == 0 || T == 0) return PAACB_OK;
   if (cudaMemsetAsync(loss, 0, sizeof(float), st) != cudaSuccess) { set_error("memset loss failed"); return PAACB_ECUDA; }
   const unsigned blocks = (unsigned)((N + kLossThreads - 1) / kLossThreads);
+  PAACB_LAUNCH_BEGIN(ctx, K_LOSS, st);
   returns_loss_grad_kernel<<<blocks, kLossThreads, 0, st>>>(rewards, over, values, boot, actions, pi, v, T, N,
                                                              ctx->num_actions, gamma, beta, y, adv, dlogits,
                                                              dv, loss);
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_LOSS, st);
   return PAACB_OK;
 }
 

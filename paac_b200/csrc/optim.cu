@@ -123,11 +123,13 @@ int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* m
   const int64_t P = ctx->param_count;
   const int blocks = opt_blocks(ctx, P);
   double* partials = reinterpret_cast<double*>(ws);
+  PAACB_LAUNCH_BEGIN(ctx, K_SUMSQ, st);
   sumsq_partials_kernel<<<blocks, kOptThreads, 0, st>>>(grads, P, gscale, partials);
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_SUMSQ, st);
+  PAACB_LAUNCH_BEGIN(ctx, K_RMSPROP, st);
   clip_rmsprop_kernel<<<blocks, kOptThreads, 0, st>>>(params, ms, mom, grads, P, gscale, lr, rho, eps, momentum, clip,
                                                       clip_type, partials, blocks, norm_out);
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_RMSPROP, st);
   return PAACB_OK;
 }
 

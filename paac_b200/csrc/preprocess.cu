@@ -87,8 +87,9 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int pairs, const uint8_
 int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
                       const uint8_t* prev, uint8_t* next, int64_t n, cudaStream_t st) {
   if (n == 0) return PAACB_OK;
+  PAACB_LAUNCH_BEGIN(ctx, K_PREPROCESS, st);
   preprocess_u8_kernel<<<(unsigned)n, kThreads, 0, st>>>(frames, pairs, reset, prev, next, ctx->tabs);
-  PAACB_CHECK_LAUNCH(ctx);
+  PAACB_LAUNCH_END(ctx, K_PREPROCESS, st);
   return PAACB_OK;
 }
 

@@ -1,0 +1,53 @@
+"""GPU: PAACLearner.train() end to end on the synthetic environment (host workers + shared, pinned+mapped buffers),
+both runner protocols."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(tmp, raw, arch='NATURE'):
+    from paac_b200 import train
+    a = train.get_arg_parser().parse_args(['-g', 'synthetic', '-d', '/gpu:0', '--arch', arch, '-ec', '8', '-ew', '2',
+                                           '--max_global_steps', str(8 * 5 * 3), '-df', str(tmp) + '/',
+                                           '--raw_frames', 'True' if raw else 'False'])
+    a.synthetic_p_terminal = 0.1
+    return a
+
+
+@pytest.mark.timeout(300)
+def test_train_raw_and_classic_protocols_agree(tmp_path):
+    from paac_b200 import train
+    from paac_b200.paac import PAACLearner
+    results = []
+    for raw in (True, False):
+        args = _args(tmp_path / ('raw' if raw else 'classic'), raw)
+        net_creator, env_creator = train.get_network_and_environment_creator(args)
+        learner = PAACLearner(net_creator, env_creator, args)
+        learner.train()
+        assert learner.global_step == 8 * 5 * 3
+        loss = float(learner.last_loss.item())
+        assert np.isfinite(loss) and np.isfinite(float(learner.last_norm.item()))
+        results.append((learner.engine.states.cpu().numpy(), learner.network.get_params(), loss))
+        assert learner.network.launch_count() > 0
+    # same seeds, same sampled actions => the GPU-preprocessed states equal the host-preprocessed ones, bit for bit
+    assert np.array_equal(results[0][0], results[1][0])
+    assert np.array_equal(results[0][1], results[1][1])
+
+
+@pytest.mark.timeout(300)
+def test_checkpoint_resume(tmp_path):
+    from paac_b200 import train
+    from paac_b200.paac import PAACLearner
+    args = _args(tmp_path, True, 'NIPS')
+    nc, ec = train.get_network_and_environment_creator(args)
+    l1 = PAACLearner(nc, ec, args)
+    l1.train()
+    w = l1.network.get_params()
+    args.max_global_steps = 8 * 5 * 4
+    nc, ec = train.get_network_and_environment_creator(args)
+    l2 = PAACLearner(nc, ec, args)
+    step0 = l2.init_network()
+    assert step0 == 8 * 5 * 3 and np.array_equal(l2.network.get_params(), w)
+    assert abs(float(l2.engine.ms.mean().item()) - 1.0) > 0          # optimizer slots restored, no longer all ones

@@ -1,0 +1,82 @@
+"""GPU: paacb_preprocess_u8 against the oracle and the reference-generated golden sequence.  Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import preprocess as opre
+from oracle.make_golden import gen_frames
+from paac_b200.resize_tables import ROW, COL
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def net():
+    return G.make_net('NIPS', 4)
+
+
+def test_golden_sequence_with_resets(net, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'preprocess_golden.npz'))
+    n_envs, steps = int(g['n_envs']), int(g['steps'])
+    frames = gen_frames(int(g['seed']), n_envs, int(g['n_pairs']))
+    prev = np.zeros((n_envs, 84, 84, 4), np.uint8)
+    for t in range(steps + 1):
+        slots = np.zeros((n_envs, 4, 2, 210, 160), np.uint8)
+        for e in range(n_envs):
+            for j in range(4 if g['resets'][t, e] else 1):
+                slots[e, j] = frames[e, g['used'][t, e, j]]
+        nxt = G.preprocess(net, slots, 4, g['resets'][t], prev).cpu().numpy()
+        assert (nxt == g['states'][t]).all(), 'step %d: %d bytes differ' % (t, (nxt != g['states'][t]).sum())
+        prev = nxt
+
+
+@pytest.mark.parametrize('n', [1, 2, 37, 300])
+def test_random_vs_oracle(net, n):
+    rng = np.random.RandomState(n)
+    frames = rng.randint(0, 256, (n, 4, 2, 210, 160)).astype(np.uint8)
+    prev = rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8)
+    reset = (rng.random_sample(n) < 0.3).astype(np.uint8)
+    want = opre.step_states(prev, frames, reset, ROW, COL)
+    got = G.preprocess(net, frames, 4, reset, prev).cpu().numpy()
+    assert (got == want).all(), '%d bytes differ' % (got != want).sum()
+    # single-slot layout, no reset flags
+    want1 = opre.step_states(prev, frames[:, :1], np.zeros(n, np.uint8), ROW, COL)
+    got1 = G.preprocess(net, np.ascontiguousarray(frames[:, :1]), 1, None, prev).cpu().numpy()
+    assert (got1 == want1).all()
+
+
+def test_in_place_and_empty(net):
+    rng = np.random.RandomState(5)
+    n = 9
+    frames = rng.randint(0, 256, (n, 4, 2, 210, 160)).astype(np.uint8)
+    prev = rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8)
+    reset = np.zeros(n, np.uint8)
+    want = opre.step_states(prev, frames, reset, ROW, COL)
+    buf = G.dev(prev)
+    from paac_b200 import _lib
+    f, r = G.dev(frames), G.dev(reset)
+    _lib.check(net._lib.paacb_preprocess_u8(net.ctx, _lib.ptr(f), 4, _lib.ptr(r), _lib.ptr(buf), _lib.ptr(buf), n, G.stream()))
+    _lib.check(net._lib.paacb_preprocess_u8(net.ctx, _lib.ptr(f), 4, _lib.ptr(r), _lib.ptr(buf), _lib.ptr(buf), 0, G.stream()))
+    torch.cuda.synchronize()
+    assert (buf.cpu().numpy() == want).all()
+    rc = net._lib.paacb_preprocess_u8(net.ctx, _lib.ptr(f), 3, _lib.ptr(r), _lib.ptr(buf), _lib.ptr(buf), n, G.stream())
+    assert rc == -1 and b'pairs_per_env' in net._lib.paacb_last_error()
+
+
+def test_large_batch_properties(net):
+    """Full-size check without the CPU oracle: shift property + max/resize computed with torch ops on the GPU."""
+    n = 4096
+    gen = torch.Generator(device='cuda'); gen.manual_seed(3)
+    frames = torch.randint(0, 256, (n, 1, 2, 210, 160), dtype=torch.uint8, device='cuda', generator=gen)
+    prev = torch.randint(0, 256, (n, 84, 84, 4), dtype=torch.uint8, device='cuda', generator=gen)
+    out = torch.empty_like(prev)
+    from paac_b200 import _lib
+    _lib.check(net._lib.paacb_preprocess_u8(net.ctx, _lib.ptr(frames), 1, None, _lib.ptr(prev), _lib.ptr(out), n, G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[..., :3], prev[..., 1:])
+    mx = torch.maximum(frames[:, 0, 0], frames[:, 0, 1])
+    row = torch.as_tensor(ROW, device='cuda', dtype=torch.long); col = torch.as_tensor(COL, device='cuda', dtype=torch.long)
+    assert torch.equal(out[..., 3], mx[:, row][:, :, col])

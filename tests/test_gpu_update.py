@@ -1,0 +1,166 @@
+"""GPU: returns+loss gradient, backward, clip+RMSProp and the whole update against the oracle and against the
+outputs of the reference's shipped TF graph (tests/golden/tf_graph_nips.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import network, update
+from oracle.make_golden import gen_train_batch
+from paac_b200 import _lib
+from paac_b200.engine import RolloutEngine
+from util import assert_close, rel_err
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('T,N,A', [(5, 37, 6), (1, 1, 4), (5, 256, 18), (3, 130, 6)])
+def test_returns_loss_grad_vs_oracle(T, N, A):
+    net = G.make_net('NIPS', A)
+    rng = np.random.RandomState(T * 1000 + N)
+    rewards = rng.choice([-3.0, -1.0, 0.0, 0.5, 1.0, 7.0], size=(T, N)).astype(np.float32)
+    over = (rng.random_sample((T, N)) < 0.2).astype(np.float32)
+    values = rng.randn(T, N).astype(np.float32)
+    boot = rng.randn(N).astype(np.float32)
+    actions = rng.randint(0, A, T * N).astype(np.int32)
+    logits = rng.randn(T * N, A) * 2
+    logits[0, :] = [-100] * (A - 1) + [50]                      # a saturated policy row
+    pi = np.exp(logits - logits.max(1, keepdims=True)); pi = (pi / pi.sum(1, keepdims=True)).astype(np.float32)
+    v = rng.randn(T * N).astype(np.float32)
+    out = G.returns_loss_grad(net, rewards, over, values, boot, actions, pi, v, 0.99, 0.02)
+    y, adv = update.nstep_returns(rewards, over, values, boot, 0.99)
+    assert np.array_equal(out['y'], y.reshape(-1)) and np.array_equal(out['adv'], adv.reshape(-1))   # f64 recurrence -> f32
+    # loss / gradients: feed pi through the exact-epsilon closed form in float64
+    z = np.log(pi.astype(np.float64) + 1e-300)
+    loss, dz, dvv = network.closed_form_head_grads(z, v, actions, adv.reshape(-1), y.reshape(-1), np.float32(0.02))
+    assert abs(out['loss'][0] - loss) <= 1e-5 * max(1.0, abs(loss))
+    assert_close(out['dlogits'], dz, 1e-5, 'dlogits')
+    assert_close(out['dv'], dvv, 1e-6, 'dv')
+
+
+@pytest.mark.parametrize('arch,A,b', [('NIPS', 4, 3), ('NATURE', 6, 5), ('NATURE', 6, 160), ('NIPS', 18, 97), ('NATURE', 4, 40)])
+def test_backward_vs_autograd(arch, A, b):
+    net = G.make_net(arch, A, seed=11)
+    params = network.unflatten_params(net.get_params(), arch, A)
+    rng = np.random.RandomState(b + A)
+    states = rng.randint(0, 256, (b, 84, 84, 4)).astype(np.uint8)
+    acts = rng.randint(0, A, b)
+    adv = rng.randn(b).astype(np.float32); tgt = rng.randn(b).astype(np.float32)
+    loss, grads, fwd_ref = network.loss_and_grads(params, states, acts, adv, tgt, np.float32(0.02), arch, A)
+    _, g64, _ = network.loss_and_grads(params, states, acts, adv, tgt, 0.02, arch, A, dtype=torch.float64)
+    fwd = G.forward(net, states)
+    _, dz, dv = network.closed_form_head_grads(fwd_ref['logits'], fwd_ref['v'], acts, adv, tgt, np.float32(0.02))
+    flat, _ = G.backward(net, fwd, dz, dv)
+    got = network.unflatten_params(flat, arch, A)
+    for name, _, _ in network.param_specs(arch, A):
+        e_gpu = rel_err(got[name], g64[name])
+        e_cpu = rel_err(grads[name], g64[name])
+        assert e_gpu <= max(1e-4, 4 * e_cpu), '%s: gpu %.2e vs torch-fp32 %.2e (both against fp64)' % (name, e_gpu, e_cpu)
+
+
+@pytest.mark.parametrize('clip_type,gscale', [(_lib.CLIP_GLOBAL, 1.0), (_lib.CLIP_GLOBAL, 0.125), (_lib.CLIP_IGNORE, 1.0)])
+def test_clip_rmsprop_vs_oracle(clip_type, gscale):
+    net = G.make_net('NIPS', 6)                  # P = 677,943: not a multiple of 4 -> exercises the scalar tail
+    P = net.param_count
+    assert P % 4 != 0
+    rng = np.random.RandomState(2)
+    params = rng.randn(P).astype(np.float32) * 0.05
+    ms = (1 + 0.1 * rng.rand(P)).astype(np.float32); mom = (0.01 * rng.randn(P)).astype(np.float32)
+    grads = (rng.randn(P) * 0.05).astype(np.float32)
+    for momentum in (0.0, 0.9):
+        p2, ms2, mom2, norm = G.clip_rmsprop(net, params, ms, mom, grads, gscale, 0.0224, 0.99, 0.1, momentum, 3.0, clip_type)
+        g = grads * np.float32(gscale)
+        want_norm = float(np.sqrt(np.sum(g.astype(np.float64) ** 2)))
+        assert abs(norm - want_norm) <= 1e-5 * want_norm
+        if clip_type == _lib.CLIP_GLOBAL:
+            (gc,), _ = update.clip_by_global_norm([g], 3.0)
+        else:
+            gc = g
+        wp, wms, wmom = update.rmsprop_apply(params, ms, mom, gc, 0.0224, 0.99, 0.1, momentum)
+        assert_close(ms2, wms, 1e-6, 'ms'); assert_close(mom2, wmom, 1e-5, 'mom'); assert_close(p2, wp, 1e-6, 'params')
+        assert_close(p2 - params, wp - params, 1e-4, 'delta')
+    rc = net._lib.paacb_clip_rmsprop(net.ctx, None, None, None, None, 1.0, 0.1, 0.99, 0.1, 0.0, 3.0, 1, None, None, None)
+    assert rc == -1
+
+
+def test_two_updates_match_reference_tf_graph(golden_dir):
+    """The same two train steps the reference's shipped graph was evaluated on (NIPS, A=4, b=12)."""
+    g = np.load(os.path.join(golden_dir, 'tf_graph_nips.npz'))
+    A, b = int(g['A']), int(g['b'])
+    net = G.make_net('NIPS', A, seed=int(g['wseed']))
+    eng = RolloutEngine(net, n_envs=b, t_max=1, gamma=1.0, rho=0.99, eps=0.1, clip_norm=3.0, clip_norm_type='global')
+    for step in range(2):
+        states, acts, adv, tgt = gen_train_batch(int(g['bseed']) + step, b, A)
+        # make paacb_returns_loss_grad reproduce the fed placeholders: gamma = 1, r = 0, no terminal => y = V(s_T) := tgt,
+        # adv = y - values with values := tgt - adv.  The bootstrap forward is overwritten by injecting boot_v.
+        eng.states[0].copy_(G.dev(states)); eng.states[1].copy_(G.dev(states))
+        eng.actions.copy_(G.dev(acts.reshape(1, b), torch.int32))
+        eng.rewards.zero_(); eng.over.zero_()
+        eng.values.copy_(G.dev((tgt - adv).reshape(1, b)))
+        p = _lib.ptr
+        flat_states = eng.states[:1].view(b, 84, 84, 4)
+        net.forward(flat_states, eng.pi, eng.v, eng.fwd_ws)
+        eng.boot_v.copy_(G.dev(tgt))
+        _lib.check(eng.lib.paacb_returns_loss_grad(eng.ctx, p(eng.rewards), p(eng.over), p(eng.values), p(eng.boot_v),
+                                                   p(eng.actions), p(eng.pi), p(eng.v), 1, b, 1.0, 0.02, p(eng.y), p(eng.adv),
+                                                   p(eng.dlogits), p(eng.dv), p(eng.loss), eng._stream()))
+        _lib.check(eng.lib.paacb_backward(eng.ctx, p(net.params), p(flat_states), b, p(eng.fwd_ws), p(eng.dlogits), p(eng.dv),
+                                          p(eng.bwd_ws), p(eng.grads), eng._stream()))
+        eng.apply(float(g['lr']))
+        torch.cuda.synchronize()
+        assert_close(eng.pi.cpu().numpy(), g['pi%d' % step], 1e-4, 'pi'); assert_close(eng.v.cpu().numpy(), g['v%d' % step], 1e-4, 'v')
+        assert abs(eng.loss.item() - float(g['loss%d' % step])) <= 1e-4 * abs(float(g['loss%d' % step]))
+        assert abs(eng.norm.item() - float(g['norm%d' % step])) <= 1e-4 * float(g['norm%d' % step])
+        specs = network.param_specs('NIPS', A)
+        gr = network.unflatten_params(eng.grads.cpu().numpy(), 'NIPS', A)
+        sumsq = np.asarray([np.sum(gr[n].astype(np.float64) ** 2) for n, _, _ in specs])
+        assert_close(sumsq, g['raw_sumsq%d' % step], 2e-4, 'raw grad sumsq')
+        head = np.concatenate([gr[n].reshape(-1)[:64] for n, _, _ in specs])
+        assert_close(head, g['raw_grad_head%d' % step], 1e-4, 'raw grad head')
+        flat = net.get_params()
+        assert_close(flat[::997], g['var_sample%d' % step], 1e-5, 'variables after ApplyRMSProp')
+
+
+def test_engine_update_vs_oracle_composite():
+    arch, A, N, T = 'NATURE', 6, 8, 5
+    net = G.make_net(arch, A, seed=5)
+    eng = RolloutEngine(net, N, T, seed=9)
+    rng = np.random.RandomState(0)
+    states = rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)
+    eng.states.copy_(G.dev(states))
+    eng.draw_uniforms()
+    for t in range(T):
+        eng.act(t)
+    rewards = rng.choice([-2.0, 0.0, 1.0], size=(T, N)).astype(np.float32)
+    over = (rng.random_sample((T, N)) < 0.15).astype(np.float32)
+    eng.rewards.copy_(G.dev(rewards)); eng.over.copy_(G.dev(over))
+    p0 = net.get_params()
+    lr = 0.0224
+    eng.update(lr)
+    torch.cuda.synchronize()
+    # oracle composite (paac.py:105-165)
+    params = network.unflatten_params(p0, arch, A)
+    B = T * N
+    vals = np.stack([network.forward(params, states[t], arch)['v'].numpy() for t in range(T)])
+    assert_close(eng.values.cpu().numpy(), vals, 1e-4, 'acting values')
+    acts = eng.actions.cpu().numpy().reshape(-1)
+    boot = network.forward(params, states[T], arch)['v'].numpy()
+    y, adv = update.nstep_returns(rewards, over, eng.values.cpu().numpy(), eng.boot_v.cpu().numpy(), 0.99)
+    assert_close(eng.boot_v.cpu().numpy(), boot, 1e-4, 'bootstrap')
+    assert np.array_equal(eng.y.cpu().numpy(), y.reshape(-1))
+    loss, grads, _ = network.loss_and_grads(params, states[:T].reshape(B, 84, 84, 4), acts, adv.reshape(-1), y.reshape(-1),
+                                            np.float32(0.02), arch, A)
+    assert abs(eng.loss.item() - loss) <= 1e-4 * max(1, abs(loss))
+    specs = network.param_specs(arch, A)
+    clipped, norm = update.clip_by_global_norm([grads[n] for n, _, _ in specs], 3.0)
+    assert abs(eng.norm.item() - float(norm)) <= 1e-4 * float(norm)
+    new = {}
+    for (n, s, _), gc in zip(specs, clipped):
+        new[n], _, _ = update.rmsprop_apply(params[n], np.ones(s, np.float32), np.zeros(s, np.float32), gc, lr, 0.99, 0.1)
+    want = network.flatten_params(new, arch, A)
+    got = net.get_params()
+    assert_close(got, want, 1e-5, 'post-RMSProp weights')
+    assert_close(got - p0, want - p0, 2e-3, 'weight delta')
+    assert torch.equal(eng.states[0], eng.states[T])
