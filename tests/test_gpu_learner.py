@@ -33,7 +33,8 @@ def test_train_raw_and_classic_protocols_agree(tmp_path):
         assert learner.network.launch_count() > 0
     # same seeds, same sampled actions => the GPU-preprocessed states equal the host-preprocessed ones, bit for bit
     assert np.array_equal(results[0][0], results[1][0])
-    assert np.array_equal(results[0][1], results[1][1])
+    # weights: the weight-gradient kernels accumulate with fp32 atomics (summation order varies run to run)
+    assert np.max(np.abs(results[0][1] - results[1][1])) <= 1e-5 * np.max(np.abs(results[1][1]))
 
 
 @pytest.mark.timeout(300)
