@@ -153,6 +153,8 @@ int paacb_destroy(paacb_ctx* ctx) {
     delete[] ctx->prof_ev;
     delete[] ctx->prof_kid;
   }
+  if (ctx->wpack_hi != nullptr) cudaFree(ctx->wpack_hi);
+  if (ctx->wpack_lo != nullptr) cudaFree(ctx->wpack_lo);
   delete ctx;
   return PAACB_OK;
 }
@@ -195,7 +197,8 @@ int paacb_profile_read(const paacb_ctx* ctx, int slot, char* name, int name_cap,
     else if (slot < K_DGRAD0) { base = "wgrad"; layer = slot - K_WGRAD0; }
     else if (slot < K_SUMSQ) { base = "dgrad"; layer = slot - K_DGRAD0; }
     else if (slot == K_SUMSQ) base = "grad_sumsq";
-    else base = "clip_rmsprop";
+    else if (slot == K_RMSPROP) base = "clip_rmsprop";
+    else base = "pack_weights";
     if (layer >= 0) {
       if (layer < ctx->n_layers) {
         char lname[40];
@@ -219,6 +222,21 @@ int paacb_set_math(paacb_ctx* ctx, int math_mode) {
   PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
   PAACB_CHECK_ARG(math_mode == PAACB_MATH_FP32 || math_mode == PAACB_MATH_TF32X3 || math_mode == PAACB_MATH_TF32,
                   "unknown math mode");
+  if (math_mode != PAACB_MATH_FP32 && ctx->wpack_hi == nullptr) {
+    // context-owned workspace (like a TMA descriptor): the prepacked tf32 weight images, 2 x P words
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(ctx->device);
+    const size_t bytes = (size_t)ctx->param_count * sizeof(uint32_t);
+    const cudaError_t e1 = cudaMalloc(&ctx->wpack_hi, bytes);
+    const cudaError_t e2 = cudaMalloc(&ctx->wpack_lo, bytes);
+    cudaSetDevice(cur);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      cudaGetLastError();
+      set_error("paacb_set_math: cannot allocate %zu bytes for packed weights", 2 * bytes);
+      return PAACB_ECUDA;
+    }
+  }
   ctx->math = math_mode;
   return PAACB_OK;
 }
@@ -293,6 +311,14 @@ int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint
   PAACB_CHECK_ARG(((uintptr_t)d_params & 15) == 0 && ((uintptr_t)d_states & 15) == 0 && ((uintptr_t)d_fwd_ws & 15) == 0,
                   "params / states / workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->math != PAACB_MATH_FP32 && batch > 0) {
+    // the caller may have changed the parameters since the last call: repack (a few microseconds)
+    for (int l = 0; l < ctx->n_layers; ++l) {
+      const LayerGeom& g = ctx->layer[l];
+      const int rc = launch_pack_weights(ctx, g, d_params + g.w_off, ctx->wpack_hi + g.w_off, ctx->wpack_lo + g.w_off, st);
+      if (rc != PAACB_OK) return rc;
+    }
+  }
   for (int l = 0; l < ctx->n_layers; ++l) {
     const int rc = run_layer_fwd(ctx, l, d_params, d_states, batch, d_fwd_ws, st);
     if (rc != PAACB_OK) return rc;

@@ -35,7 +35,7 @@ struct ResizeTables {
 // profiling slots: one per kernel family per layer (paacb_profile_read)
 enum KernelId {
   K_PREPROCESS = 0, K_FWD0 = 1, K_HEADS_FWD = 5, K_LOSS = 6, K_HEADS_BWD = 7, K_WGRAD0 = 8, K_DGRAD0 = 12,
-  K_SUMSQ = 16, K_RMSPROP = 17, K_COUNT = 18
+  K_SUMSQ = 16, K_RMSPROP = 17, K_PACK = 18, K_COUNT = 19
 };
 constexpr int kMaxProfEvents = 8192;
 
@@ -72,6 +72,9 @@ struct paacb_ctx {
   mutable int* prof_kid;
   mutable double prof_ms[paacb::K_COUNT];
   mutable int64_t prof_cnt[paacb::K_COUNT];
+  // context-owned workspace of the tcgen05 path: weights prepacked as swizzled tf32 operand images (hi, lo)
+  uint32_t* wpack_hi;
+  uint32_t* wpack_lo;
 };
 
 namespace paacb {
@@ -145,6 +148,7 @@ int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* m
                         float* ws, cudaStream_t st);
 
 // tcgen05 path (gemm_tc.cu); returns PAACB_EUNSUPPORTED when a layer/mode is not covered
+int launch_pack_weights(const paacb_ctx* ctx, const LayerGeom& g, const float* w, uint32_t* hi, uint32_t* lo, cudaStream_t st);
 int launch_conv_fwd_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* w, const float* bias,
                        float* y, int64_t batch, int split3, cudaStream_t st);
 
