@@ -155,6 +155,8 @@ int paacb_destroy(paacb_ctx* ctx) {
   }
   if (ctx->wpack_hi != nullptr) cudaFree(ctx->wpack_hi);
   if (ctx->wpack_lo != nullptr) cudaFree(ctx->wpack_lo);
+  if (ctx->wpack_d_hi != nullptr) cudaFree(ctx->wpack_d_hi);
+  if (ctx->wpack_d_lo != nullptr) cudaFree(ctx->wpack_d_lo);
   delete ctx;
   return PAACB_OK;
 }
@@ -230,8 +232,10 @@ int paacb_set_math(paacb_ctx* ctx, int math_mode) {
     const size_t bytes = (size_t)ctx->param_count * sizeof(uint32_t);
     const cudaError_t e1 = cudaMalloc(&ctx->wpack_hi, bytes);
     const cudaError_t e2 = cudaMalloc(&ctx->wpack_lo, bytes);
+    const cudaError_t e3 = cudaMalloc(&ctx->wpack_d_hi, bytes);
+    const cudaError_t e4 = cudaMalloc(&ctx->wpack_d_lo, bytes);
     cudaSetDevice(cur);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
       cudaGetLastError();
       set_error("paacb_set_math: cannot allocate %zu bytes for packed weights", 2 * bytes);
       return PAACB_ECUDA;
@@ -315,7 +319,7 @@ int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint
     // the caller may have changed the parameters since the last call: repack (a few microseconds)
     for (int l = 0; l < ctx->n_layers; ++l) {
       const LayerGeom& g = ctx->layer[l];
-      const int rc = launch_pack_weights(ctx, g, d_params + g.w_off, ctx->wpack_hi + g.w_off, ctx->wpack_lo + g.w_off, st);
+      const int rc = launch_pack_weights(ctx, g, d_params + g.w_off, st);
       if (rc != PAACB_OK) return rc;
     }
   }
@@ -359,15 +363,25 @@ int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d
                             dh, d_grads + ctx->actor_w_off, d_grads + ctx->actor_b_off, d_grads + ctx->critic_w_off,
                             d_grads + ctx->critic_b_off, st);
   if (rc != PAACB_OK) return rc;
+  const bool tc = (ctx->math != PAACB_MATH_FP32) && batch > 0;
+  const int split3 = ctx->math == PAACB_MATH_TF32X3;
+  if (tc) {
+    for (int l = 1; l < L; ++l) {
+      rc = launch_pack_dgrad_weights(ctx, ctx->layer[l], d_params + ctx->layer[l].w_off, st);
+      if (rc != PAACB_OK) return rc;
+    }
+  }
   for (int l = L - 1; l >= 0; --l) {
     const LayerGeom& g = ctx->layer[l];
     const void* x = (l == 0) ? (const void*)d_states : (const void*)(d_fwd_ws + g.in_act_off * batch);
     const float* dz = d_bwd_ws + g.out_act_off * batch;
-    rc = launch_conv_wgrad_simt(ctx, g, x, dz, d_grads + g.w_off, d_grads + g.b_off, batch, st);
+    rc = tc ? launch_conv_wgrad_tc(ctx, g, x, dz, d_grads + g.w_off, d_grads + g.b_off, batch, split3, st) : PAACB_EUNSUPPORTED;
+    if (rc == PAACB_EUNSUPPORTED) rc = launch_conv_wgrad_simt(ctx, g, x, dz, d_grads + g.w_off, d_grads + g.b_off, batch, st);
     if (rc != PAACB_OK) return rc;
     if (l > 0) {
-      rc = launch_conv_dgrad_simt(ctx, g, dz, d_params + g.w_off, (const float*)x, d_bwd_ws + g.in_act_off * batch,
-                                  batch, st);
+      float* dx = d_bwd_ws + g.in_act_off * batch;
+      rc = tc ? launch_conv_dgrad_tc(ctx, g, dz, (const float*)x, dx, batch, split3, st) : PAACB_EUNSUPPORTED;
+      if (rc == PAACB_EUNSUPPORTED) rc = launch_conv_dgrad_simt(ctx, g, dz, d_params + g.w_off, (const float*)x, dx, batch, st);
       if (rc != PAACB_OK) return rc;
     }
   }

@@ -75,6 +75,8 @@ struct paacb_ctx {
   // context-owned workspace of the tcgen05 path: weights prepacked as swizzled tf32 operand images (hi, lo)
   uint32_t* wpack_hi;
   uint32_t* wpack_lo;
+  uint32_t* wpack_d_hi;         // the transposed / per-stride-class images the data-gradient kernels read
+  uint32_t* wpack_d_lo;
 };
 
 namespace paacb {
@@ -148,7 +150,12 @@ int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* m
                         float* ws, cudaStream_t st);
 
 // tcgen05 path (gemm_tc.cu); returns PAACB_EUNSUPPORTED when a layer/mode is not covered
-int launch_pack_weights(const paacb_ctx* ctx, const LayerGeom& g, const float* w, uint32_t* hi, uint32_t* lo, cudaStream_t st);
+int launch_pack_weights(const paacb_ctx* ctx, const LayerGeom& g, const float* w, cudaStream_t st);
+int launch_pack_dgrad_weights(const paacb_ctx* ctx, const LayerGeom& g, const float* w, cudaStream_t st);
+int launch_conv_dgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const float* dz, const float* x_act, float* dx,
+                         int64_t batch, int split3, cudaStream_t st);
+int launch_conv_wgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* dz, float* dw, float* db,
+                         int64_t batch, int split3, cudaStream_t st);
 int launch_conv_fwd_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* w, const float* bias,
                        float* y, int64_t batch, int split3, cudaStream_t st);
 
