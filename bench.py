@@ -46,7 +46,7 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='environments per GPU')
     ap.add_argument('--arch', default='NATURE', choices=['NATURE', 'NIPS'])
-    ap.add_argument('--math', default=os.environ.get('PAACB_BENCH_MATH', 'fp32'), choices=['fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--math', default=os.environ.get('PAACB_BENCH_MATH', 'tf32x3'), choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--frame_pool', type=int, default=8, help='device frame buffers rotated between env steps')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')

@@ -156,3 +156,37 @@ def closed_form_head_grads(logits, v, actions, adv, target, beta):
     dlogits = (LOSS_SCALING / b) * dz
     dv = (LOSS_SCALING * CRITIC_SCALE * 2.0 / b) * (v - target)
     return loss, dlogits, dv
+
+
+def masked_loss_and_grads(params, states_u8, actions, adv, target, beta, arch, num_actions, masks, dtype=torch.float64):
+    """Like loss_and_grads, but every ReLU is replaced by multiplication with a GIVEN 0/1 mask (``masks``: one array
+    per conv layer + the hidden fc, NHWC / [b, F]).  Used to check a backward implementation like-for-like: with the
+    masks taken from the implementation's own forward activations, a pre-activation that rounds to the other side of
+    zero in fp32 cannot flip a ReLU between the two sides of the comparison (TF's ReluGrad uses its own activations too).
+    Returns (grads dict, dz list [conv layers..., hidden fc] as numpy, NHWC)."""
+    names = [n for n, _, _ in param_specs(arch, num_actions)]
+    P = {n: _t(params[n], dtype).clone().requires_grad_(True) for n in names}
+    a = ARCH[arch.upper()]
+    x = torch.as_tensor(np.asarray(states_u8)).to(dtype) * torch.tensor(float(INPUT_SCALE), dtype=dtype)
+    x = x.permute(0, 3, 1, 2)
+    zs = []
+    for li, (name, k, cin, cout, stride) in enumerate(a['convs']):
+        w = P[name + '_weights'].permute(3, 2, 0, 1)
+        z = F.conv2d(x, w, P[name + '_biases'], stride=stride)
+        z.retain_grad()
+        zs.append(z)
+        x = z * torch.as_tensor(np.asarray(masks[li])).to(dtype).permute(0, 3, 1, 2)
+    flat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+    fname = a['fc'][0]
+    zh = flat @ P[fname + '_weights'] + P[fname + '_biases']
+    zh.retain_grad()
+    h = zh * torch.as_tensor(np.asarray(masks[len(a['convs'])])).to(dtype)
+    logits = h @ P['actor_output_weights'] + P['actor_output_biases']
+    pi = torch.softmax(logits, dim=1)
+    v = (h @ P['critic_output_weights'] + P['critic_output_biases']).reshape(-1)
+    onehot = F.one_hot(torch.as_tensor(np.asarray(actions), dtype=torch.long), num_actions).to(dtype)
+    loss = a2c_loss(pi, v, onehot, _t(adv, dtype), _t(target, dtype), float(beta))
+    loss.backward()
+    grads = {n: P[n].grad.numpy() for n in names}
+    dz = [z.grad.permute(0, 2, 3, 1).contiguous().numpy() for z in zs] + [zh.grad.numpy()]
+    return grads, dz, dict(logits=logits.detach().numpy(), v=v.detach().numpy())

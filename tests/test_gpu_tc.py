@@ -33,21 +33,28 @@ def test_forward_tc_vs_oracle(math, arch, A, b):
 
 
 @pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
-@pytest.mark.parametrize('arch,A,b', [('NATURE', 6, 5), ('NATURE', 6, 160), ('NIPS', 4, 97), ('NATURE', 4, 333)])
+@pytest.mark.parametrize('arch,A,b', [('NATURE', 6, 5), ('NATURE', 6, 160), ('NIPS', 4, 97), ('NATURE', 4, 1111)])
 def test_backward_tc_vs_autograd(math, arch, A, b):
+    """Gradients (and every layer's dZ) against fp64 autograd whose ReLU masks are the GPU's own activations
+    (oracle.network.masked_loss_and_grads): like-for-like, immune to a pre-activation rounding across zero."""
     net = G.make_net(arch, A, seed=11, math=math)
     params = network.unflatten_params(net.get_params(), arch, A)
     rng = np.random.RandomState(b + A)
     states = rng.randint(0, 256, (b, 84, 84, 4)).astype(np.uint8)
     acts = rng.randint(0, A, b)
     adv = rng.randn(b).astype(np.float32); tgt = rng.randn(b).astype(np.float32)
-    _, g64, f64 = network.loss_and_grads(params, states, acts, adv, tgt, 0.02, arch, A, dtype=torch.float64)
     fwd = G.forward(net, states)
+    masks = [x > 0 for x in G.layer_acts(net, fwd['ws'], b)]
+    g64, dzs, f64 = network.masked_loss_and_grads(params, states, acts, adv, tgt, 0.02, arch, A, masks)
     _, dz, dv = network.closed_form_head_grads(f64['logits'], f64['v'], acts, adv, tgt, np.float32(0.02))
-    flat, _ = G.backward(net, fwd, dz, dv)
+    flat, bws = G.backward(net, fwd, dz, dv)
     got = network.unflatten_params(flat, arch, A)
     for name, _, _ in network.param_specs(arch, A):
         assert_close(got[name], g64[name], TOL[math], name)
+    off = 0
+    for i, d in enumerate(dzs):
+        assert_close(bws[off:off + d.size].cpu().numpy().reshape(d.shape), d, TOL[math], 'dZ of layer %d' % i)
+        off += d.size
 
 
 def test_engine_update_tf32x3_vs_oracle_composite():
@@ -70,9 +77,12 @@ def test_engine_update_tf32x3_vs_oracle_composite():
     B = T * N
     acts = eng.actions.cpu().numpy().reshape(-1)
     y, adv = update.nstep_returns(rewards, over, eng.values.cpu().numpy(), eng.boot_v.cpu().numpy(), 0.99)
-    loss, grads, _ = network.loss_and_grads(params, states[:T].reshape(B, 84, 84, 4), acts, adv.reshape(-1), y.reshape(-1),
-                                            np.float32(0.02), arch, A)
+    loss, _, _ = network.loss_and_grads(params, states[:T].reshape(B, 84, 84, 4), acts, adv.reshape(-1), y.reshape(-1),
+                                        np.float32(0.02), arch, A)
     assert abs(eng.loss.item() - loss) <= 1e-4 * max(1, abs(loss))
+    masks = [x > 0 for x in G.layer_acts(net, eng.fwd_ws, B)]
+    grads, _, _ = network.masked_loss_and_grads(params, states[:T].reshape(B, 84, 84, 4), acts, adv.reshape(-1), y.reshape(-1),
+                                                np.float32(0.02), arch, A, masks)
     specs = network.param_specs(arch, A)
     clipped, norm = update.clip_by_global_norm([grads[n] for n, _, _ in specs], 3.0)
     assert abs(eng.norm.item() - float(norm)) <= 1e-4 * float(norm)

@@ -40,7 +40,8 @@ def test_returns_loss_grad_vs_oracle(T, N, A):
     assert_close(out['dv'], dvv, 1e-6, 'dv')
 
 
-@pytest.mark.parametrize('arch,A,b', [('NIPS', 4, 3), ('NATURE', 6, 5), ('NATURE', 6, 160), ('NIPS', 18, 97), ('NATURE', 4, 40)])
+@pytest.mark.parametrize('arch,A,b', [('NIPS', 4, 3), ('NATURE', 6, 5), ('NATURE', 6, 160), ('NIPS', 18, 97), ('NATURE', 4, 40),
+                                      ('NATURE', 6, 1111)])
 def test_backward_vs_autograd(arch, A, b):
     net = G.make_net(arch, A, seed=11)
     params = network.unflatten_params(net.get_params(), arch, A)
@@ -48,16 +49,19 @@ def test_backward_vs_autograd(arch, A, b):
     states = rng.randint(0, 256, (b, 84, 84, 4)).astype(np.uint8)
     acts = rng.randint(0, A, b)
     adv = rng.randn(b).astype(np.float32); tgt = rng.randn(b).astype(np.float32)
-    loss, grads, fwd_ref = network.loss_and_grads(params, states, acts, adv, tgt, np.float32(0.02), arch, A)
-    _, g64, _ = network.loss_and_grads(params, states, acts, adv, tgt, 0.02, arch, A, dtype=torch.float64)
     fwd = G.forward(net, states)
-    _, dz, dv = network.closed_form_head_grads(fwd_ref['logits'], fwd_ref['v'], acts, adv, tgt, np.float32(0.02))
-    flat, _ = G.backward(net, fwd, dz, dv)
+    # fp64 autograd with the GPU's own ReLU masks (see oracle.network.masked_loss_and_grads)
+    masks = [x > 0 for x in G.layer_acts(net, fwd['ws'], b)]
+    g64, dzs, f64 = network.masked_loss_and_grads(params, states, acts, adv, tgt, 0.02, arch, A, masks)
+    _, dz, dv = network.closed_form_head_grads(f64['logits'], f64['v'], acts, adv, tgt, np.float32(0.02))
+    flat, bws = G.backward(net, fwd, dz, dv)
     got = network.unflatten_params(flat, arch, A)
     for name, _, _ in network.param_specs(arch, A):
-        e_gpu = rel_err(got[name], g64[name])
-        e_cpu = rel_err(grads[name], g64[name])
-        assert e_gpu <= max(1e-4, 4 * e_cpu), '%s: gpu %.2e vs torch-fp32 %.2e (both against fp64)' % (name, e_gpu, e_cpu)
+        assert_close(got[name], g64[name], 1e-4, name)
+    off = 0
+    for i, d in enumerate(dzs):
+        assert_close(bws[off:off + d.size].cpu().numpy().reshape(d.shape), d, 1e-4, 'dZ of layer %d' % i)
+        off += d.size
 
 
 @pytest.mark.parametrize('clip_type,gscale', [(_lib.CLIP_GLOBAL, 1.0), (_lib.CLIP_GLOBAL, 0.125), (_lib.CLIP_IGNORE, 1.0)])
