@@ -101,6 +101,10 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
   memset(c, 0, sizeof(*c));
   c->arch = arch; c->num_actions = num_actions; c->device = device; c->math = PAACB_MATH_FP32;
   c->num_sms = prop.multiProcessorCount;
+  {
+    const char* knob = getenv("PAACB_TC_A");
+    c->tc_a_tmem = (knob != nullptr && strcmp(knob, "smem") == 0) ? 0 : 1;
+  }
   int h = PAACB_OBS, w = PAACB_OBS, ch = PAACB_STACK;
   int64_t poff = 0, aoff = 0;
   if (arch == PAACB_ARCH_NIPS) {                       // networks.py:145-149

@@ -8,10 +8,12 @@
 //   warps 0-7   A producers: two groups of 128 threads alternate K-blocks.  Thread r of a group owns tile row r.  It
 //               gathers the 32 consecutive k of its row (128 contiguous bytes of NHWC fp32, or 32 bytes of the uint8
 //               state), keeps PF K-blocks in flight in registers, converts to tf32 (round-to-nearest; in TF32X3 mode
-//               also the residual lo = rna(a - hi)) and stores 16-byte chunks into the 128B-swizzled K-major operand
-//               tile in shared memory.  im2col is never materialised.
+//               also the residual lo = rna(a - hi)) and hands the row to the tensor core.  im2col is never materialised.
+//               A_TMEM = true : the row goes straight into TENSOR MEMORY with tcgen05.st (lane = row, 32 columns = the
+//                               32 k) and the MMA reads A from TMEM -- no shared-memory traffic for A at all;
+//               A_TMEM = false: 16-byte chunks into the 128B-swizzled K-major operand tile in shared memory.
 //   warp  8     lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = BN, K = 8) into a TMEM accumulator;
-//               tcgen05.commit releases the smem stage / publishes the accumulator.
+//               tcgen05.commit releases the stage / publishes the accumulator.
 //   warps 9-12  epilogue: tcgen05.ld the accumulator rows (32 lanes per warp), then scale + bias + ReLU (forward) or
 //               ReLU-mask + scatter to the input pixel (dgrad), 16-byte stores.
 // B (weights) is prepacked once per call into the exact swizzled shared-memory image of every (class, n-tile, k-block),
@@ -46,8 +48,8 @@ __global__ void pack_fwd_weights_kernel(const float* __restrict__ w, int K, int 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float v = __ldg(w + (int64_t)(k4 * 4 + e) * N + n);
-      h[e] = f32_to_tf32_rna(v);
-      l[e] = f32_to_tf32_rna(v - __uint_as_float(h[e]));
+      h[e] = tf32_rna(v);
+      l[e] = tf32_rna(v - __uint_as_float(h[e]));
     }
     const int64_t dst = (((int64_t)nt * KB + kb) * BN + row) * 32 + ((chunk ^ (row & 7)) << 2);
     *reinterpret_cast<uint4*>(hi + dst) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -79,8 +81,8 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, LayerGeom
     uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      h[e] = f32_to_tf32_rna(f[e]);
-      l[e] = f32_to_tf32_rna(f[e] - __uint_as_float(h[e]));
+      h[e] = tf32_rna(f[e]);
+      l[e] = tf32_rna(f[e] - __uint_as_float(h[e]));
     }
     const int kb = k4 >> 3, chunk = k4 & 7;
     const int nt = c / BN, row = c - nt * BN;
@@ -96,6 +98,7 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, LayerGeom
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcProducerThreads = 256;     // two groups of 128
 constexpr int kTcThreads = kTcProducerThreads + 32 + 128;
+constexpr int kMaxKB = 128;                 // K-blocks per tile the per-K-block table can hold
 
 struct TcParams {
   const void* x;          // fwd: layer input (uint8 states or fp32 NHWC); dgrad: dZ of this layer [b, OH, OW, Cout]
@@ -105,37 +108,41 @@ struct TcParams {
   const float* xact;      // dgrad: activation feeding this layer (ReLU mask) or nullptr
   float* y;               // fwd: output [M, N]; dgrad: dX [b, H, W, C]
   LayerGeom g;
-  int64_t M;              // GEMM rows (per class)
-  int64_t m_tiles;        // per class
+  uint32_t M;             // GEMM rows (per class)
+  uint32_t m_tiles;       // per class
   int n_tiles;
   int classes;            // dgrad: stride^2
   int kblocks;
   int Hq, Wq, I;          // dgrad: class grid and taps per row
-  int Ngemm;              // GEMM N: Cout (fwd) or C (dgrad)
   float in_scale;
   int relu;
 };
 
-template <int BN, int MODE, bool SPLIT>
+template <int BN, int MODE, bool SPLIT, bool A_TMEM>
 struct TcCfg {
   static constexpr bool U8 = (MODE == TC_FWD_U8);
-  static constexpr int A_BYTES = 128 * 128;
   static constexpr bool A_LO = SPLIT && !U8;
+  static constexpr int A_BYTES = A_TMEM ? 0 : 128 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES * (A_LO ? 2 : 1) + B_BYTES * (SPLIT ? 2 : 1);
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int ACOLS = A_LO ? 64 : 32;                                  // TMEM columns per A stage
+  static constexpr int S_SMEM = 200 * 1024 / STAGE_BYTES;
+  static constexpr int S_TMEM = A_TMEM ? (512 - 2 * BN) / ACOLS : 8;
+  static constexpr int STAGES = (S_SMEM < S_TMEM ? S_SMEM : S_TMEM) > 8 ? 8 : (S_SMEM < S_TMEM ? S_SMEM : S_TMEM);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-  static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int TMEM_COLS = A_TMEM ? 512 : ((2 * BN) < 32 ? 32 : (2 * BN));
   static constexpr int NV = U8 ? 2 : 8;       // 16-byte loads per row per K-block
   static constexpr int PF = U8 ? 4 : 2;       // K-blocks in flight per producer thread
+  static_assert(STAGES >= 2, "need at least two pipeline stages");
 };
 
-template <int BN, int MODE, bool SPLIT>
+template <int BN, int MODE, bool SPLIT, bool A_TMEM>
 __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams p) {
-  using Cfg = TcCfg<BN, MODE, SPLIT>;
+  using Cfg = TcCfg<BN, MODE, SPLIT, A_TMEM>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NV = Cfg::NV, PF = Cfg::PF;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ int kb_tab[kMaxKB];                // per-K-block source offsets (no division in the hot loop)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]  producers (128 + 1) -> MMA
@@ -147,9 +154,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const LayerGeom& g = p.g;
-  const int64_t tiles_per_class = p.m_tiles * p.n_tiles;
-  const int64_t total_tiles = tiles_per_class * p.classes;
-  const int64_t my_tiles = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA
+  const uint32_t tiles_per_class = p.m_tiles * (uint32_t)p.n_tiles;
+  const uint32_t total_tiles = tiles_per_class * (uint32_t)p.classes;
+  const int my_tiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
   const int KB = p.kblocks;
 
   if (tid == 0) {
@@ -163,146 +170,205 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
     }
     fence_barrier_init();
   }
+  for (int kb = tid; kb < KB; kb += kTcThreads) {
+    const int k0 = kb * 32;
+    if constexpr (MODE == TC_DGRAD) {
+      const int tap = k0 / g.N, co0 = k0 - tap * g.N;
+      const int tj = tap / p.I, ti = tap - tj * p.I;
+      kb_tab[kb] = (tj << 24) | (ti << 16) | co0;
+    } else {
+      const int SC = g.S * g.C;
+      const int kh = k0 / SC, off = k0 - kh * SC;
+      kb_tab[kb] = kh * g.W * g.C + off;
+    }
+  }
   if (warp == 8) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kAcol0 = 2 * BN;           // first TMEM column of the A stages (A_TMEM)
 
   if (warp < 8) {
     // =========================== A producers (+ B bulk copy) ===========================
     const int grp = warp >> 2;                 // owns iterations it with (it & 1) == grp
     const int r = tid & 127;                   // tile row
-    const int SC = g.S * g.C, WC = g.W * g.C, ohw = g.OH * g.OW;
-    const int64_t total_it = my_tiles * KB;
+    const uint32_t ohw = (uint32_t)(g.OH * g.OW);
+    const int total_it = my_tiles * KB;
 
-    // per-tile row state (refreshed when the load stream enters a new tile)
-    int64_t cached_tile = -1;
+    // load-stream position (advances by 2 K-blocks per owned iteration) and per-tile row state
+    int ld_tl = 0, ld_kb = grp;
+    while (ld_kb >= KB) { ld_kb -= KB; ++ld_tl; }
+    int cached_tile = -1;
     int64_t rowbase = 0;       // fwd: element offset of (sample, oh*stride, ow*stride, 0)
-    int64_t smp = 0;           // dgrad
+    uint32_t smp = 0;          // dgrad
     int hq = 0, wq = 0;        // dgrad
     bool row_ok = false;
-    int64_t img_base = 0;      // (class * n_tiles + n_tile) * KB
+    int img_base = 0;          // (class * n_tiles + n_tile) * KB
 
     uint4 buf[PF][NV];
-    int64_t img_of[PF];
+    int img_of[PF];
 
-    auto issue = [&](int64_t it, uint4 (&b)[NV], int64_t& img) {
-      const int64_t tl = it / KB;
-      const int kb = (int)(it - tl * KB);
-      if (tl != cached_tile) {
-        cached_tile = tl;
-        const int64_t t = blockIdx.x + tl * gridDim.x;
-        const int64_t cls = t / tiles_per_class;
-        const int64_t tc = t - cls * tiles_per_class;
-        const int64_t mt = tc / p.n_tiles;
-        const int nt = (int)(tc - mt * p.n_tiles);
-        img_base = (cls * p.n_tiles + nt) * KB;
-        const int64_t m = mt * 128 + r;
+    auto issue = [&](uint4 (&b)[NV], int& img) {
+      if (ld_tl != cached_tile) {
+        cached_tile = ld_tl;
+        const uint32_t t = blockIdx.x + (uint32_t)ld_tl * gridDim.x;
+        const uint32_t cls = t / tiles_per_class;
+        const uint32_t tc = t - cls * tiles_per_class;
+        const uint32_t mt = tc / (uint32_t)p.n_tiles;
+        const int nt = (int)(tc - mt * (uint32_t)p.n_tiles);
+        img_base = ((int)cls * p.n_tiles + nt) * KB;
+        const uint32_t m = mt * 128u + (uint32_t)r;
         row_ok = m < p.M;
         if (row_ok) {
           if constexpr (MODE == TC_DGRAD) {
-            const int hw = p.Hq * p.Wq;
+            const uint32_t hw = (uint32_t)(p.Hq * p.Wq);
             smp = m / hw;
-            const int rem = (int)(m - smp * hw);
-            hq = rem / p.Wq;
-            wq = rem - hq * p.Wq;
+            const uint32_t rem = m - smp * hw;
+            hq = (int)(rem / (uint32_t)p.Wq);
+            wq = (int)(rem - (uint32_t)hq * (uint32_t)p.Wq);
           } else {
-            const int64_t sm = m / ohw;
-            const int rem = (int)(m - sm * ohw);
-            const int oh = rem / g.OW, ow = rem - oh * g.OW;
-            rowbase = ((sm * g.H + (int64_t)oh * g.stride) * g.W + (int64_t)ow * g.stride) * g.C;
+            const uint32_t sm = m / ohw;
+            const uint32_t rem = m - sm * ohw;
+            const uint32_t oh = rem / (uint32_t)g.OW, ow = rem - oh * (uint32_t)g.OW;
+            rowbase = (((int64_t)sm * g.H + (int64_t)oh * g.stride) * g.W + (int64_t)ow * g.stride) * g.C;
           }
         }
       }
-      img = img_base + kb;
-      const int k0 = kb * 32;
+      img = img_base + ld_kb;
+      const int tab = kb_tab[ld_kb];
 #pragma unroll
       for (int c = 0; c < NV; ++c) b[c] = make_uint4(0u, 0u, 0u, 0u);
       if constexpr (MODE == TC_FWD_U8) {
         if (row_ok) {
-          const int kh = k0 / SC, off = k0 - kh * SC;
-          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + rowbase + (int64_t)kh * WC + off);
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + rowbase + tab);
           b[0] = __ldg(src);
           b[1] = __ldg(src + 1);
         }
       } else if constexpr (MODE == TC_FWD_F32) {
         if (row_ok) {
-          const int kh = k0 / SC, off = k0 - kh * SC;
-          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) + rowbase + (int64_t)kh * WC + off);
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) + rowbase + tab);
 #pragma unroll
           for (int c = 0; c < 8; ++c) b[c] = __ldg(src + c);
         }
       } else {
         // dgrad: k = (tj, ti, co); the row reads dZ[smp, hq - tj, wq - ti, co0 .. co0 + 32)
-        const int tap = k0 / g.N, co0 = k0 - tap * g.N;
-        const int tj = tap / p.I, ti = tap - tj * p.I;
-        const int oh = hq - tj, ow = wq - ti;
+        const int oh = hq - (tab >> 24), ow = wq - ((tab >> 16) & 0xff), co0 = tab & 0xffff;
         if (row_ok && oh >= 0 && oh < g.OH && ow >= 0 && ow < g.OW) {
           const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) +
-                                                            ((smp * g.OH + oh) * g.OW + ow) * (int64_t)g.N + co0);
+                                                            (((int64_t)smp * g.OH + oh) * g.OW + ow) * (int64_t)g.N + co0);
 #pragma unroll
           for (int c = 0; c < 8; ++c) b[c] = __ldg(src + c);
         }
       }
+      ld_kb += 2;
+      while (ld_kb >= KB) { ld_kb -= KB; ++ld_tl; }
     };
 
-    auto process = [&](int64_t it, const uint4 (&b)[NV], int64_t img) {
-      const int stage = (int)(it % STAGES);
-      const uint32_t phase = (uint32_t)((it / STAGES) & 1);
-      mbar_wait(&empty_bar[stage], phase ^ 1u);
-      uint8_t* st = smem + (size_t)stage * Cfg::STAGE_BYTES;
-      uint8_t* a_hi = st;
-      uint8_t* a_lo = st + Cfg::A_BYTES;
+    int pstage = grp % STAGES;
+    uint32_t pphase = 0;
+
+    auto process = [&](const uint4 (&b)[NV], int img) {
+      mbar_wait(&empty_bar[pstage], pphase ^ 1u);
+      uint8_t* st = smem + (size_t)pstage * Cfg::STAGE_BYTES;
       uint8_t* b_hi = st + Cfg::A_BYTES * (Cfg::A_LO ? 2 : 1);
       if (r == 0) {
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES * (SPLIT ? 2 : 1));
-        bulk_g2s(b_hi, p.b_hi + img * (BN * 32), Cfg::B_BYTES, &full_bar[stage]);
-        if constexpr (SPLIT) bulk_g2s(b_hi + Cfg::B_BYTES, p.b_lo + img * (BN * 32), Cfg::B_BYTES, &full_bar[stage]);
+        mbar_arrive_expect_tx(&full_bar[pstage], Cfg::B_BYTES * (SPLIT ? 2 : 1));
+        bulk_g2s(b_hi, p.b_hi + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
+        if constexpr (SPLIT) bulk_g2s(b_hi + Cfg::B_BYTES, p.b_lo + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
       }
-      if constexpr (Cfg::U8) {
-        const uint32_t wds[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+      if constexpr (A_TMEM) {
+        // this thread's row of the A operand goes straight into tensor memory: lane = row, 32 columns = 32 k
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAcol0 + (uint32_t)(pstage * Cfg::ACOLS);
+        uint32_t hi[32];
+        if constexpr (Cfg::U8) {
+          const uint32_t wds[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t wv = wds[c];
-          uint4 o;      // small integers are exact in tf32: the fp32 bit pattern is the tf32 operand
-          o.x = __float_as_uint((float)(wv & 0xffu));
-          o.y = __float_as_uint((float)((wv >> 8) & 0xffu));
-          o.z = __float_as_uint((float)((wv >> 16) & 0xffu));
-          o.w = __float_as_uint((float)(wv >> 24));
-          *reinterpret_cast<uint4*>(a_hi + sw128_off((uint32_t)r, (uint32_t)c)) = o;
+          for (int c = 0; c < 8; ++c) {       // small integers are exact in tf32
+            hi[c * 4 + 0] = __float_as_uint(u8_to_f32(wds[c], 0));
+            hi[c * 4 + 1] = __float_as_uint(u8_to_f32(wds[c], 1));
+            hi[c * 4 + 2] = __float_as_uint(u8_to_f32(wds[c], 2));
+            hi[c * 4 + 3] = __float_as_uint(u8_to_f32(wds[c], 3));
+          }
+          tmem_st32(taddr, hi);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            hi[c * 4 + 0] = tf32_rna(__uint_as_float(b[c].x));
+            hi[c * 4 + 1] = tf32_rna(__uint_as_float(b[c].y));
+            hi[c * 4 + 2] = tf32_rna(__uint_as_float(b[c].z));
+            hi[c * 4 + 3] = tf32_rna(__uint_as_float(b[c].w));
+          }
+          tmem_st32(taddr, hi);
+          if constexpr (Cfg::A_LO) {
+            uint32_t lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              lo[c * 4 + 0] = tf32_rna(__uint_as_float(b[c].x) - __uint_as_float(hi[c * 4 + 0]));
+              lo[c * 4 + 1] = tf32_rna(__uint_as_float(b[c].y) - __uint_as_float(hi[c * 4 + 1]));
+              lo[c * 4 + 2] = tf32_rna(__uint_as_float(b[c].z) - __uint_as_float(hi[c * 4 + 2]));
+              lo[c * 4 + 3] = tf32_rna(__uint_as_float(b[c].w) - __uint_as_float(hi[c * 4 + 3]));
+            }
+            tmem_st32(taddr + 32u, lo);
+          }
         }
       } else {
+        uint8_t* a_hi = st;
+        uint8_t* a_lo = st + Cfg::A_BYTES;
+        if constexpr (Cfg::U8) {
+          const uint32_t wds[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float f0 = __uint_as_float(b[c].x), f1 = __uint_as_float(b[c].y);
-          const float f2 = __uint_as_float(b[c].z), f3 = __uint_as_float(b[c].w);
-          uint4 h;
-          h.x = f32_to_tf32_rna(f0); h.y = f32_to_tf32_rna(f1); h.z = f32_to_tf32_rna(f2); h.w = f32_to_tf32_rna(f3);
-          *reinterpret_cast<uint4*>(a_hi + sw128_off((uint32_t)r, (uint32_t)c)) = h;
-          if constexpr (Cfg::A_LO) {
-            uint4 l;
-            l.x = f32_to_tf32_rna(f0 - __uint_as_float(h.x)); l.y = f32_to_tf32_rna(f1 - __uint_as_float(h.y));
-            l.z = f32_to_tf32_rna(f2 - __uint_as_float(h.z)); l.w = f32_to_tf32_rna(f3 - __uint_as_float(h.w));
-            *reinterpret_cast<uint4*>(a_lo + sw128_off((uint32_t)r, (uint32_t)c)) = l;
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t wv = wds[c];
+            uint4 o;
+            o.x = __float_as_uint(u8_to_f32(wv, 0));
+            o.y = __float_as_uint(u8_to_f32(wv, 1));
+            o.z = __float_as_uint(u8_to_f32(wv, 2));
+            o.w = __float_as_uint(u8_to_f32(wv, 3));
+            *reinterpret_cast<uint4*>(a_hi + sw128_off((uint32_t)r, (uint32_t)c)) = o;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float f0 = __uint_as_float(b[c].x), f1 = __uint_as_float(b[c].y);
+            const float f2 = __uint_as_float(b[c].z), f3 = __uint_as_float(b[c].w);
+            uint4 h;
+            h.x = tf32_rna(f0); h.y = tf32_rna(f1); h.z = tf32_rna(f2); h.w = tf32_rna(f3);
+            *reinterpret_cast<uint4*>(a_hi + sw128_off((uint32_t)r, (uint32_t)c)) = h;
+            if constexpr (Cfg::A_LO) {
+              uint4 l;
+              l.x = tf32_rna(f0 - __uint_as_float(h.x)); l.y = tf32_rna(f1 - __uint_as_float(h.y));
+              l.z = tf32_rna(f2 - __uint_as_float(h.z)); l.w = tf32_rna(f3 - __uint_as_float(h.w));
+              *reinterpret_cast<uint4*>(a_lo + sw128_off((uint32_t)r, (uint32_t)c)) = l;
+            }
           }
         }
       }
     };
 
+    auto publish = [&]() {
+      if constexpr (A_TMEM) {
+        tmem_st_wait();                        // tcgen05.st complete ...
+        tc_fence_before();                     // ... and ordered before the arrive the MMA thread observes
+      } else {
+        fence_proxy_async();                   // generic-proxy smem stores -> visible to the tensor core (async proxy)
+      }
+      mbar_arrive(&full_bar[pstage]);
+      pstage += 2;
+      if (pstage >= STAGES) { pstage -= STAGES; pphase ^= 1u; }
+    };
+
 #pragma unroll
     for (int u = 0; u < PF; ++u)
-      if (grp + 2 * u < total_it) issue(grp + 2 * u, buf[u], img_of[u]);
-    for (int64_t base = grp; base < total_it; base += 2 * PF) {
+      if (grp + 2 * u < total_it) issue(buf[u], img_of[u]);
+    for (int base = grp; base < total_it; base += 2 * PF) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
-        const int64_t it = base + 2 * u;
+        const int it = base + 2 * u;
         if (it < total_it) {
-          process(it, buf[u], img_of[u]);
-          const int stage = (int)(it % STAGES);
-          if (it + 2 * PF < total_it) issue(it + 2 * PF, buf[u], img_of[u]);   // refill while the MMA consumes
-          fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
-          mbar_arrive(&full_bar[stage]);
+          process(buf[u], img_of[u]);
+          if (it + 2 * PF < total_it) issue(buf[u], img_of[u]);   // refill while the MMA consumes
+          publish();
         }
       }
     }
@@ -310,36 +376,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
     // =========================== MMA issuer ===========================
     if ((tid & 31) == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(BN);
-      int64_t it = 0;
-      for (int64_t tl = 0; tl < my_tiles; ++tl) {
-        const int acc = (int)(tl & 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int acc = tl & 1;
         const uint32_t acc_phase = (uint32_t)((tl >> 1) & 1);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int stage = (int)(it % STAGES);
-          const uint32_t phase = (uint32_t)((it / STAGES) & 1);
+        for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
-          const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES;
           const uint32_t b_hi = st + Cfg::A_BYTES * (Cfg::A_LO ? 2 : 1), b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {     // K = 8 tf32 = 32 bytes per instruction
+          for (int ks = 0; ks < 4; ++ks) {     // K = 8 tf32 per instruction: 32 bytes of smem / 8 TMEM columns
             const uint32_t ko = (uint32_t)ks * 32u;
             uint32_t accum = (kb > 0 || ks > 0) ? 1u : 0u;
-            if constexpr (SPLIT) {
-              if constexpr (Cfg::A_LO) {
-                umma_tf32(d_tmem, make_sw128_desc(a_lo + ko), make_sw128_desc(b_hi + ko), idesc, accum);
+            if constexpr (A_TMEM) {
+              const uint32_t a_hi = tmem_base + kAcol0 + (uint32_t)(stage * Cfg::ACOLS) + (uint32_t)ks * 8u;
+              if constexpr (SPLIT) {
+                if constexpr (Cfg::A_LO) {
+                  umma_tf32_ts(d_tmem, a_hi + 32u, make_sw128_desc(b_hi + ko), idesc, accum);
+                  accum = 1u;
+                }
+                umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_lo + ko), idesc, accum);
                 accum = 1u;
               }
-              umma_tf32(d_tmem, make_sw128_desc(a_hi + ko), make_sw128_desc(b_lo + ko), idesc, accum);
-              accum = 1u;
+              umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_hi + ko), idesc, accum);
+            } else {
+              const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES;
+              if constexpr (SPLIT) {
+                if constexpr (Cfg::A_LO) {
+                  umma_tf32(d_tmem, make_sw128_desc(a_lo + ko), make_sw128_desc(b_hi + ko), idesc, accum);
+                  accum = 1u;
+                }
+                umma_tf32(d_tmem, make_sw128_desc(a_hi + ko), make_sw128_desc(b_lo + ko), idesc, accum);
+                accum = 1u;
+              }
+              umma_tf32(d_tmem, make_sw128_desc(a_hi + ko), make_sw128_desc(b_hi + ko), idesc, accum);
             }
-            umma_tf32(d_tmem, make_sw128_desc(a_hi + ko), make_sw128_desc(b_hi + ko), idesc, accum);
           }
-          umma_commit(&empty_bar[stage]);      // smem stage reusable once these MMAs retire
+          umma_commit(&empty_bar[stage]);      // stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tfull_bar[acc]);          // accumulator complete
       }
@@ -348,31 +427,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
     // =========================== epilogue ===========================
     const int ew = warp & 3;                   // TMEM lane quarter this warp may access
     const int lane = tid & 31;
-    for (int64_t tl = 0; tl < my_tiles; ++tl) {
-      const int acc = (int)(tl & 1);
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int acc = tl & 1;
       const uint32_t acc_phase = (uint32_t)((tl >> 1) & 1);
-      const int64_t t = blockIdx.x + tl * gridDim.x;
-      const int64_t cls = t / tiles_per_class;
-      const int64_t tc = t - cls * tiles_per_class;
-      const int64_t mt = tc / p.n_tiles;
-      const int nt = (int)(tc - mt * p.n_tiles);
-      const int64_t m = mt * 128 + ew * 32 + lane;
+      const uint32_t t = blockIdx.x + (uint32_t)tl * gridDim.x;
+      const uint32_t cls = t / tiles_per_class;
+      const uint32_t tc = t - cls * tiles_per_class;
+      const uint32_t mt = tc / (uint32_t)p.n_tiles;
+      const int nt = (int)(tc - mt * (uint32_t)p.n_tiles);
+      const uint32_t m = mt * 128u + (uint32_t)(ew * 32 + lane);
       bool ok = m < p.M;
       int64_t out_base = 0;
       if constexpr (MODE == TC_DGRAD) {
         if (ok) {
           const int s = g.stride;
           const int ph = (int)cls / s, pw = (int)cls - ph * s;
-          const int hw = p.Hq * p.Wq;
-          const int64_t sm = m / hw;
-          const int rem = (int)(m - sm * hw);
-          const int qh = rem / p.Wq, qw = rem - qh * p.Wq;
+          const uint32_t hw = (uint32_t)(p.Hq * p.Wq);
+          const uint32_t sm = m / hw;
+          const uint32_t rem = m - sm * hw;
+          const int qh = (int)(rem / (uint32_t)p.Wq), qw = (int)(rem - (uint32_t)qh * (uint32_t)p.Wq);
           const int h = ph + s * qh, wv = pw + s * qw;
           ok = (h < g.H) && (wv < g.W);
-          out_base = ((sm * g.H + h) * g.W + wv) * (int64_t)g.C + nt * BN;
+          out_base = (((int64_t)sm * g.H + h) * g.W + wv) * (int64_t)g.C + nt * BN;
         }
       } else {
-        out_base = m * g.N + nt * BN;
+        out_base = (int64_t)m * g.N + nt * BN;
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -428,24 +507,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-template <int BN, int MODE, bool SPLIT>
-static int launch_tc_inst(const paacb_ctx* ctx, const TcParams& p, int slot, cudaStream_t st) {
-  using Cfg = TcCfg<BN, MODE, SPLIT>;
+template <int BN, int MODE, bool SPLIT, bool A_TMEM>
+static int launch_tc_inst2(const paacb_ctx* ctx, const TcParams& p, int slot, cudaStream_t st) {
+  using Cfg = TcCfg<BN, MODE, SPLIT, A_TMEM>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_tc_kernel<BN, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(igemm_tc_kernel<BN, MODE, SPLIT, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess) {
       set_error("igemm_tc: cannot set %d bytes of dynamic shared memory", Cfg::SMEM_BYTES);
       return PAACB_ECUDA;
     }
     attr_set = true;
   }
-  const int64_t tiles = p.m_tiles * p.n_tiles * p.classes;
-  const unsigned grid = (unsigned)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
+  const uint32_t tiles = p.m_tiles * (uint32_t)p.n_tiles * (uint32_t)p.classes;
+  const unsigned grid = tiles < (uint32_t)ctx->num_sms ? tiles : (unsigned)ctx->num_sms;
   PAACB_LAUNCH_BEGIN(ctx, slot, st);
-  igemm_tc_kernel<BN, MODE, SPLIT><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(p);
+  igemm_tc_kernel<BN, MODE, SPLIT, A_TMEM><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(p);
   PAACB_LAUNCH_END(ctx, slot, st);
   return PAACB_OK;
+}
+
+template <int BN, int MODE>
+static int launch_tc_inst(const paacb_ctx* ctx, const TcParams& p, int slot, int split3, cudaStream_t st) {
+  if (ctx->tc_a_tmem) {
+    return split3 ? launch_tc_inst2<BN, MODE, true, true>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, true>(ctx, p, slot, st);
+  }
+  return split3 ? launch_tc_inst2<BN, MODE, true, false>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, false>(ctx, p, slot, st);
 }
 
 static int pick_bn(int n) { return (n % 128 == 0) ? 128 : ((n % 64 == 0) ? 64 : ((n % 32 == 0) ? 32 : 0)); }
@@ -481,7 +568,11 @@ int launch_conv_fwd_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, 
                        float* y, int64_t batch, int split3, cudaStream_t st) {
   (void)w;
   const int bn = pick_bn(g.N);
-  if ((g.S * g.C) % 32 != 0 || g.K % 32 != 0 || bn == 0 || ctx->wpack_hi == nullptr) return PAACB_EUNSUPPORTED;
+  const int64_t M = batch * g.OH * g.OW;
+  if ((g.S * g.C) % 32 != 0 || g.K % 32 != 0 || g.K / 32 > kMaxKB || bn == 0 || ctx->wpack_hi == nullptr ||
+      M >= (1LL << 31) - 256)
+    return PAACB_EUNSUPPORTED;
+  if (M == 0) return PAACB_OK;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.x = x;
@@ -490,27 +581,22 @@ int launch_conv_fwd_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, 
   p.bias = bias;
   p.y = y;
   p.g = g;
-  p.M = batch * g.OH * g.OW;
-  if (p.M == 0) return PAACB_OK;
-  p.m_tiles = (p.M + 127) / 128;
+  p.M = (uint32_t)M;
+  p.m_tiles = (uint32_t)((M + 127) / 128);
   p.n_tiles = g.N / bn;
   p.classes = 1;
   p.kblocks = g.K / 32;
-  p.Ngemm = g.N;
   p.in_scale = g.in_u8 ? 0.003921568859368563f : 1.0f;
   p.relu = 1;
   const int slot = K_FWD0 + g.index;
-#define TC(BN_, MODE_) \
-  (split3 ? launch_tc_inst<BN_, MODE_, true>(ctx, p, slot, st) : launch_tc_inst<BN_, MODE_, false>(ctx, p, slot, st))
   if (g.in_u8) {
-    if (bn == 32) return TC(32, TC_FWD_U8);
-    if (bn == 64) return TC(64, TC_FWD_U8);
+    if (bn == 32) return launch_tc_inst<32, TC_FWD_U8>(ctx, p, slot, split3, st);
+    if (bn == 64) return launch_tc_inst<64, TC_FWD_U8>(ctx, p, slot, split3, st);
     return PAACB_EUNSUPPORTED;
   }
-  if (bn == 32) return TC(32, TC_FWD_F32);
-  if (bn == 64) return TC(64, TC_FWD_F32);
-  return TC(128, TC_FWD_F32);
-#undef TC
+  if (bn == 32) return launch_tc_inst<32, TC_FWD_F32>(ctx, p, slot, split3, st);
+  if (bn == 64) return launch_tc_inst<64, TC_FWD_F32>(ctx, p, slot, split3, st);
+  return launch_tc_inst<128, TC_FWD_F32>(ctx, p, slot, split3, st);
 }
 
 int launch_conv_dgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const float* dz, const float* x_act, float* dx,
@@ -518,8 +604,12 @@ int launch_conv_dgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const float* 
   const int s = g.stride;
   const int J = (g.R + s - 1) / s, I = (g.S + s - 1) / s;
   const int bn = pick_bn(g.C);
-  if (bn == 0 || g.N % 32 != 0 || g.in_u8 || ctx->wpack_d_hi == nullptr || (int64_t)s * s * J * I != (int64_t)g.R * g.S)
+  const int Hq = (g.H + s - 1) / s, Wq = (g.W + s - 1) / s;
+  const int64_t M = batch * Hq * Wq;
+  if (bn == 0 || g.N % 32 != 0 || g.N > 65535 || g.in_u8 || ctx->wpack_d_hi == nullptr || J * I * g.N / 32 > kMaxKB ||
+      (int64_t)s * s * J * I != (int64_t)g.R * g.S || M >= (1LL << 31) - 256 || J > 127 || I > 127)
     return PAACB_EUNSUPPORTED;
+  if (M == 0) return PAACB_OK;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.x = dz;
@@ -528,24 +618,19 @@ int launch_conv_dgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const float* 
   p.xact = x_act;
   p.y = dx;
   p.g = g;
-  p.Hq = (g.H + s - 1) / s;
-  p.Wq = (g.W + s - 1) / s;
+  p.Hq = Hq;
+  p.Wq = Wq;
   p.I = I;
-  p.M = batch * p.Hq * p.Wq;
-  if (p.M == 0) return PAACB_OK;
-  p.m_tiles = (p.M + 127) / 128;
+  p.M = (uint32_t)M;
+  p.m_tiles = (uint32_t)((M + 127) / 128);
   p.n_tiles = g.C / bn;
   p.classes = s * s;
   p.kblocks = J * I * g.N / 32;
-  p.Ngemm = g.C;
   p.in_scale = 1.0f;
   const int slot = K_DGRAD0 + g.index;
-#define TC(BN_) \
-  (split3 ? launch_tc_inst<BN_, TC_DGRAD, true>(ctx, p, slot, st) : launch_tc_inst<BN_, TC_DGRAD, false>(ctx, p, slot, st))
-  if (bn == 32) return TC(32);
-  if (bn == 64) return TC(64);
-  return TC(128);
-#undef TC
+  if (bn == 32) return launch_tc_inst<32, TC_DGRAD>(ctx, p, slot, split3, st);
+  if (bn == 64) return launch_tc_inst<64, TC_DGRAD>(ctx, p, slot, split3, st);
+  return launch_tc_inst<128, TC_DGRAD>(ctx, p, slot, split3, st);
 }
 
 }  // namespace paacb

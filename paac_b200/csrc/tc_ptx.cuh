@@ -64,6 +64,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand read from tensor memory (128 lanes = rows, one tf32 per 32-bit column, 8 columns per MMA).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrive once all MMAs previously issued by this thread have retired (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -82,12 +91,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// registers -> TMEM: thread t of the warp writes 32 consecutive 32-bit columns of lane (lane base + t)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t f32_to_tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
+}
+
+// The same rounding (nearest, ties away from zero, to the 10-bit tf32 mantissa) on the integer pipe: type conversions
+// issue at 16 results/clk/SM, and the operand producers convert 32-64 values per thread per K-block, so cvt was the
+// bottleneck of the first version of these kernels; IADD + LOP3 run at full rate.  Bit-identical to cvt.rna.tf32.f32
+// for finite inputs (adds half an ulp of the dropped 13 bits to the magnitude, then truncates).
+__device__ __forceinline__ uint32_t tf32_rna_bits(uint32_t bits) { return (bits + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return tf32_rna_bits(__float_as_uint(x)); }
+// byte i (0..3) of w as an exact fp32 / tf32 value without an I2F conversion: 0x4B0000bb is 8388608 + bb
+__device__ __forceinline__ float u8_to_f32(uint32_t w, int i) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)i)) - 8388608.0f;
 }
 
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes (32 tf32 along K), 8-row groups

@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
         const uint32_t wds[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          f[c * 4 + 0] = (float)(wds[c] & 0xffu);
-          f[c * 4 + 1] = (float)((wds[c] >> 8) & 0xffu);
-          f[c * 4 + 2] = (float)((wds[c] >> 16) & 0xffu);
-          f[c * 4 + 3] = (float)(wds[c] >> 24);
+          f[c * 4 + 0] = u8_to_f32(wds[c], 0);
+          f[c * 4 + 1] = u8_to_f32(wds[c], 1);
+          f[c * 4 + 2] = u8_to_f32(wds[c], 2);
+          f[c * 4 + 3] = u8_to_f32(wds[c], 3);
         }
       } else {
 #pragma unroll
@@ -192,9 +192,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
       for (int kk = 0; kk < 32; ++kk) {
         const uint32_t row = (uint32_t)(j * 32 + kk);
         const uint32_t off = row * 128u + ((colc ^ (row & 7u)) << 4) + colb;
-        const uint32_t h = U8 ? __float_as_uint(f[kk]) : f32_to_tf32_rna(f[kk]);
+        const uint32_t h = U8 ? __float_as_uint(f[kk]) : tf32_rna(f[kk]);
         *reinterpret_cast<uint32_t*>(a_hi + off) = h;
-        if constexpr (Cfg::A_LO) *reinterpret_cast<uint32_t*>(a_lo + off) = f32_to_tf32_rna(f[kk] - __uint_as_float(h));
+        if constexpr (Cfg::A_LO) *reinterpret_cast<uint32_t*>(a_lo + off) = tf32_rna(f[kk] - __uint_as_float(h));
       }
     };
 
@@ -256,9 +256,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
         for (int e = 0; e < 4; ++e) {
           const uint32_t row = (uint32_t)(q * (BN / 4) + c * 4 + e);
           const uint32_t off = row * 128u + ((colc ^ (row & 7u)) << 4) + colb;
-          const uint32_t h = f32_to_tf32_rna(f[e]);
+          const uint32_t h = tf32_rna(f[e]);
           *reinterpret_cast<uint32_t*>(b_hi + off) = h;
-          if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(b_lo + off) = f32_to_tf32_rna(f[e] - __uint_as_float(h));
+          if constexpr (SPLIT) *reinterpret_cast<uint32_t*>(b_lo + off) = tf32_rna(f[e] - __uint_as_float(h));
           bsum[c * 4 + e] += f[e];
         }
       }
