@@ -7,11 +7,13 @@
 // One persistent CTA per SM, warp-specialised (13 warps):
 //   warps 0-7   A producers: two groups of 128 threads alternate K-blocks.  Thread r of a group owns tile row r.  It
 //               gathers the 32 consecutive k of its row (128 contiguous bytes of NHWC fp32, or 32 bytes of the uint8
-//               state), keeps PF K-blocks in flight in registers, converts to tf32 (round-to-nearest; in TF32X3 mode
-//               also the residual lo = rna(a - hi)) and hands the row to the tensor core.  im2col is never materialised.
-//               A_TMEM = true : the row goes straight into TENSOR MEMORY with tcgen05.st (lane = row, 32 columns = the
-//                               32 k) and the MMA reads A from TMEM -- no shared-memory traffic for A at all;
-//               A_TMEM = false: 16-byte chunks into the 128B-swizzled K-major operand tile in shared memory.
+//               state) with cp.async into a thread-private, bank-swizzled staging slot in shared memory, DEPTH
+//               K-blocks ahead (no registers held, no scoreboard wait at the loop back-edge -- the first version kept
+//               the prefetch in registers and ptxas serialised it); when a K-block has landed the thread reads its row
+//               back, converts to tf32 (round-to-nearest on the integer pipe; in TF32X3 mode also the residual
+//               lo = rna(a - hi)) and writes the row straight into TENSOR MEMORY with tcgen05.st (lane = row,
+//               32 columns = the 32 k).  The MMA reads A from TMEM: the operand never occupies a shared-memory
+//               operand tile and costs the MMA no shared-memory bandwidth.  im2col is never materialised.
 //   warp  8     lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = BN, K = 8) into a TMEM accumulator;
 //               tcgen05.commit releases the stage / publishes the accumulator.
 //   warps 9-12  epilogue: tcgen05.ld the accumulator rows (32 lanes per warp), then scale + bias + ReLU (forward) or
@@ -118,33 +120,36 @@ struct TcParams {
   int relu;
 };
 
-template <int BN, int MODE, bool SPLIT, bool A_TMEM>
+template <int BN, int MODE, bool SPLIT>
 struct TcCfg {
   static constexpr bool U8 = (MODE == TC_FWD_U8);
   static constexpr bool A_LO = SPLIT && !U8;
-  static constexpr int A_BYTES = A_TMEM ? 0 : 128 * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES * (A_LO ? 2 : 1) + B_BYTES * (SPLIT ? 2 : 1);
+  static constexpr int STAGE_BYTES = B_BYTES * (SPLIT ? 2 : 1);                 // shared memory per pipeline stage (B only)
   static constexpr int ACOLS = A_LO ? 64 : 32;                                  // TMEM columns per A stage
-  static constexpr int S_SMEM = 200 * 1024 / STAGE_BYTES;
-  static constexpr int S_TMEM = A_TMEM ? (512 - 2 * BN) / ACOLS : 8;
+  static constexpr int ROWB = U8 ? 32 : 128;                                    // bytes of one row of one K-block
+  static constexpr int NV = ROWB / 16;                                          // 16-byte chunks per row per K-block
+  static constexpr int DEPTH = U8 ? 8 : (BN == 128 ? 2 : 3);                    // K-blocks in flight per producer thread
+  static constexpr int STG_BYTES = 2 * 128 * ROWB * DEPTH;                      // both groups' staging rings
+  static constexpr int S_SMEM = (200 * 1024 - STG_BYTES) / STAGE_BYTES;
+  static constexpr int S_TMEM = (512 - 2 * BN) / ACOLS;
   static constexpr int STAGES = (S_SMEM < S_TMEM ? S_SMEM : S_TMEM) > 8 ? 8 : (S_SMEM < S_TMEM ? S_SMEM : S_TMEM);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-  static constexpr int TMEM_COLS = A_TMEM ? 512 : ((2 * BN) < 32 ? 32 : (2 * BN));
-  static constexpr int NV = U8 ? 2 : 8;       // 16-byte loads per row per K-block
-  static constexpr int PF = U8 ? 4 : 2;       // K-blocks in flight per producer thread
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int TMEM_COLS = 512;
   static_assert(STAGES >= 2, "need at least two pipeline stages");
 };
 
-template <int BN, int MODE, bool SPLIT, bool A_TMEM>
+template <int BN, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams p) {
-  using Cfg = TcCfg<BN, MODE, SPLIT, A_TMEM>;
+  using Cfg = TcCfg<BN, MODE, SPLIT>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int NV = Cfg::NV, PF = Cfg::PF;
+  constexpr int NV = Cfg::NV, DEPTH = Cfg::DEPTH;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ int kb_tab[kMaxKB];                // per-K-block source offsets (no division in the hot loop)
+  __shared__ int kb_tab[kMaxKB];                // per-K-block source element offsets (no division in the hot loop)
+  __shared__ int kb_tap[kMaxKB];                // dgrad: (tj << 8) | ti of the K-block's filter tap
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* stg_base = smem + STAGES * Cfg::STAGE_BYTES;                        // cp.async staging rings
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + Cfg::STG_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]  producers (128 + 1) -> MMA
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA commit -> producers
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA commit -> epilogue
@@ -175,7 +180,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
     if constexpr (MODE == TC_DGRAD) {
       const int tap = k0 / g.N, co0 = k0 - tap * g.N;
       const int tj = tap / p.I, ti = tap - tj * p.I;
-      kb_tab[kb] = (tj << 24) | (ti << 16) | co0;
+      kb_tab[kb] = co0 - (tj * g.OW + ti) * g.N;
+      kb_tap[kb] = (tj << 8) | ti;
     } else {
       const int SC = g.S * g.C;
       const int kh = k0 / SC, off = k0 - kh * SC;
@@ -192,24 +198,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
   if (warp < 8) {
     // =========================== A producers (+ B bulk copy) ===========================
     const int grp = warp >> 2;                 // owns iterations it with (it & 1) == grp
-    const int r = tid & 127;                   // tile row
+    const int wq4 = warp & 3;                  // this warp stages, converts and writes tile rows 32*wq4 .. 32*wq4+31
+    const int lane = tid & 31;
     const uint32_t ohw = (uint32_t)(g.OH * g.OW);
     const int total_it = my_tiles * KB;
+    // COALESCED staging: the NVR lanes that share a row fetch its NVR consecutive 16-byte chunks, so one warp-wide
+    // cp.async touches 32/NVR rows = 32/NVR cache lines (a lane-per-row gather would touch 32 lines per instruction
+    // and is bound by the L1 wavefront rate: measured 4x slower).  Lane l later reads back ROW l of the warp's slab.
+    constexpr int NVR = Cfg::NV;               // 16-byte chunks per row per K-block (8 fp32 / 2 uint8)
+    constexpr int RPI = 32 / NVR;              // rows covered by one warp-wide cp.async
+    constexpr int NI = 32 / RPI;               // cp.async instructions per K-block per lane
+    constexpr int ESZ = Cfg::U8 ? 1 : 4;
+    const int my_chunk = lane % NVR;
+    const int my_row0 = lane / NVR;            // instruction j stages slab row j*RPI + my_row0
+    const uint32_t slab = smem_u32(stg_base) + (uint32_t)(((grp * 4 + wq4) * DEPTH) * 32 * Cfg::ROWB);
+    auto swz_of = [](int row) -> uint32_t { return Cfg::U8 ? (uint32_t)((row >> 2) & 1) : (uint32_t)(row & 7); };
 
-    // load-stream position (advances by 2 K-blocks per owned iteration) and per-tile row state
+    // load-stream position (advances by 2 K-blocks per owned iteration) and per-tile state of the NI rows this lane stages
     int ld_tl = 0, ld_kb = grp;
     while (ld_kb >= KB) { ld_kb -= KB; ++ld_tl; }
     int cached_tile = -1;
-    int64_t rowbase = 0;       // fwd: element offset of (sample, oh*stride, ow*stride, 0)
-    uint32_t smp = 0;          // dgrad
-    int hq = 0, wq = 0;        // dgrad
-    bool row_ok = false;
+    int64_t base_j[NI];        // element offset of the row's first k (fwd) / of dZ[smp, hq, wq, 0] (dgrad)
+    int hw_j[NI];              // dgrad: (hq << 16) | wq
+    uint32_t ok_mask = 0;      // bit j: row j*RPI + my_row0 exists
     int img_base = 0;          // (class * n_tiles + n_tile) * KB
+    int img_of[DEPTH];
 
-    uint4 buf[PF][NV];
-    int img_of[PF];
-
-    auto issue = [&](uint4 (&b)[NV], int& img) {
+    auto issue = [&](int d, int& img) {
       if (ld_tl != cached_tile) {
         cached_tile = ld_tl;
         const uint32_t t = blockIdx.x + (uint32_t)ld_tl * gridDim.x;
@@ -218,48 +233,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
         const uint32_t mt = tc / (uint32_t)p.n_tiles;
         const int nt = (int)(tc - mt * (uint32_t)p.n_tiles);
         img_base = ((int)cls * p.n_tiles + nt) * KB;
-        const uint32_t m = mt * 128u + (uint32_t)r;
-        row_ok = m < p.M;
-        if (row_ok) {
-          if constexpr (MODE == TC_DGRAD) {
-            const uint32_t hw = (uint32_t)(p.Hq * p.Wq);
-            smp = m / hw;
-            const uint32_t rem = m - smp * hw;
-            hq = (int)(rem / (uint32_t)p.Wq);
-            wq = (int)(rem - (uint32_t)hq * (uint32_t)p.Wq);
-          } else {
-            const uint32_t sm = m / ohw;
-            const uint32_t rem = m - sm * ohw;
-            const uint32_t oh = rem / (uint32_t)g.OW, ow = rem - oh * (uint32_t)g.OW;
-            rowbase = (((int64_t)sm * g.H + (int64_t)oh * g.stride) * g.W + (int64_t)ow * g.stride) * g.C;
+        ok_mask = 0;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const uint32_t m = mt * 128u + (uint32_t)(wq4 * 32 + j * RPI + my_row0);
+          base_j[j] = 0;
+          hw_j[j] = 0;
+          if (m < p.M) {
+            ok_mask |= 1u << j;
+            if constexpr (MODE == TC_DGRAD) {
+              const uint32_t hw = (uint32_t)(p.Hq * p.Wq);
+              const uint32_t sm = m / hw;
+              const uint32_t rem = m - sm * hw;
+              const uint32_t hq = rem / (uint32_t)p.Wq, wq = rem - hq * (uint32_t)p.Wq;
+              hw_j[j] = (int)((hq << 16) | wq);
+              base_j[j] = (((int64_t)sm * g.OH + hq) * g.OW + wq) * (int64_t)g.N;
+            } else {
+              const uint32_t sm = m / ohw;
+              const uint32_t rem = m - sm * ohw;
+              const uint32_t oh = rem / (uint32_t)g.OW, ow = rem - oh * (uint32_t)g.OW;
+              base_j[j] = (((int64_t)sm * g.H + (int64_t)oh * g.stride) * g.W + (int64_t)ow * g.stride) * g.C;
+            }
           }
         }
       }
       img = img_base + ld_kb;
       const int tab = kb_tab[ld_kb];
+      const int tap = (MODE == TC_DGRAD) ? kb_tap[ld_kb] : 0;
+      const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x);
+      const uint32_t dst0 = slab + (uint32_t)(d * 32 * Cfg::ROWB);
 #pragma unroll
-      for (int c = 0; c < NV; ++c) b[c] = make_uint4(0u, 0u, 0u, 0u);
-      if constexpr (MODE == TC_FWD_U8) {
-        if (row_ok) {
-          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + rowbase + tab);
-          b[0] = __ldg(src);
-          b[1] = __ldg(src + 1);
+      for (int j = 0; j < NI; ++j) {
+        bool ok = (ok_mask >> j) & 1u;
+        if constexpr (MODE == TC_DGRAD) {
+          // k = (tj, ti, co): the row reads dZ[smp, hq - tj, wq - ti, co0 .. co0 + 32); tab = co0 - (tj*OW + ti)*Cout
+          const int oh = (hw_j[j] >> 16) - (tap >> 8), ow = (hw_j[j] & 0xffff) - (tap & 0xff);
+          ok = ok && oh >= 0 && ow >= 0 && oh < g.OH && ow < g.OW;
         }
-      } else if constexpr (MODE == TC_FWD_F32) {
-        if (row_ok) {
-          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) + rowbase + tab);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) b[c] = __ldg(src + c);
-        }
-      } else {
-        // dgrad: k = (tj, ti, co); the row reads dZ[smp, hq - tj, wq - ti, co0 .. co0 + 32)
-        const int oh = hq - (tab >> 24), ow = wq - ((tab >> 16) & 0xff), co0 = tab & 0xffff;
-        if (row_ok && oh >= 0 && oh < g.OH && ow >= 0 && ow < g.OW) {
-          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) +
-                                                            (((int64_t)smp * g.OH + oh) * g.OW + ow) * (int64_t)g.N + co0);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) b[c] = __ldg(src + c);
-        }
+        const uint8_t* src = ok ? xb + (base_j[j] + tab) * ESZ + my_chunk * 16 : xb;   // !ok: 0 bytes read, zero fill
+        const int row = j * RPI + my_row0;
+        cp_async16(dst0 + (uint32_t)(row * Cfg::ROWB) + (((uint32_t)my_chunk ^ swz_of(row)) << 4), src, ok ? 16u : 0u);
       }
       ld_kb += 2;
       while (ld_kb >= KB) { ld_kb -= KB; ++ld_tl; }
@@ -268,110 +281,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
     int pstage = grp % STAGES;
     uint32_t pphase = 0;
 
-    auto process = [&](const uint4 (&b)[NV], int img) {
-      mbar_wait(&empty_bar[pstage], pphase ^ 1u);
-      uint8_t* st = smem + (size_t)pstage * Cfg::STAGE_BYTES;
-      uint8_t* b_hi = st + Cfg::A_BYTES * (Cfg::A_LO ? 2 : 1);
-      if (r == 0) {
-        mbar_arrive_expect_tx(&full_bar[pstage], Cfg::B_BYTES * (SPLIT ? 2 : 1));
-        bulk_g2s(b_hi, p.b_hi + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
-        if constexpr (SPLIT) bulk_g2s(b_hi + Cfg::B_BYTES, p.b_lo + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
-      }
-      if constexpr (A_TMEM) {
-        // this thread's row of the A operand goes straight into tensor memory: lane = row, 32 columns = 32 k
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAcol0 + (uint32_t)(pstage * Cfg::ACOLS);
-        uint32_t hi[32];
-        if constexpr (Cfg::U8) {
-          const uint32_t wds[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {       // small integers are exact in tf32
-            hi[c * 4 + 0] = __float_as_uint(u8_to_f32(wds[c], 0));
-            hi[c * 4 + 1] = __float_as_uint(u8_to_f32(wds[c], 1));
-            hi[c * 4 + 2] = __float_as_uint(u8_to_f32(wds[c], 2));
-            hi[c * 4 + 3] = __float_as_uint(u8_to_f32(wds[c], 3));
-          }
-          tmem_st32(taddr, hi);
-        } else {
+    for (int u = 0; u < DEPTH; ++u) {
+      if (grp + 2 * u < total_it) issue(u, img_of[u]);
+      cp_async_commit();
+    }
+    for (int base = grp; base < total_it; base += 2 * DEPTH) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            hi[c * 4 + 0] = tf32_rna(__uint_as_float(b[c].x));
-            hi[c * 4 + 1] = tf32_rna(__uint_as_float(b[c].y));
-            hi[c * 4 + 2] = tf32_rna(__uint_as_float(b[c].z));
-            hi[c * 4 + 3] = tf32_rna(__uint_as_float(b[c].w));
-          }
-          tmem_st32(taddr, hi);
-          if constexpr (Cfg::A_LO) {
-            uint32_t lo[32];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              lo[c * 4 + 0] = tf32_rna(__uint_as_float(b[c].x) - __uint_as_float(hi[c * 4 + 0]));
-              lo[c * 4 + 1] = tf32_rna(__uint_as_float(b[c].y) - __uint_as_float(hi[c * 4 + 1]));
-              lo[c * 4 + 2] = tf32_rna(__uint_as_float(b[c].z) - __uint_as_float(hi[c * 4 + 2]));
-              lo[c * 4 + 3] = tf32_rna(__uint_as_float(b[c].w) - __uint_as_float(hi[c * 4 + 3]));
-            }
-            tmem_st32(taddr + 32u, lo);
-          }
-        }
-      } else {
-        uint8_t* a_hi = st;
-        uint8_t* a_lo = st + Cfg::A_BYTES;
-        if constexpr (Cfg::U8) {
-          const uint32_t wds[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t wv = wds[c];
-            uint4 o;
-            o.x = __float_as_uint(u8_to_f32(wv, 0));
-            o.y = __float_as_uint(u8_to_f32(wv, 1));
-            o.z = __float_as_uint(u8_to_f32(wv, 2));
-            o.w = __float_as_uint(u8_to_f32(wv, 3));
-            *reinterpret_cast<uint4*>(a_hi + sw128_off((uint32_t)r, (uint32_t)c)) = o;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float f0 = __uint_as_float(b[c].x), f1 = __uint_as_float(b[c].y);
-            const float f2 = __uint_as_float(b[c].z), f3 = __uint_as_float(b[c].w);
-            uint4 h;
-            h.x = tf32_rna(f0); h.y = tf32_rna(f1); h.z = tf32_rna(f2); h.w = tf32_rna(f3);
-            *reinterpret_cast<uint4*>(a_hi + sw128_off((uint32_t)r, (uint32_t)c)) = h;
-            if constexpr (Cfg::A_LO) {
-              uint4 l;
-              l.x = tf32_rna(f0 - __uint_as_float(h.x)); l.y = tf32_rna(f1 - __uint_as_float(h.y));
-              l.z = tf32_rna(f2 - __uint_as_float(h.z)); l.w = tf32_rna(f3 - __uint_as_float(h.w));
-              *reinterpret_cast<uint4*>(a_lo + sw128_off((uint32_t)r, (uint32_t)c)) = l;
-            }
-          }
-        }
-      }
-    };
-
-    auto publish = [&]() {
-      if constexpr (A_TMEM) {
-        tmem_st_wait();                        // tcgen05.st complete ...
-        tc_fence_before();                     // ... and ordered before the arrive the MMA thread observes
-      } else {
-        fence_proxy_async();                   // generic-proxy smem stores -> visible to the tensor core (async proxy)
-      }
-      mbar_arrive(&full_bar[pstage]);
-      pstage += 2;
-      if (pstage >= STAGES) { pstage -= STAGES; pphase ^= 1u; }
-    };
-
-#pragma unroll
-    for (int u = 0; u < PF; ++u)
-      if (grp + 2 * u < total_it) issue(buf[u], img_of[u]);
-    for (int base = grp; base < total_it; base += 2 * PF) {
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
+      for (int u = 0; u < DEPTH; ++u) {
         const int it = base + 2 * u;
         if (it < total_it) {
-          process(buf[u], img_of[u]);
-          if (it + 2 * PF < total_it) issue(buf[u], img_of[u]);   // refill while the MMA consumes
-          publish();
+          cp_async_wait<DEPTH - 1>();          // this lane's copies for iteration `it` have landed in slot u ...
+          __syncwarp();                        // ... and so have the other lanes' (the slab row is written by NVR lanes)
+          uint4 b[NV];
+          {
+            const uint32_t rowp = slab + (uint32_t)(u * 32 * Cfg::ROWB) + (uint32_t)(lane * Cfg::ROWB);
+#pragma unroll
+            for (int c = 0; c < NV; ++c) b[c] = lds128(rowp + (((uint32_t)c ^ swz_of(lane)) << 4));
+          }
+          __syncwarp();                        // every lane has read its row: slot u may be refilled
+          const int img = img_of[u];
+          if (it + 2 * DEPTH < total_it) issue(u, img_of[u]);
+          cp_async_commit();
+
+          mbar_wait(&empty_bar[pstage], pphase ^ 1u);
+          if (wq4 == 0 && lane == 0) {
+            uint8_t* b_hi = smem + (size_t)pstage * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[pstage], Cfg::B_BYTES * (SPLIT ? 2 : 1));
+            bulk_g2s(b_hi, p.b_hi + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
+            if constexpr (SPLIT) bulk_g2s(b_hi + Cfg::B_BYTES, p.b_lo + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
+          }
+          // this thread's row of the A operand goes straight into tensor memory: lane = row, 32 columns = 32 k
+          const uint32_t taddr = tmem_base + ((uint32_t)(wq4 * 32) << 16) + kAcol0 + (uint32_t)(pstage * Cfg::ACOLS);
+          uint32_t hi[32];
+          if constexpr (Cfg::U8) {
+            const uint32_t wds[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {     // small integers are exact in tf32
+              hi[c * 4 + 0] = __float_as_uint(u8_to_f32(wds[c], 0));
+              hi[c * 4 + 1] = __float_as_uint(u8_to_f32(wds[c], 1));
+              hi[c * 4 + 2] = __float_as_uint(u8_to_f32(wds[c], 2));
+              hi[c * 4 + 3] = __float_as_uint(u8_to_f32(wds[c], 3));
+            }
+            tmem_st32(taddr, hi);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              hi[c * 4 + 0] = tf32_rna_bits(b[c].x);
+              hi[c * 4 + 1] = tf32_rna_bits(b[c].y);
+              hi[c * 4 + 2] = tf32_rna_bits(b[c].z);
+              hi[c * 4 + 3] = tf32_rna_bits(b[c].w);
+            }
+            tmem_st32(taddr, hi);
+            if constexpr (Cfg::A_LO) {
+              uint32_t lo[32];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                lo[c * 4 + 0] = tf32_rna(__uint_as_float(b[c].x) - __uint_as_float(hi[c * 4 + 0]));
+                lo[c * 4 + 1] = tf32_rna(__uint_as_float(b[c].y) - __uint_as_float(hi[c * 4 + 1]));
+                lo[c * 4 + 2] = tf32_rna(__uint_as_float(b[c].z) - __uint_as_float(hi[c * 4 + 2]));
+                lo[c * 4 + 3] = tf32_rna(__uint_as_float(b[c].w) - __uint_as_float(hi[c * 4 + 3]));
+              }
+              tmem_st32(taddr + 32u, lo);
+            }
+          }
+          tmem_st_wait();                      // tcgen05.st complete ...
+          tc_fence_before();                   // ... and ordered before the arrive the MMA thread observes
+          mbar_arrive(&full_bar[pstage]);
+          pstage += 2;
+          if (pstage >= STAGES) { pstage -= STAGES; pphase ^= 1u; }
         }
       }
     }
+    cp_async_wait<0>();
   } else if (warp == 8) {
     // =========================== MMA issuer ===========================
     if ((tid & 31) == 0) {
@@ -387,35 +369,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
-          const uint32_t b_hi = st + Cfg::A_BYTES * (Cfg::A_LO ? 2 : 1), b_lo = b_hi + Cfg::B_BYTES;
+          const uint32_t b_hi = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES), b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {     // K = 8 tf32 per instruction: 32 bytes of smem / 8 TMEM columns
+          for (int ks = 0; ks < 4; ++ks) {     // K = 8 tf32 per instruction: 32 bytes of smem (B) / 8 TMEM columns (A)
             const uint32_t ko = (uint32_t)ks * 32u;
             uint32_t accum = (kb > 0 || ks > 0) ? 1u : 0u;
-            if constexpr (A_TMEM) {
-              const uint32_t a_hi = tmem_base + kAcol0 + (uint32_t)(stage * Cfg::ACOLS) + (uint32_t)ks * 8u;
-              if constexpr (SPLIT) {
-                if constexpr (Cfg::A_LO) {
-                  umma_tf32_ts(d_tmem, a_hi + 32u, make_sw128_desc(b_hi + ko), idesc, accum);
-                  accum = 1u;
-                }
-                umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_lo + ko), idesc, accum);
+            const uint32_t a_hi = tmem_base + kAcol0 + (uint32_t)(stage * Cfg::ACOLS) + (uint32_t)ks * 8u;
+            if constexpr (SPLIT) {
+              if constexpr (Cfg::A_LO) {
+                umma_tf32_ts(d_tmem, a_hi + 32u, make_sw128_desc(b_hi + ko), idesc, accum);
                 accum = 1u;
               }
-              umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_hi + ko), idesc, accum);
-            } else {
-              const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES;
-              if constexpr (SPLIT) {
-                if constexpr (Cfg::A_LO) {
-                  umma_tf32(d_tmem, make_sw128_desc(a_lo + ko), make_sw128_desc(b_hi + ko), idesc, accum);
-                  accum = 1u;
-                }
-                umma_tf32(d_tmem, make_sw128_desc(a_hi + ko), make_sw128_desc(b_lo + ko), idesc, accum);
-                accum = 1u;
-              }
-              umma_tf32(d_tmem, make_sw128_desc(a_hi + ko), make_sw128_desc(b_hi + ko), idesc, accum);
+              umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_lo + ko), idesc, accum);
+              accum = 1u;
             }
+            umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_hi + ko), idesc, accum);
           }
           umma_commit(&empty_bar[stage]);      // stage reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -507,12 +475,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-template <int BN, int MODE, bool SPLIT, bool A_TMEM>
+template <int BN, int MODE, bool SPLIT>
 static int launch_tc_inst2(const paacb_ctx* ctx, const TcParams& p, int slot, cudaStream_t st) {
-  using Cfg = TcCfg<BN, MODE, SPLIT, A_TMEM>;
+  using Cfg = TcCfg<BN, MODE, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_tc_kernel<BN, MODE, SPLIT, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(igemm_tc_kernel<BN, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess) {
       set_error("igemm_tc: cannot set %d bytes of dynamic shared memory", Cfg::SMEM_BYTES);
       return PAACB_ECUDA;
@@ -522,17 +490,14 @@ static int launch_tc_inst2(const paacb_ctx* ctx, const TcParams& p, int slot, cu
   const uint32_t tiles = p.m_tiles * (uint32_t)p.n_tiles * (uint32_t)p.classes;
   const unsigned grid = tiles < (uint32_t)ctx->num_sms ? tiles : (unsigned)ctx->num_sms;
   PAACB_LAUNCH_BEGIN(ctx, slot, st);
-  igemm_tc_kernel<BN, MODE, SPLIT, A_TMEM><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(p);
+  igemm_tc_kernel<BN, MODE, SPLIT><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(p);
   PAACB_LAUNCH_END(ctx, slot, st);
   return PAACB_OK;
 }
 
 template <int BN, int MODE>
 static int launch_tc_inst(const paacb_ctx* ctx, const TcParams& p, int slot, int split3, cudaStream_t st) {
-  if (ctx->tc_a_tmem) {
-    return split3 ? launch_tc_inst2<BN, MODE, true, true>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, true>(ctx, p, slot, st);
-  }
-  return split3 ? launch_tc_inst2<BN, MODE, true, false>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, false>(ctx, p, slot, st);
+  return split3 ? launch_tc_inst2<BN, MODE, true>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false>(ctx, p, slot, st);
 }
 
 static int pick_bn(int n) { return (n % 128 == 0) ? 128 : ((n % 64 == 0) ? 64 : ((n % 32 == 0) ? 32 : 0)); }
