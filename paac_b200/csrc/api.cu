@@ -1,5 +1,6 @@
 // extern "C" entry points of libpaacb.so (see include/paacb.h for the contract of each).
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace paacb {
@@ -102,8 +103,8 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
   c->arch = arch; c->num_actions = num_actions; c->device = device; c->math = PAACB_MATH_FP32;
   c->num_sms = prop.multiProcessorCount;
   {
-    const char* knob = getenv("PAACB_TC_A");
-    c->tc_a_tmem = (knob != nullptr && strcmp(knob, "smem") == 0) ? 0 : 1;
+    const char* knob = getenv("PAACB_DBG");
+    c->dbg = (knob != nullptr) ? atoi(knob) : 0;
   }
   int h = PAACB_OBS, w = PAACB_OBS, ch = PAACB_STACK;
   int64_t poff = 0, aoff = 0;

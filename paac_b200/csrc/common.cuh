@@ -77,8 +77,7 @@ struct paacb_ctx {
   uint32_t* wpack_lo;
   uint32_t* wpack_d_hi;         // the transposed / per-stride-class images the data-gradient kernels read
   uint32_t* wpack_d_lo;
-  int tc_a_tmem;                // 1: the A operand of the tcgen05 kernels lives in tensor memory (default); 0: shared memory
-                                // (debug knob, environment variable PAACB_TC_A=smem at context creation)
+  int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };
 
 namespace paacb {

@@ -98,8 +98,9 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, LayerGeom
 // ------------------------------------------------------------------------------------------------
 // the implicit-GEMM kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcProducerThreads = 256;     // two groups of 128
-constexpr int kTcThreads = kTcProducerThreads + 32 + 128;
+constexpr int kTcGroups = 3;                // producer groups of 128 threads (4 warps) that take K-blocks round-robin
+constexpr int kTcThreads = kTcGroups * 128 + 32 + 128;
+constexpr int kTcMmaWarp = kTcGroups * 4;   // warps [0, 4*NG) produce, warp 4*NG issues MMAs, the next four run the epilogue
 constexpr int kMaxKB = 128;                 // K-blocks per tile the per-K-block table can hold
 
 struct TcParams {
@@ -118,6 +119,8 @@ struct TcParams {
   int Hq, Wq, I;          // dgrad: class grid and taps per row
   float in_scale;
   int relu;
+  int dbg;                // ablation switches for timing experiments (PAACB_DBG): 1 skip B copy, 2 skip tcgen05.st, 4 skip cp.async,
+                          // 8 skip the MMAs, 16 skip the epilogue stores.  Results are wrong when non-zero.
 };
 
 template <int BN, int MODE, bool SPLIT>
@@ -129,8 +132,9 @@ struct TcCfg {
   static constexpr int ACOLS = A_LO ? 64 : 32;                                  // TMEM columns per A stage
   static constexpr int ROWB = U8 ? 32 : 128;                                    // bytes of one row of one K-block
   static constexpr int NV = ROWB / 16;                                          // 16-byte chunks per row per K-block
-  static constexpr int DEPTH = U8 ? 8 : (BN == 128 ? 2 : 3);                    // K-blocks in flight per producer thread
-  static constexpr int STG_BYTES = 2 * 128 * ROWB * DEPTH;                      // both groups' staging rings
+  static constexpr int NG = kTcGroups;
+  static constexpr int DEPTH = U8 ? 6 : 2;                                      // K-blocks in flight per producer thread
+  static constexpr int STG_BYTES = NG * 128 * ROWB * DEPTH;                     // all groups' staging rings
   static constexpr int S_SMEM = (200 * 1024 - STG_BYTES) / STAGE_BYTES;
   static constexpr int S_TMEM = (512 - 2 * BN) / ACOLS;
   static constexpr int STAGES = (S_SMEM < S_TMEM ? S_SMEM : S_TMEM) > 8 ? 8 : (S_SMEM < S_TMEM ? S_SMEM : S_TMEM);
@@ -143,7 +147,7 @@ template <int BN, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams p) {
   using Cfg = TcCfg<BN, MODE, SPLIT>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int NV = Cfg::NV, DEPTH = Cfg::DEPTH;
+  constexpr int NV = Cfg::NV, DEPTH = Cfg::DEPTH, NG = Cfg::NG;
   extern __shared__ uint8_t smem_raw[];
   __shared__ int kb_tab[kMaxKB];                // per-K-block source element offsets (no division in the hot loop)
   __shared__ int kb_tap[kMaxKB];                // dgrad: (tj << 8) | ti of the K-block's filter tap
@@ -188,16 +192,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
       kb_tab[kb] = kh * g.W * g.C + off;
     }
   }
-  if (warp == 8) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == kTcMmaWarp) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kAcol0 = 2 * BN;           // first TMEM column of the A stages (A_TMEM)
 
-  if (warp < 8) {
+  if (warp < kTcMmaWarp) {
     // =========================== A producers (+ B bulk copy) ===========================
-    const int grp = warp >> 2;                 // owns iterations it with (it & 1) == grp
+    const int grp = warp >> 2;                 // owns iterations it with it % NG == grp
     const int wq4 = warp & 3;                  // this warp stages, converts and writes tile rows 32*wq4 .. 32*wq4+31
     const int lane = tid & 31;
     const uint32_t ohw = (uint32_t)(g.OH * g.OW);
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
     const uint32_t slab = smem_u32(stg_base) + (uint32_t)(((grp * 4 + wq4) * DEPTH) * 32 * Cfg::ROWB);
     auto swz_of = [](int row) -> uint32_t { return Cfg::U8 ? (uint32_t)((row >> 2) & 1) : (uint32_t)(row & 7); };
 
-    // load-stream position (advances by 2 K-blocks per owned iteration) and per-tile state of the NI rows this lane stages
+    // load-stream position (advances by NG K-blocks per owned iteration) and per-tile state of the NI rows this lane stages
     int ld_tl = 0, ld_kb = grp;
     while (ld_kb >= KB) { ld_kb -= KB; ++ld_tl; }
     int cached_tile = -1;
@@ -272,24 +276,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
         }
         const uint8_t* src = ok ? xb + (base_j[j] + tab) * ESZ + my_chunk * 16 : xb;   // !ok: 0 bytes read, zero fill
         const int row = j * RPI + my_row0;
-        cp_async16(dst0 + (uint32_t)(row * Cfg::ROWB) + (((uint32_t)my_chunk ^ swz_of(row)) << 4), src, ok ? 16u : 0u);
+        if (!(p.dbg & 4)) cp_async16(dst0 + (uint32_t)(row * Cfg::ROWB) + (((uint32_t)my_chunk ^ swz_of(row)) << 4), src, ok ? 16u : 0u);
       }
-      ld_kb += 2;
+      ld_kb += NG;
       while (ld_kb >= KB) { ld_kb -= KB; ++ld_tl; }
     };
 
-    int pstage = grp % STAGES;
+    int pstage = grp;
     uint32_t pphase = 0;
+    while (pstage >= STAGES) { pstage -= STAGES; pphase ^= 1u; }
 
 #pragma unroll
     for (int u = 0; u < DEPTH; ++u) {
-      if (grp + 2 * u < total_it) issue(u, img_of[u]);
+      if (grp + NG * u < total_it) issue(u, img_of[u]);
       cp_async_commit();
     }
-    for (int base = grp; base < total_it; base += 2 * DEPTH) {
+    for (int base = grp; base < total_it; base += NG * DEPTH) {
 #pragma unroll
       for (int u = 0; u < DEPTH; ++u) {
-        const int it = base + 2 * u;
+        const int it = base + NG * u;
         if (it < total_it) {
           cp_async_wait<DEPTH - 1>();          // this lane's copies for iteration `it` have landed in slot u ...
           __syncwarp();                        // ... and so have the other lanes' (the slab row is written by NVR lanes)
@@ -301,15 +306,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
           }
           __syncwarp();                        // every lane has read its row: slot u may be refilled
           const int img = img_of[u];
-          if (it + 2 * DEPTH < total_it) issue(u, img_of[u]);
+          if (it + NG * DEPTH < total_it) issue(u, img_of[u]);
           cp_async_commit();
 
           mbar_wait(&empty_bar[pstage], pphase ^ 1u);
-          if (wq4 == 0 && lane == 0) {
+          if (wq4 == 0 && elect_one_sync()) {
             uint8_t* b_hi = smem + (size_t)pstage * Cfg::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[pstage], Cfg::B_BYTES * (SPLIT ? 2 : 1));
-            bulk_g2s(b_hi, p.b_hi + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
-            if constexpr (SPLIT) bulk_g2s(b_hi + Cfg::B_BYTES, p.b_lo + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
+            if (p.dbg & 1) {
+              mbar_arrive(&full_bar[pstage]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[pstage], Cfg::B_BYTES * (SPLIT ? 2 : 1));
+              bulk_g2s(b_hi, p.b_hi + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
+              if constexpr (SPLIT) bulk_g2s(b_hi + Cfg::B_BYTES, p.b_lo + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
+            }
           }
           // this thread's row of the A operand goes straight into tensor memory: lane = row, 32 columns = 32 k
           const uint32_t taddr = tmem_base + ((uint32_t)(wq4 * 32) << 16) + kAcol0 + (uint32_t)(pstage * Cfg::ACOLS);
@@ -323,41 +332,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
               hi[c * 4 + 2] = __float_as_uint(u8_to_f32(wds[c], 2));
               hi[c * 4 + 3] = __float_as_uint(u8_to_f32(wds[c], 3));
             }
-            tmem_st32(taddr, hi);
+            if (!(p.dbg & 2)) tmem_st32(taddr, hi);
           } else {
+            // TF32X3: hi = a with the 13 low mantissa bits cleared (1 LOP), lo = a - hi exactly (1 FADD); the tensor core
+            // reads only the tf32 bits of lo, an error of 2^-21 |a|.  Plain TF32 rounds to nearest (2 integer ops).
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              hi[c * 4 + 0] = tf32_rna_bits(b[c].x);
-              hi[c * 4 + 1] = tf32_rna_bits(b[c].y);
-              hi[c * 4 + 2] = tf32_rna_bits(b[c].z);
-              hi[c * 4 + 3] = tf32_rna_bits(b[c].w);
+              hi[c * 4 + 0] = Cfg::A_LO ? (b[c].x & 0xFFFFE000u) : tf32_rna_bits(b[c].x);
+              hi[c * 4 + 1] = Cfg::A_LO ? (b[c].y & 0xFFFFE000u) : tf32_rna_bits(b[c].y);
+              hi[c * 4 + 2] = Cfg::A_LO ? (b[c].z & 0xFFFFE000u) : tf32_rna_bits(b[c].z);
+              hi[c * 4 + 3] = Cfg::A_LO ? (b[c].w & 0xFFFFE000u) : tf32_rna_bits(b[c].w);
             }
-            tmem_st32(taddr, hi);
+            if (!(p.dbg & 2)) tmem_st32(taddr, hi);
             if constexpr (Cfg::A_LO) {
               uint32_t lo[32];
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                lo[c * 4 + 0] = tf32_rna(__uint_as_float(b[c].x) - __uint_as_float(hi[c * 4 + 0]));
-                lo[c * 4 + 1] = tf32_rna(__uint_as_float(b[c].y) - __uint_as_float(hi[c * 4 + 1]));
-                lo[c * 4 + 2] = tf32_rna(__uint_as_float(b[c].z) - __uint_as_float(hi[c * 4 + 2]));
-                lo[c * 4 + 3] = tf32_rna(__uint_as_float(b[c].w) - __uint_as_float(hi[c * 4 + 3]));
+                lo[c * 4 + 0] = __float_as_uint(__uint_as_float(b[c].x) - __uint_as_float(hi[c * 4 + 0]));
+                lo[c * 4 + 1] = __float_as_uint(__uint_as_float(b[c].y) - __uint_as_float(hi[c * 4 + 1]));
+                lo[c * 4 + 2] = __float_as_uint(__uint_as_float(b[c].z) - __uint_as_float(hi[c * 4 + 2]));
+                lo[c * 4 + 3] = __float_as_uint(__uint_as_float(b[c].w) - __uint_as_float(hi[c * 4 + 3]));
               }
-              tmem_st32(taddr + 32u, lo);
+              if (!(p.dbg & 2)) tmem_st32(taddr + 32u, lo);
             }
           }
           tmem_st_wait();                      // tcgen05.st complete ...
           tc_fence_before();                   // ... and ordered before the arrive the MMA thread observes
           mbar_arrive(&full_bar[pstage]);
-          pstage += 2;
-          if (pstage >= STAGES) { pstage -= STAGES; pphase ^= 1u; }
+          pstage += NG;
+          while (pstage >= STAGES) { pstage -= STAGES; pphase ^= 1u; }
         }
       }
     }
     cp_async_wait<0>();
-  } else if (warp == 8) {
+  } else if (warp == kTcMmaWarp) {
     // =========================== MMA issuer ===========================
-    if ((tid & 31) == 0) {
+    // The whole warp walks the loop (warp-uniform control flow, so descriptors and addresses live in uniform
+    // registers); one elected lane issues.  Issuing from inside a divergent `if (lane == 0)` made the compiler wrap
+    // every tcgen05.mma in an ELECT / BRA.U.ANY sequence (~90 cycles per MMA: the first version's real bottleneck).
+    {
       constexpr uint32_t idesc = make_idesc_tf32(BN);
+      const bool leader = elect_one_sync();
       int stage = 0;
       uint32_t phase = 0;
       for (int tl = 0; tl < my_tiles; ++tl) {
@@ -370,6 +385,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t b_hi = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES), b_lo = b_hi + Cfg::B_BYTES;
+          if (leader) {
+          if (!(p.dbg & 8)) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {     // K = 8 tf32 per instruction: 32 bytes of smem (B) / 8 TMEM columns (A)
             const uint32_t ko = (uint32_t)ks * 32u;
@@ -385,10 +402,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
             }
             umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_hi + ko), idesc, accum);
           }
+          }
           umma_commit(&empty_bar[stage]);      // stage reusable once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);          // accumulator complete
+        if (leader) umma_commit(&tfull_bar[acc]);   // accumulator complete
+        __syncwarp();
       }
     }
   } else {
@@ -429,7 +450,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (ok) {
+        if (ok && !(p.dbg & 16)) {
           float* dst = p.y + out_base + c0;
           if constexpr (MODE == TC_DGRAD) {
             const float* xa = (p.xact != nullptr) ? p.xact + out_base + c0 : nullptr;
@@ -466,7 +487,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -553,6 +574,7 @@ int launch_conv_fwd_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, 
   p.kblocks = g.K / 32;
   p.in_scale = g.in_u8 ? 0.003921568859368563f : 1.0f;
   p.relu = 1;
+  p.dbg = ctx->dbg;
   const int slot = K_FWD0 + g.index;
   if (g.in_u8) {
     if (bn == 32) return launch_tc_inst<32, TC_FWD_U8>(ctx, p, slot, split3, st);
@@ -592,6 +614,7 @@ int launch_conv_dgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const float* 
   p.classes = s * s;
   p.kblocks = J * I * g.N / 32;
   p.in_scale = 1.0f;
+  p.dbg = ctx->dbg;
   const int slot = K_DGRAD0 + g.index;
   if (bn == 32) return launch_tc_inst<32, TC_DGRAD>(ctx, p, slot, split3, st);
   if (bn == 64) return launch_tc_inst<64, TC_DGRAD>(ctx, p, slot, split3, st);

@@ -296,8 +296,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
     }
   } else if (warp == 8) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    {   // warp-uniform loop, one elected lane issues (see igemm_tc.cu)
       constexpr uint32_t idesc = make_idesc_tf32(BN);
+      const bool leader = elect_one_sync();
       WgCursor c;
       c.unit_i = 0; c.kb = 0;
       int64_t it = 0;
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
           const uint32_t st = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
           const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES;
           const uint32_t b_hi = st + Cfg::A_BYTES * (Cfg::A_LO ? 2 : 1), b_lo = b_hi + Cfg::B_BYTES;
+          if (leader) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t ko = (uint32_t)ks * 32u;
@@ -332,8 +334,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
             umma_tf32(d_tmem, make_sw128_desc(a_hi + ko), make_sw128_desc(b_hi + ko), idesc, accum);
           }
           umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
         }
-        umma_commit(&tfull_bar[acc]);
+        if (leader) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
       }
     }
   } else {
