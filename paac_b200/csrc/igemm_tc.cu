@@ -98,7 +98,7 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, LayerGeom
 // ------------------------------------------------------------------------------------------------
 // the implicit-GEMM kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcGroups = 3;                // producer groups of 128 threads (4 warps) that take K-blocks round-robin
+constexpr int kTcGroups = 2;                // producer groups of 128 threads (4 warps) that take K-blocks round-robin
 constexpr int kTcThreads = kTcGroups * 128 + 32 + 128;
 constexpr int kTcMmaWarp = kTcGroups * 4;   // warps [0, 4*NG) produce, warp 4*NG issues MMAs, the next four run the epilogue
 constexpr int kMaxKB = 128;                 // K-blocks per tile the per-K-block table can hold
@@ -123,29 +123,35 @@ struct TcParams {
                           // 8 skip the MMAs, 16 skip the epilogue stores.  Results are wrong when non-zero.
 };
 
-template <int BN, int MODE, bool SPLIT>
+constexpr int kSmemBudget = 224 * 1024;      // B stages + cp.async staging (the per-SM maximum is 227 KB incl. static)
+
+template <int BN, int MODE, bool SPLIT, int KSUB>
 struct TcCfg {
+  // One pipeline stage covers KSUB consecutive 32-wide K-blocks: the producer/MMA handshake (mbarrier round trip,
+  // tcgen05.wait::st, fences) costs ~700 cycles per stage whatever its payload, so narrow tiles use larger stages.
   static constexpr bool U8 = (MODE == TC_FWD_U8);
   static constexpr bool A_LO = SPLIT && !U8;
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = B_BYTES * (SPLIT ? 2 : 1);                 // shared memory per pipeline stage (B only)
-  static constexpr int ACOLS = A_LO ? 64 : 32;                                  // TMEM columns per A stage
-  static constexpr int ROWB = U8 ? 32 : 128;                                    // bytes of one row of one K-block
+  static constexpr int B_BYTES = BN * 128;                                      // one 32-wide K-block image of B
+  static constexpr int STAGE_BYTES = KSUB * B_BYTES * (SPLIT ? 2 : 1);          // shared memory per pipeline stage (B only)
+  static constexpr int ACOLS = A_LO ? 64 : 32;                                  // TMEM columns per 32-wide K-block of A
+  static constexpr int SCOLS = KSUB * ACOLS;                                    // TMEM columns per A stage
+  static constexpr int ROWB = U8 ? 32 : 128;                                    // bytes of one row of one 32-wide K-block
   static constexpr int NV = ROWB / 16;                                          // 16-byte chunks per row per K-block
   static constexpr int NG = kTcGroups;
-  static constexpr int DEPTH = U8 ? 6 : 2;                                      // K-blocks in flight per producer thread
-  static constexpr int STG_BYTES = NG * 128 * ROWB * DEPTH;                     // all groups' staging rings
-  static constexpr int S_SMEM = (200 * 1024 - STG_BYTES) / STAGE_BYTES;
-  static constexpr int S_TMEM = (512 - 2 * BN) / ACOLS;
-  static constexpr int STAGES = (S_SMEM < S_TMEM ? S_SMEM : S_TMEM) > 8 ? 8 : (S_SMEM < S_TMEM ? S_SMEM : S_TMEM);
+  static constexpr int S_TMEM = ((512 - 2 * BN) / SCOLS) > 4 ? 4 : ((512 - 2 * BN) / SCOLS);
+  static constexpr int STAGES = S_TMEM;
+  static constexpr int STG_UNIT = NG * 128 * ROWB * KSUB;                       // staging bytes per unit of depth
+  static constexpr int D_FIT = (kSmemBudget - STAGES * STAGE_BYTES) / STG_UNIT;
+  static constexpr int DEPTH = D_FIT > (U8 ? 6 : 3) ? (U8 ? 6 : 3) : D_FIT;    // stages in flight per producer thread
+  static constexpr int STG_BYTES = STG_UNIT * DEPTH;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
   static constexpr int TMEM_COLS = 512;
-  static_assert(STAGES >= 2, "need at least two pipeline stages");
+  static_assert(STAGES >= 2 && DEPTH >= 1, "pipeline does not fit");
 };
 
-template <int BN, int MODE, bool SPLIT>
+template <int BN, int MODE, bool SPLIT, int KSUB>
 __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams p) {
-  using Cfg = TcCfg<BN, MODE, SPLIT>;
+  using Cfg = TcCfg<BN, MODE, SPLIT, KSUB>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NV = Cfg::NV, DEPTH = Cfg::DEPTH, NG = Cfg::NG;
   extern __shared__ uint8_t smem_raw[];
@@ -166,7 +172,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
   const uint32_t tiles_per_class = p.m_tiles * (uint32_t)p.n_tiles;
   const uint32_t total_tiles = tiles_per_class * (uint32_t)p.classes;
   const int my_tiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
-  const int KB = p.kblocks;
+  const int KB = p.kblocks;                     // 32-wide K-blocks per tile
+  const int KBS = KB / KSUB;                    // pipeline stages per tile
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
     const int wq4 = warp & 3;                  // this warp stages, converts and writes tile rows 32*wq4 .. 32*wq4+31
     const int lane = tid & 31;
     const uint32_t ohw = (uint32_t)(g.OH * g.OW);
-    const int total_it = my_tiles * KB;
+    const int total_it = my_tiles * KBS;
     // COALESCED staging: the NVR lanes that share a row fetch its NVR consecutive 16-byte chunks, so one warp-wide
     // cp.async touches 32/NVR rows = 32/NVR cache lines (a lane-per-row gather would touch 32 lines per instruction
     // and is bound by the L1 wavefront rate: measured 4x slower).  Lane l later reads back ROW l of the warp's slab.
@@ -215,11 +222,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
     constexpr int ESZ = Cfg::U8 ? 1 : 4;
     const int my_chunk = lane % NVR;
     const int my_row0 = lane / NVR;            // instruction j stages slab row j*RPI + my_row0
-    const uint32_t slab = smem_u32(stg_base) + (uint32_t)(((grp * 4 + wq4) * DEPTH) * 32 * Cfg::ROWB);
+    constexpr uint32_t kSlot = KSUB * 32 * Cfg::ROWB;    // one depth slot of this warp's slab: [KSUB][32 rows][ROWB]
+    const uint32_t slab = smem_u32(stg_base) + (uint32_t)((grp * 4 + wq4) * DEPTH) * kSlot;
     auto swz_of = [](int row) -> uint32_t { return Cfg::U8 ? (uint32_t)((row >> 2) & 1) : (uint32_t)(row & 7); };
 
     // load-stream position (advances by NG K-blocks per owned iteration) and per-tile state of the NI rows this lane stages
-    int ld_tl = 0, ld_kb = grp;
+    int ld_tl = 0, ld_kb = grp * KSUB;
     while (ld_kb >= KB) { ld_kb -= KB; ++ld_tl; }
     int cached_tile = -1;
     int64_t base_j[NI];        // element offset of the row's first k (fwd) / of dZ[smp, hq, wq, 0] (dgrad)
@@ -262,23 +270,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
         }
       }
       img = img_base + ld_kb;
-      const int tab = kb_tab[ld_kb];
-      const int tap = (MODE == TC_DGRAD) ? kb_tap[ld_kb] : 0;
       const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x);
-      const uint32_t dst0 = slab + (uint32_t)(d * 32 * Cfg::ROWB);
 #pragma unroll
-      for (int j = 0; j < NI; ++j) {
-        bool ok = (ok_mask >> j) & 1u;
-        if constexpr (MODE == TC_DGRAD) {
-          // k = (tj, ti, co): the row reads dZ[smp, hq - tj, wq - ti, co0 .. co0 + 32); tab = co0 - (tj*OW + ti)*Cout
-          const int oh = (hw_j[j] >> 16) - (tap >> 8), ow = (hw_j[j] & 0xffff) - (tap & 0xff);
-          ok = ok && oh >= 0 && ow >= 0 && oh < g.OH && ow < g.OW;
+      for (int sb = 0; sb < KSUB; ++sb) {
+        const int tab = kb_tab[ld_kb + sb];
+        const int tap = (MODE == TC_DGRAD) ? kb_tap[ld_kb + sb] : 0;
+        const uint32_t dst0 = slab + (uint32_t)d * kSlot + (uint32_t)(sb * 32 * Cfg::ROWB);
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          bool ok = (ok_mask >> j) & 1u;
+          if constexpr (MODE == TC_DGRAD) {
+            // k = (tj, ti, co): the row reads dZ[smp, hq - tj, wq - ti, co0 .. co0 + 32); tab = co0 - (tj*OW + ti)*Cout
+            const int oh = (hw_j[j] >> 16) - (tap >> 8), ow = (hw_j[j] & 0xffff) - (tap & 0xff);
+            ok = ok && oh >= 0 && ow >= 0 && oh < g.OH && ow < g.OW;
+          }
+          const uint8_t* src = ok ? xb + (base_j[j] + tab) * ESZ + my_chunk * 16 : xb;   // !ok: 0 bytes read, zero fill
+          const int row = j * RPI + my_row0;
+          if (!(p.dbg & 4)) cp_async16(dst0 + (uint32_t)(row * Cfg::ROWB) + (((uint32_t)my_chunk ^ swz_of(row)) << 4), src, ok ? 16u : 0u);
         }
-        const uint8_t* src = ok ? xb + (base_j[j] + tab) * ESZ + my_chunk * 16 : xb;   // !ok: 0 bytes read, zero fill
-        const int row = j * RPI + my_row0;
-        if (!(p.dbg & 4)) cp_async16(dst0 + (uint32_t)(row * Cfg::ROWB) + (((uint32_t)my_chunk ^ swz_of(row)) << 4), src, ok ? 16u : 0u);
       }
-      ld_kb += NG;
+      ld_kb += NG * KSUB;
       while (ld_kb >= KB) { ld_kb -= KB; ++ld_tl; }
     };
 
@@ -298,13 +309,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
         if (it < total_it) {
           cp_async_wait<DEPTH - 1>();          // this lane's copies for iteration `it` have landed in slot u ...
           __syncwarp();                        // ... and so have the other lanes' (the slab row is written by NVR lanes)
-          uint4 b[NV];
-          {
-            const uint32_t rowp = slab + (uint32_t)(u * 32 * Cfg::ROWB) + (uint32_t)(lane * Cfg::ROWB);
+          uint4 b[KSUB][NV];
 #pragma unroll
-            for (int c = 0; c < NV; ++c) b[c] = lds128(rowp + (((uint32_t)c ^ swz_of(lane)) << 4));
+          for (int sb = 0; sb < KSUB; ++sb) {
+            const uint32_t rowp = slab + (uint32_t)u * kSlot + (uint32_t)(sb * 32 * Cfg::ROWB) + (uint32_t)(lane * Cfg::ROWB);
+#pragma unroll
+            for (int c = 0; c < NV; ++c) b[sb][c] = lds128(rowp + (((uint32_t)c ^ swz_of(lane)) << 4));
           }
-          __syncwarp();                        // every lane has read its row: slot u may be refilled
+          __syncwarp();                        // every lane has read its rows: slot u may be refilled
           const int img = img_of[u];
           if (it + NG * DEPTH < total_it) issue(u, img_of[u]);
           cp_async_commit();
@@ -315,45 +327,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
             if (p.dbg & 1) {
               mbar_arrive(&full_bar[pstage]);
             } else {
-              mbar_arrive_expect_tx(&full_bar[pstage], Cfg::B_BYTES * (SPLIT ? 2 : 1));
-              bulk_g2s(b_hi, p.b_hi + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
-              if constexpr (SPLIT) bulk_g2s(b_hi + Cfg::B_BYTES, p.b_lo + (int64_t)img * (BN * 32), Cfg::B_BYTES, &full_bar[pstage]);
+              mbar_arrive_expect_tx(&full_bar[pstage], Cfg::STAGE_BYTES);
+              bulk_g2s(b_hi, p.b_hi + (int64_t)img * (BN * 32), KSUB * Cfg::B_BYTES, &full_bar[pstage]);
+              if constexpr (SPLIT)
+                bulk_g2s(b_hi + KSUB * Cfg::B_BYTES, p.b_lo + (int64_t)img * (BN * 32), KSUB * Cfg::B_BYTES, &full_bar[pstage]);
             }
           }
-          // this thread's row of the A operand goes straight into tensor memory: lane = row, 32 columns = 32 k
-          const uint32_t taddr = tmem_base + ((uint32_t)(wq4 * 32) << 16) + kAcol0 + (uint32_t)(pstage * Cfg::ACOLS);
-          uint32_t hi[32];
-          if constexpr (Cfg::U8) {
-            const uint32_t wds[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+          // this thread's row of the A operand goes straight into tensor memory: lane = row, 32 columns per K-block
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {     // small integers are exact in tf32
-              hi[c * 4 + 0] = __float_as_uint(u8_to_f32(wds[c], 0));
-              hi[c * 4 + 1] = __float_as_uint(u8_to_f32(wds[c], 1));
-              hi[c * 4 + 2] = __float_as_uint(u8_to_f32(wds[c], 2));
-              hi[c * 4 + 3] = __float_as_uint(u8_to_f32(wds[c], 3));
-            }
-            if (!(p.dbg & 2)) tmem_st32(taddr, hi);
-          } else {
-            // TF32X3: hi = a with the 13 low mantissa bits cleared (1 LOP), lo = a - hi exactly (1 FADD); the tensor core
-            // reads only the tf32 bits of lo, an error of 2^-21 |a|.  Plain TF32 rounds to nearest (2 integer ops).
+          for (int sb = 0; sb < KSUB; ++sb) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq4 * 32) << 16) + kAcol0 + (uint32_t)(pstage * Cfg::SCOLS + sb * Cfg::ACOLS);
+            uint32_t hi[32];
+            if constexpr (Cfg::U8) {
+              const uint32_t wds[8] = {b[sb][0].x, b[sb][0].y, b[sb][0].z, b[sb][0].w, b[sb][1].x, b[sb][1].y, b[sb][1].z, b[sb][1].w};
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              hi[c * 4 + 0] = Cfg::A_LO ? (b[c].x & 0xFFFFE000u) : tf32_rna_bits(b[c].x);
-              hi[c * 4 + 1] = Cfg::A_LO ? (b[c].y & 0xFFFFE000u) : tf32_rna_bits(b[c].y);
-              hi[c * 4 + 2] = Cfg::A_LO ? (b[c].z & 0xFFFFE000u) : tf32_rna_bits(b[c].z);
-              hi[c * 4 + 3] = Cfg::A_LO ? (b[c].w & 0xFFFFE000u) : tf32_rna_bits(b[c].w);
-            }
-            if (!(p.dbg & 2)) tmem_st32(taddr, hi);
-            if constexpr (Cfg::A_LO) {
-              uint32_t lo[32];
+              for (int c = 0; c < 8; ++c) {     // small integers are exact in tf32
+                hi[c * 4 + 0] = __float_as_uint(u8_to_f32(wds[c], 0));
+                hi[c * 4 + 1] = __float_as_uint(u8_to_f32(wds[c], 1));
+                hi[c * 4 + 2] = __float_as_uint(u8_to_f32(wds[c], 2));
+                hi[c * 4 + 3] = __float_as_uint(u8_to_f32(wds[c], 3));
+              }
+              if (!(p.dbg & 2)) tmem_st32(taddr, hi);
+            } else {
+              // TF32X3: hi = a with the 13 low mantissa bits cleared (1 LOP), lo = a - hi exactly (1 FADD); the tensor
+              // core reads only the tf32 bits of lo, an error of 2^-21 |a|.  Plain TF32 rounds to nearest (2 integer ops).
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                lo[c * 4 + 0] = __float_as_uint(__uint_as_float(b[c].x) - __uint_as_float(hi[c * 4 + 0]));
-                lo[c * 4 + 1] = __float_as_uint(__uint_as_float(b[c].y) - __uint_as_float(hi[c * 4 + 1]));
-                lo[c * 4 + 2] = __float_as_uint(__uint_as_float(b[c].z) - __uint_as_float(hi[c * 4 + 2]));
-                lo[c * 4 + 3] = __float_as_uint(__uint_as_float(b[c].w) - __uint_as_float(hi[c * 4 + 3]));
+                hi[c * 4 + 0] = Cfg::A_LO ? (b[sb][c].x & 0xFFFFE000u) : tf32_rna_bits(b[sb][c].x);
+                hi[c * 4 + 1] = Cfg::A_LO ? (b[sb][c].y & 0xFFFFE000u) : tf32_rna_bits(b[sb][c].y);
+                hi[c * 4 + 2] = Cfg::A_LO ? (b[sb][c].z & 0xFFFFE000u) : tf32_rna_bits(b[sb][c].z);
+                hi[c * 4 + 3] = Cfg::A_LO ? (b[sb][c].w & 0xFFFFE000u) : tf32_rna_bits(b[sb][c].w);
               }
-              if (!(p.dbg & 2)) tmem_st32(taddr + 32u, lo);
+              if (!(p.dbg & 2)) tmem_st32(taddr, hi);
+              if constexpr (Cfg::A_LO) {
+                uint32_t lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  lo[c * 4 + 0] = __float_as_uint(__uint_as_float(b[sb][c].x) - __uint_as_float(hi[c * 4 + 0]));
+                  lo[c * 4 + 1] = __float_as_uint(__uint_as_float(b[sb][c].y) - __uint_as_float(hi[c * 4 + 1]));
+                  lo[c * 4 + 2] = __float_as_uint(__uint_as_float(b[sb][c].z) - __uint_as_float(hi[c * 4 + 2]));
+                  lo[c * 4 + 3] = __float_as_uint(__uint_as_float(b[sb][c].w) - __uint_as_float(hi[c * 4 + 3]));
+                }
+                if (!(p.dbg & 2)) tmem_st32(taddr + 32u, lo);
+              }
             }
           }
           tmem_st_wait();                      // tcgen05.st complete ...
@@ -381,26 +397,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < KBS; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t b_hi = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES), b_lo = b_hi + Cfg::B_BYTES;
+          const uint32_t b_st = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
           if (leader) {
           if (!(p.dbg & 8)) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {     // K = 8 tf32 per instruction: 32 bytes of smem (B) / 8 TMEM columns (A)
-            const uint32_t ko = (uint32_t)ks * 32u;
-            uint32_t accum = (kb > 0 || ks > 0) ? 1u : 0u;
-            const uint32_t a_hi = tmem_base + kAcol0 + (uint32_t)(stage * Cfg::ACOLS) + (uint32_t)ks * 8u;
-            if constexpr (SPLIT) {
-              if constexpr (Cfg::A_LO) {
-                umma_tf32_ts(d_tmem, a_hi + 32u, make_sw128_desc(b_hi + ko), idesc, accum);
+          for (int sb = 0; sb < KSUB; ++sb) {
+            const uint32_t b_hi = b_st + (uint32_t)(sb * Cfg::B_BYTES), b_lo = b_hi + (uint32_t)(KSUB * Cfg::B_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {   // K = 8 tf32 per instruction: 32 bytes of smem (B) / 8 TMEM columns (A)
+              const uint32_t ko = (uint32_t)ks * 32u;
+              uint32_t accum = (kb > 0 || sb > 0 || ks > 0) ? 1u : 0u;
+              const uint32_t a_hi = tmem_base + kAcol0 + (uint32_t)(stage * Cfg::SCOLS + sb * Cfg::ACOLS) + (uint32_t)ks * 8u;
+              if constexpr (SPLIT) {
+                if constexpr (Cfg::A_LO) {
+                  umma_tf32_ts(d_tmem, a_hi + 32u, make_sw128_desc(b_hi + ko), idesc, accum);
+                  accum = 1u;
+                }
+                umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_lo + ko), idesc, accum);
                 accum = 1u;
               }
-              umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_lo + ko), idesc, accum);
-              accum = 1u;
+              umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_hi + ko), idesc, accum);
             }
-            umma_tf32_ts(d_tmem, a_hi, make_sw128_desc(b_hi + ko), idesc, accum);
           }
           }
           umma_commit(&empty_bar[stage]);      // stage reusable once these MMAs retire
@@ -496,13 +516,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-template <int BN, int MODE, bool SPLIT>
+template <int BN, int MODE, bool SPLIT, int KSUB>
 static int launch_tc_inst2(const paacb_ctx* ctx, const TcParams& p, int slot, cudaStream_t st) {
-  using Cfg = TcCfg<BN, MODE, SPLIT>;
+  using Cfg = TcCfg<BN, MODE, SPLIT, KSUB>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_tc_kernel<BN, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(igemm_tc_kernel<BN, MODE, SPLIT, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
       set_error("igemm_tc: cannot set %d bytes of dynamic shared memory", Cfg::SMEM_BYTES);
       return PAACB_ECUDA;
     }
@@ -511,14 +532,20 @@ static int launch_tc_inst2(const paacb_ctx* ctx, const TcParams& p, int slot, cu
   const uint32_t tiles = p.m_tiles * (uint32_t)p.n_tiles * (uint32_t)p.classes;
   const unsigned grid = tiles < (uint32_t)ctx->num_sms ? tiles : (unsigned)ctx->num_sms;
   PAACB_LAUNCH_BEGIN(ctx, slot, st);
-  igemm_tc_kernel<BN, MODE, SPLIT><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(p);
+  igemm_tc_kernel<BN, MODE, SPLIT, KSUB><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(p);
   PAACB_LAUNCH_END(ctx, slot, st);
   return PAACB_OK;
 }
 
 template <int BN, int MODE>
 static int launch_tc_inst(const paacb_ctx* ctx, const TcParams& p, int slot, int split3, cudaStream_t st) {
-  return split3 ? launch_tc_inst2<BN, MODE, true>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false>(ctx, p, slot, st);
+  // K-blocks per pipeline stage: 4 for the uint8 layer (32-byte rows: small stages are all handshake); the fp32
+  // layers measured faster with single-K-block stages (deeper TMEM / smem pipelines, fewer live registers)
+  constexpr int KS = (MODE == TC_FWD_U8) ? 4 : 1;
+  if (KS > 1 && p.kblocks % KS == 0 && !(ctx->dbg & 32)) {
+    return split3 ? launch_tc_inst2<BN, MODE, true, KS>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, KS>(ctx, p, slot, st);
+  }
+  return split3 ? launch_tc_inst2<BN, MODE, true, 1>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, 1>(ctx, p, slot, st);
 }
 
 static int pick_bn(int n) { return (n % 128 == 0) ? 128 : ((n % 64 == 0) ? 64 : ((n % 32 == 0) ? 32 : 0)); }
