@@ -46,7 +46,7 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='environments per GPU')
     ap.add_argument('--arch', default='NATURE', choices=['NATURE', 'NIPS'])
-    ap.add_argument('--math', default=os.environ.get('PAACB_BENCH_MATH', 'tf32x3'), choices=['fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--math', default=os.environ.get('PAACB_BENCH_MATH', 'bf16x3'), choices=['fp32', 'tf32x3', 'tf32', 'bf16x3'])
     ap.add_argument('--frame_pool', type=int, default=8, help='device frame buffers rotated between env steps')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
@@ -248,7 +248,12 @@ def run_b200(args):
 
     # ---- per-kernel roofline table (device time from CUDA events on the launching stream) ---------------
     hbm_peak, tc_burst, tc_sust, peak_kind = load_peaks()
-    tf32_peak = 0.5 * tc_sust                       # tf32 issues at half the bf16 rate; kernels are timed inside a long step
+    # kernels are timed inside a long step -> sustained figure; kind::tf32 issues at half the bf16 rate
+    bf16_math = args.math == 'bf16x3'
+    tf32_peak = tc_sust if bf16_math else 0.5 * tc_sust
+    peak_note = ('bf16_tflops_sustained (kind::f16 on bf16-split operands, 3 MMAs per algorithmic product: 1/3 is the ceiling)'
+                 if bf16_math else
+                 '0.5 x bf16_tflops_sustained (kind::tf32 / fp32 contraction; tf32 issues at half the bf16 rate)')
     B = N * T
     fwd_samples = (T * N + N + B) * args.steps       # acting + bootstrap + training forward
     kernels = []
@@ -284,8 +289,7 @@ def run_b200(args):
                 'launches': dom['launches'], 'avg_launch_ms': dom['ms'] / dom['launches'],
                 'algo_per_launch': dom['algo_per_launch'],
                 'peak_source': ('%s: MEASURED_PEAKS.json ' % peak_kind) +
-                               ('0.5 x bf16_tflops_sustained (kind::tf32 / fp32 contraction; tf32 issues at half the bf16 rate)'
-                                if dom['bound'] == 'tensor' else 'hbm_gbs')}
+                               (peak_note if dom['bound'] == 'tensor' else 'hbm_gbs')}
     # nominal whole-step fraction: contract flops per env-step / tf32 peak
     flops_per_env_step = 71.96e6 if args.arch == 'NATURE' else 21.65e6
     step_frac = (value / world) * flops_per_env_step / 1e12 / tf32_peak
@@ -337,10 +341,10 @@ def run_b200(args):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'update_ms': ms_per_step,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': {'fp32': 'f32', 'tf32x3': 'tf32x3', 'tf32': 'tf32'}[args.math], 'data': 'synthetic',
+                'dtype': {'fp32': 'f32', 'tf32x3': 'tf32x3', 'tf32': 'tf32', 'bf16x3': 'bf16x3'}[args.math], 'data': 'synthetic',
                 'config': workload_config(args, world), 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'cpu_baseline': cpu,
-                'step_fraction_of_tf32_peak': step_frac, 'kernel_time_accounted': accounted / ms_total,
+                'step_fraction_of_tensor_peak': step_frac, 'kernel_time_accounted': accounted / ms_total,
                 'kernels': [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels],
                 'loss': loss_val}
         print(json.dumps(line), flush=True)

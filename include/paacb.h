@@ -43,7 +43,9 @@ enum { PAACB_ARCH_NIPS = 0, PAACB_ARCH_NATURE = 1 };
 /* arithmetic of the conv/fc contractions */
 enum { PAACB_MATH_FP32 = 0,      /* SIMT fp32 FFMA: the parity anchor */
        PAACB_MATH_TF32X3 = 1,    /* tcgen05 kind::tf32, split operands (hi*hi + hi*lo + lo*hi) */
-       PAACB_MATH_TF32 = 2 };    /* tcgen05 kind::tf32, operands rounded to nearest tf32 */
+       PAACB_MATH_TF32 = 2,      /* tcgen05 kind::tf32, operands rounded to nearest tf32 */
+       PAACB_MATH_BF16X3 = 3 };  /* tcgen05 kind::f16 on bf16-split operands (hi*hi + hi*lo + lo*hi), activations kept as
+                                    two bf16 planes, TMA-fed patch-resident implicit GEMMs; Nature architecture only */
 enum { PAACB_CLIP_IGNORE = 0, PAACB_CLIP_GLOBAL = 1 };   /* actor_learner.py:51-58 ('local' is broken upstream) */
 
 typedef struct paacb_ctx paacb_ctx;

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(HERE, 'libpaacb.so')
 
 PAACB_OK = 0
 ARCH_NIPS, ARCH_NATURE = 0, 1
-MATH_FP32, MATH_TF32X3, MATH_TF32 = 0, 1, 2
+MATH_FP32, MATH_TF32X3, MATH_TF32, MATH_BF16X3 = 0, 1, 2, 3
 CLIP_IGNORE, CLIP_GLOBAL = 0, 1
 MAX_ACTIONS = 18
 

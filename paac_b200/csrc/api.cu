@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc2.cuh"
 
 namespace paacb {
 
@@ -162,6 +163,10 @@ int paacb_destroy(paacb_ctx* ctx) {
   if (ctx->wpack_lo != nullptr) cudaFree(ctx->wpack_lo);
   if (ctx->wpack_d_hi != nullptr) cudaFree(ctx->wpack_d_hi);
   if (ctx->wpack_d_lo != nullptr) cudaFree(ctx->wpack_d_lo);
+  if (ctx->wb_f_hi != nullptr) cudaFree(ctx->wb_f_hi);
+  if (ctx->wb_f_lo != nullptr) cudaFree(ctx->wb_f_lo);
+  if (ctx->wb_d_hi != nullptr) cudaFree(ctx->wb_d_hi);
+  if (ctx->wb_d_lo != nullptr) cudaFree(ctx->wb_d_lo);
   delete ctx;
   return PAACB_OK;
 }
@@ -227,8 +232,32 @@ int paacb_profile_read(const paacb_ctx* ctx, int slot, char* name, int name_cap,
 
 int paacb_set_math(paacb_ctx* ctx, int math_mode) {
   PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
-  PAACB_CHECK_ARG(math_mode == PAACB_MATH_FP32 || math_mode == PAACB_MATH_TF32X3 || math_mode == PAACB_MATH_TF32,
-                  "unknown math mode");
+  PAACB_CHECK_ARG(math_mode == PAACB_MATH_FP32 || math_mode == PAACB_MATH_TF32X3 || math_mode == PAACB_MATH_TF32 ||
+                  math_mode == PAACB_MATH_BF16X3, "unknown math mode");
+  if (math_mode == PAACB_MATH_BF16X3) {
+    if (!bf16x3_supported(ctx)) {
+      set_error("paacb_set_math: PAACB_MATH_BF16X3 covers the Nature architecture only (use PAACB_MATH_TF32X3)");
+      return PAACB_EUNSUPPORTED;
+    }
+    if (ctx->wb_f_hi == nullptr) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(ctx->device);
+      const size_t bytes = (size_t)ctx->param_count * sizeof(uint16_t) + 256;
+      const cudaError_t e1 = cudaMalloc(&ctx->wb_f_hi, bytes);
+      const cudaError_t e2 = cudaMalloc(&ctx->wb_f_lo, bytes);
+      const cudaError_t e3 = cudaMalloc(&ctx->wb_d_hi, bytes);
+      const cudaError_t e4 = cudaMalloc(&ctx->wb_d_lo, bytes);
+      cudaSetDevice(cur);
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+        cudaGetLastError();
+        set_error("paacb_set_math: cannot allocate %zu bytes for the bf16 weight images", 4 * bytes);
+        return PAACB_ECUDA;
+      }
+    }
+    ctx->math = math_mode;
+    return PAACB_OK;
+  }
   if (math_mode != PAACB_MATH_FP32 && ctx->wpack_hi == nullptr) {
     // context-owned workspace (like a TMA descriptor): the prepacked tf32 weight images, 2 x P words
     int cur = 0;
@@ -280,7 +309,8 @@ int paacb_tensor_info(const paacb_ctx* ctx, int index, char* name, int name_cap,
 }
 
 int64_t paacb_forward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
-  return ctx ? ctx->act_floats_per_sample * batch : PAACB_EINVAL;
+  // activations (fp32, or two bf16 planes per tensor: the same bytes) + the bf16 image of the states (BF16X3 mode)
+  return ctx ? (ctx->act_floats_per_sample + kStateElems / 2) * batch : PAACB_EINVAL;
 }
 int64_t paacb_backward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
   return ctx ? ctx->act_floats_per_sample * batch : PAACB_EINVAL;
@@ -320,6 +350,20 @@ int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint
   PAACB_CHECK_ARG(((uintptr_t)d_params & 15) == 0 && ((uintptr_t)d_states & 15) == 0 && ((uintptr_t)d_fwd_ws & 15) == 0,
                   "params / states / workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->math == PAACB_MATH_BF16X3) {
+    if (batch == 0) return PAACB_OK;
+    const int L = ctx->n_layers;
+    int rc = launch_pack_bf16_weights(ctx, d_params, st);      // the caller may have changed the parameters
+    if (rc == PAACB_OK)
+      rc = launch_states_to_bf16(ctx, d_states, reinterpret_cast<uint8_t*>(d_fwd_ws) + ctx->act_floats_per_sample * batch * 4, batch, st);
+    for (int l = 0; l < L - 1 && rc == PAACB_OK; ++l) rc = launch_conv_fwd_bf16(ctx, l, d_params, d_fwd_ws, batch, st);
+    if (rc == PAACB_OK) rc = launch_fc_fwd_bf16(ctx, L - 1, d_params, d_fwd_ws, batch, st);
+    if (rc != PAACB_OK) return rc;
+    const Planes hp = layer_planes(d_fwd_ws, ctx->layer[L - 1].out_act_off, ctx->feat, batch);
+    return launch_heads_fwd(ctx, nullptr, reinterpret_cast<const uint16_t*>(hp.hi), reinterpret_cast<const uint16_t*>(hp.lo),
+                            d_params + ctx->actor_w_off, d_params + ctx->actor_b_off, d_params + ctx->critic_w_off,
+                            d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms, d_actions, d_onehot, st);
+  }
   if (ctx->math != PAACB_MATH_FP32 && batch > 0) {
     // the caller may have changed the parameters since the last call: repack (a few microseconds)
     for (int l = 0; l < ctx->n_layers; ++l) {
@@ -333,7 +377,7 @@ int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint
     if (rc != PAACB_OK) return rc;
   }
   const float* h = d_fwd_ws + ctx->layer[ctx->n_layers - 1].out_act_off * batch;
-  return launch_heads_fwd(ctx, h, d_params + ctx->actor_w_off, d_params + ctx->actor_b_off,
+  return launch_heads_fwd(ctx, h, nullptr, nullptr, d_params + ctx->actor_w_off, d_params + ctx->actor_b_off,
                           d_params + ctx->critic_w_off, d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms,
                           d_actions, d_onehot, st);
 }
@@ -362,9 +406,26 @@ int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d
     return PAACB_ECUDA;
   }
   const int L = ctx->n_layers;
+  if (ctx->math == PAACB_MATH_BF16X3) {
+    if (batch == 0) return PAACB_OK;
+    const Planes hp = layer_planes(const_cast<float*>(d_fwd_ws), ctx->layer[L - 1].out_act_off, ctx->feat, batch);
+    const Planes dhp = layer_planes(d_bwd_ws, ctx->layer[L - 1].out_act_off, ctx->feat, batch);
+    int rc = launch_heads_bwd(ctx, nullptr, reinterpret_cast<const uint16_t*>(hp.hi), reinterpret_cast<const uint16_t*>(hp.lo),
+                              reinterpret_cast<uint16_t*>(dhp.hi), reinterpret_cast<uint16_t*>(dhp.lo),
+                              d_grads + ctx->layer[L - 1].b_off, d_params + ctx->actor_w_off, d_params + ctx->critic_w_off,
+                              d_dlogits, d_dv, batch, nullptr, d_grads + ctx->actor_w_off, d_grads + ctx->actor_b_off,
+                              d_grads + ctx->critic_w_off, d_grads + ctx->critic_b_off, st);
+    if (rc == PAACB_OK) rc = launch_pack_bf16_dgrad_weights(ctx, d_params, st);
+    // data gradients first (they produce the dZ planes and the bias gradients), then the weight gradients
+    if (rc == PAACB_OK) rc = launch_fc_dgrad_bf16(ctx, L - 1, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
+    for (int l = L - 2; l >= 1 && rc == PAACB_OK; --l) rc = launch_conv_dgrad_bf16(ctx, l, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
+    if (rc == PAACB_OK) rc = launch_fc_wgrad_bf16(ctx, L - 1, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
+    for (int l = L - 2; l >= 0 && rc == PAACB_OK; --l) rc = launch_conv_wgrad_bf16(ctx, l, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
+    return rc;
+  }
   const float* h = d_fwd_ws + ctx->layer[L - 1].out_act_off * batch;
   float* dh = d_bwd_ws + ctx->layer[L - 1].out_act_off * batch;
-  int rc = launch_heads_bwd(ctx, h, d_params + ctx->actor_w_off, d_params + ctx->critic_w_off, d_dlogits, d_dv, batch,
+  int rc = launch_heads_bwd(ctx, h, nullptr, nullptr, nullptr, nullptr, nullptr, d_params + ctx->actor_w_off, d_params + ctx->critic_w_off, d_dlogits, d_dv, batch,
                             dh, d_grads + ctx->actor_w_off, d_grads + ctx->actor_b_off, d_grads + ctx->critic_w_off,
                             d_grads + ctx->critic_b_off, st);
   if (rc != PAACB_OK) return rc;

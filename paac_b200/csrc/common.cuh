@@ -77,6 +77,11 @@ struct paacb_ctx {
   uint32_t* wpack_lo;
   uint32_t* wpack_d_hi;         // the transposed / per-stride-class images the data-gradient kernels read
   uint32_t* wpack_d_lo;
+  // bf16-split path (PAACB_MATH_BF16X3): weights as (hi, lo) bf16 images, forward (transposed) and data-gradient layouts
+  uint16_t* wb_f_hi;
+  uint16_t* wb_f_lo;
+  uint16_t* wb_d_hi;
+  uint16_t* wb_d_lo;
   int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };
 
@@ -131,10 +136,13 @@ int launch_conv_wgrad_simt(const paacb_ctx* ctx, const LayerGeom& g, const void*
                            int64_t batch, cudaStream_t st);
 
 // heads (heads.cu)
-int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const float* wa, const float* ba, const float* wc,
+// h == nullptr: the hidden activation is given as bf16-split planes (h_hi, h_lo)
+int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi, const uint16_t* h_lo, const float* wa, const float* ba, const float* wc,
                      const float* bc, int64_t batch, float* pi, float* v, const float* uniforms, int32_t* actions,
                      float* onehot, cudaStream_t st);
-int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const float* wa, const float* wc, const float* dlogits,
+// dh == nullptr: dh is written as bf16-split planes (dh_hi, dh_lo) and its column sums are added to dbh
+int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi, const uint16_t* h_lo, uint16_t* dh_hi,
+                     uint16_t* dh_lo, float* dbh, const float* wa, const float* wc, const float* dlogits,
                      const float* dv, int64_t batch, float* dh, float* dwa, float* dba, float* dwc, float* dbc,
                      cudaStream_t st);
 

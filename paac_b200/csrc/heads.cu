@@ -9,14 +9,22 @@
 // Backward: dWa = h^T dlogits, dba = colsum(dlogits), dWc = h^T dv, dbc = sum(dv),
 //           dh = (dlogits Wa^T + dv Wc^T) * [h > 0]   (ReLU mask of the hidden layer fused).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace paacb {
+
+// bf16-split activations (PAACB_MATH_BF16X3): value = float(hi) + float(lo)
+__device__ __forceinline__ float split_load(const uint16_t* hi, const uint16_t* lo, int64_t i) {
+  return __uint_as_float((uint32_t)__ldg(hi + i) << 16) + __uint_as_float((uint32_t)__ldg(lo + i) << 16);
+}
+
 
 constexpr int kMaxA = PAACB_MAX_ACTIONS;
 constexpr int kHeadWarps = 8;
 
 __global__ void __launch_bounds__(kHeadWarps * 32)
-heads_fwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, const float* __restrict__ ba,
+heads_fwd_kernel(const float* __restrict__ h, const uint16_t* __restrict__ h_hi, const uint16_t* __restrict__ h_lo,
+                 const float* __restrict__ wa, const float* __restrict__ ba,
                  const float* __restrict__ wc, const float* __restrict__ bc, int64_t batch, int F, int A,
                  float* __restrict__ pi, float* __restrict__ v, const float* __restrict__ uniforms,
                  int32_t* __restrict__ actions, float* __restrict__ onehot) {
@@ -32,9 +40,8 @@ heads_fwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, cons
     float acc[kMaxA + 1];
 #pragma unroll
     for (int a = 0; a <= kMaxA; ++a) acc[a] = 0.f;
-    const float* hr = h + b * F;
     for (int f = lane; f < F; f += 32) {
-      const float hv = __ldg(hr + f);
+      const float hv = (h != nullptr) ? __ldg(h + b * F + f) : split_load(h_hi, h_lo, b * F + f);
       const float* wr = sw + f * A1;
 #pragma unroll
       for (int a = 0; a <= kMaxA; ++a)
@@ -85,7 +92,9 @@ constexpr int kHbChunk = 64;     // samples per CTA
 
 template <int FPT>   // features per thread: F = FPT * 256
 __global__ void __launch_bounds__(kHbThreads)
-heads_bwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, const float* __restrict__ wc,
+heads_bwd_kernel(const float* __restrict__ h, const uint16_t* __restrict__ h_hi, const uint16_t* __restrict__ h_lo,
+                 uint16_t* __restrict__ dh_hi, uint16_t* __restrict__ dh_lo, float* __restrict__ dbh,
+                 const float* __restrict__ wa, const float* __restrict__ wc,
                  const float* __restrict__ dlogits, const float* __restrict__ dv, int64_t batch, int F, int A,
                  float* __restrict__ dh, float* __restrict__ dwa, float* __restrict__ dba, float* __restrict__ dwc,
                  float* __restrict__ dbc) {
@@ -100,9 +109,11 @@ heads_bwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, cons
   }
   float wreg[FPT][kMaxA + 1];
   float gacc[FPT][kMaxA + 1];
+  float dsum[FPT];
 #pragma unroll
   for (int q = 0; q < FPT; ++q) {
     const int f = tid + q * kHbThreads;
+    dsum[q] = 0.f;
 #pragma unroll
     for (int a = 0; a <= kMaxA; ++a) {
       gacc[q][a] = 0.f;
@@ -117,7 +128,8 @@ heads_bwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, cons
     for (int q = 0; q < FPT; ++q) {
       const int f = tid + q * kHbThreads;
       if (f < F) {
-        const float hv = __ldg(h + (b0 + r) * F + f);
+        const int64_t hi_ = (b0 + r) * F + f;
+        const float hv = (h != nullptr) ? __ldg(h + hi_) : split_load(h_hi, h_lo, hi_);
         float g = 0.f;
 #pragma unroll
         for (int a = 0; a <= kMaxA; ++a) {
@@ -127,7 +139,15 @@ heads_bwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, cons
             g = fmaf(d, wreg[q][a], g);
           }
         }
-        dh[(b0 + r) * F + f] = hv > 0.f ? g : 0.f;
+        const float gm = hv > 0.f ? g : 0.f;
+        if (dh != nullptr) {
+          dh[hi_] = gm;
+        } else {      // bf16-split planes for the tensor-core data/weight-gradient kernels; db of the hidden layer here
+          const __nv_bfloat16 gh = __float2bfloat16_rn(gm);
+          dh_hi[hi_] = __bfloat16_as_ushort(gh);
+          dh_lo[hi_] = __bfloat16_as_ushort(__float2bfloat16_rn(gm - __bfloat162float(gh)));
+          dsum[q] += gm;
+        }
       }
     }
   }
@@ -140,6 +160,7 @@ heads_bwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, cons
         if (a < A) atomicAdd(dwa + (int64_t)f * A + a, gacc[q][a]);
         if (a == A) atomicAdd(dwc + f, gacc[q][a]);
       }
+      if (dbh != nullptr) atomicAdd(dbh + f, dsum[q]);
     }
   }
   if (tid < A1) {
@@ -149,7 +170,7 @@ heads_bwd_kernel(const float* __restrict__ h, const float* __restrict__ wa, cons
   }
 }
 
-int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const float* wa, const float* ba, const float* wc,
+int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi, const uint16_t* h_lo, const float* wa, const float* ba, const float* wc,
                      const float* bc, int64_t batch, float* pi, float* v, const float* uniforms, int32_t* actions,
                      float* onehot, cudaStream_t st) {
   if (batch == 0) return PAACB_OK;
@@ -159,13 +180,14 @@ int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const float* wa, cons
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)F * (A + 1) * sizeof(float);
   PAACB_LAUNCH_BEGIN(ctx, K_HEADS_FWD, st);
-  heads_fwd_kernel<<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h, wa, ba, wc, bc, batch, F, A, pi, v, uniforms,
+  heads_fwd_kernel<<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h, h_hi, h_lo, wa, ba, wc, bc, batch, F, A, pi, v, uniforms,
                                                                      actions, onehot);
   PAACB_LAUNCH_END(ctx, K_HEADS_FWD, st);
   return PAACB_OK;
 }
 
-int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const float* wa, const float* wc, const float* dlogits,
+int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi, const uint16_t* h_lo, uint16_t* dh_hi,
+                     uint16_t* dh_lo, float* dbh, const float* wa, const float* wc, const float* dlogits,
                      const float* dv, int64_t batch, float* dh, float* dwa, float* dba, float* dwc, float* dbc,
                      cudaStream_t st) {
   if (batch == 0) return PAACB_OK;
@@ -174,9 +196,9 @@ int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const float* wa, cons
   if (F > 2 * kHbThreads) { set_error("heads_bwd: hidden width > 512 unsupported"); return PAACB_EUNSUPPORTED; }
   PAACB_LAUNCH_BEGIN(ctx, K_HEADS_BWD, st);
   if (F <= kHbThreads)
-    heads_bwd_kernel<1><<<blocks, kHbThreads, 0, st>>>(h, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
+    heads_bwd_kernel<1><<<blocks, kHbThreads, 0, st>>>(h, h_hi, h_lo, dh_hi, dh_lo, dbh, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
   else
-    heads_bwd_kernel<2><<<blocks, kHbThreads, 0, st>>>(h, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
+    heads_bwd_kernel<2><<<blocks, kHbThreads, 0, st>>>(h, h_hi, h_lo, dh_hi, dh_lo, dbh, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
   PAACB_LAUNCH_END(ctx, K_HEADS_BWD, st);
   return PAACB_OK;
 }

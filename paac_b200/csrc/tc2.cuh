@@ -1,0 +1,47 @@
+// Shared declarations of the bf16-split tensor-core path (PAACB_MATH_BF16X3): tensor-map helper, workspace layout,
+// per-layer geometry of the patch-resident implicit GEMMs.
+#pragma once
+#include <cuda.h>          // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched from the driver at run time
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace paacb {
+
+// ---- host: tensor maps ------------------------------------------------------------------------------
+// rank-`rank` bf16 tensor, dims innermost first, strides in bytes for dims 1..rank-1, zero fill out of bounds.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes /* 32, 64, 128 */);
+
+// ---- workspace layout (bytes) -------------------------------------------------------------------------
+// forward / backward workspace, bf16-split mode: for layer l the region [out_act_off(l) * batch * 4, +E_l * batch * 4)
+// holds the hi plane (E_l * batch bf16) followed by the lo plane; value = float(hi) + float(lo).
+// The forward workspace additionally holds the bf16 image of the uint8 states after all activations.
+struct Planes {
+  uint8_t* hi;
+  uint8_t* lo;
+};
+__host__ __device__ inline Planes layer_planes(void* ws, int64_t off_floats_per_sample, int64_t elems_per_sample, int64_t batch) {
+  Planes p;
+  p.hi = reinterpret_cast<uint8_t*>(ws) + off_floats_per_sample * batch * 4;
+  p.lo = p.hi + elems_per_sample * batch * 2;
+  return p;
+}
+constexpr int64_t kStateElems = (int64_t)PAACB_OBS * PAACB_OBS * PAACB_STACK;   // 28,224
+
+// ---- launchers (tc2_*.cu) ---------------------------------------------------------------------------
+bool bf16x3_supported(const paacb_ctx* ctx);
+int launch_states_to_bf16(const paacb_ctx* ctx, const uint8_t* states, void* out_bf16, int64_t batch, cudaStream_t st);
+int launch_pack_bf16_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st);          // forward images
+int launch_pack_bf16_dgrad_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st);    // data-gradient images
+int launch_conv_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st);
+int launch_fc_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st);
+int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,
+                           cudaStream_t st);
+int launch_fc_dgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,
+                         cudaStream_t st);
+int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, const void* bwd_ws, float* grads,
+                           int64_t batch, cudaStream_t st);
+int launch_fc_wgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, const void* bwd_ws, float* grads,
+                         int64_t batch, cudaStream_t st);
+
+}  // namespace paacb

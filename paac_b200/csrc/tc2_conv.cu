@@ -1,0 +1,635 @@
+// bf16-split tensor-core path, part 1: patch-resident implicit GEMMs for the conv layers (forward and data-gradient),
+// plus the small producers of their operands (uint8 -> bf16 states, packed weight images) and the tensor-map helper.
+//
+// Design (sm_100a):
+//  * Activations live in HBM as TWO bf16 planes, value = hi + lo (|x - hi - lo| <= 2^-18 |x|).  A product is evaluated as
+//    hi*hi + hi*lo + lo*hi in three kind::f16 MMAs with fp32 accumulation in TMEM: the dropped lo*lo term and the
+//    residuals are ~2^-17 relative, an order of magnitude inside the 1e-4 parity bar, at twice the MMA rate and half
+//    the operand bytes of the tf32x3 scheme.  uint8 pixels are exact in bf16 (conv1 needs two MMAs per K-step).
+//  * No im2col, neither in HBM nor in shared memory.  The activation patch a tile of 128 output positions needs is
+//    landed ONCE by the TMA engine, row-parity plane by row-parity plane, as rows of s*C consecutive channels
+//    (32 B for conv1, 128 B for conv2/conv3).  Output positions are enumerated over the (padded) INPUT grid, so the
+//    operand of filter tap (kh, kw) is the same patch at a byte offset: every tap is just another start address in
+//    the MMA's shared-memory descriptor (the absolute-address swizzle that makes this legal was measured, tc_ptx.cuh).
+//    Shared-memory fill traffic is 1x the input instead of the 4-9x an im2col-style tile pipeline re-reads.
+//  * The layer's weights (both bf16 pieces, <= 144 KB) stay resident in shared memory for the whole kernel.
+//  * Persistent CTA per SM: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue
+//    (tcgen05.ld, bias + ReLU or ReLU-mask, bf16 split, 16-byte stores; bias gradients as warp-transposed column sums).
+//    Accumulators are double-buffered in TMEM; patch slots form an mbarrier ring.
+#include "tc2.cuh"
+
+namespace paacb {
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return PAACB_ECUDA;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides_bytes[i - 1];
+  }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r, rank,
+              (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0), (unsigned long long)(rank > 2 ? gd[2] : 0),
+              (unsigned long long)(rank > 3 ? gd[3] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0);
+    return PAACB_ECUDA;
+  }
+  return PAACB_OK;
+}
+
+bool bf16x3_supported(const paacb_ctx* ctx) { return ctx->arch == PAACB_ARCH_NATURE; }
+
+// ------------------------------------------------------------------------------------------------
+// operand producers
+// ------------------------------------------------------------------------------------------------
+// uint8 NHWC states -> bf16 (exact), 16 pixels-channels per thread
+__global__ void states_to_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n16) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(in + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float f0 = (float)(w[j] & 0xffu), f1 = (float)((w[j] >> 8) & 0xffu), f2 = (float)((w[j] >> 16) & 0xffu),
+                  f3 = (float)(w[j] >> 24);
+      o[2 * j] = (__float_as_uint(f0) >> 16) | (__float_as_uint(f1) & 0xffff0000u);      // small integers: truncation is exact
+      o[2 * j + 1] = (__float_as_uint(f2) >> 16) | (__float_as_uint(f3) & 0xffff0000u);
+    }
+    out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+int launch_states_to_bf16(const paacb_ctx* ctx, const uint8_t* states, void* out_bf16, int64_t batch, cudaStream_t st) {
+  const int64_t n16 = batch * kStateElems / 16;
+  if (n16 == 0) return PAACB_OK;
+  int64_t blocks = (n16 + 255) / 256;
+  const int64_t cap = (int64_t)ctx->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  PAACB_LAUNCH_BEGIN(ctx, K_PACK, st);
+  states_to_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(states),
+                                                          reinterpret_cast<uint4*>(out_bf16), n16);
+  PAACB_LAUNCH_END(ctx, K_PACK, st);
+  return PAACB_OK;
+}
+
+// forward image: Wp[n][k] = W[k][n] as (hi, lo) bf16, row-major [N][K] (the B operand, K-major)
+__global__ void pack_bf16_transpose_kernel(const float* __restrict__ w, int K, int N, uint16_t* __restrict__ hi,
+                                           uint16_t* __restrict__ lo) {
+  const int64_t total = (int64_t)K * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / N), n = (int)(i - (int64_t)k * N);       // coalesced reads of W
+    uint16_t h, l;
+    split_bf16(__ldg(w + i), h, l);
+    hi[(int64_t)n * K + k] = h;
+    lo[(int64_t)n * K + k] = l;
+  }
+}
+// same orientation as stored (fc data-gradient: rows = inputs, K = outputs)
+__global__ void pack_bf16_copy_kernel(const float* __restrict__ w, int64_t total, uint16_t* __restrict__ hi,
+                                      uint16_t* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    uint16_t h, l;
+    split_bf16(__ldg(w + i), h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+// conv data-gradient image: Wd[cls][ci][(tj*I + ti)*Cout + co] = W[ph + s*tj][pw + s*ti][ci][co], cls = ph*s + pw
+__global__ void pack_bf16_dgrad_kernel(const float* __restrict__ w, LayerGeom g, int J, int I, uint16_t* __restrict__ hi,
+                                       uint16_t* __restrict__ lo) {
+  const int s = g.stride;
+  const int Kd = J * I * g.N;
+  const int64_t total = (int64_t)s * s * g.C * Kd;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kd = (int)(i % Kd);
+    const int64_t rest = i / Kd;
+    const int ci = (int)(rest % g.C), cls = (int)(rest / g.C);
+    const int tap = kd / g.N, co = kd - tap * g.N;
+    const int tj = tap / I, ti = tap - tj * I;
+    const int kh = cls / s + s * tj, kw = cls % s + s * ti;
+    uint16_t h, l;
+    split_bf16(__ldg(w + ((int64_t)(kh * g.S + kw) * g.C + ci) * g.N + co), h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+int launch_pack_bf16_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st) {
+  for (int l = 0; l < ctx->n_layers; ++l) {
+    const LayerGeom& g = ctx->layer[l];
+    const int64_t total = (int64_t)g.K * g.N;
+    PAACB_LAUNCH_BEGIN(ctx, K_PACK, st);
+    pack_bf16_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(params + g.w_off, g.K, g.N,
+                                                                                ctx->wb_f_hi + g.w_off, ctx->wb_f_lo + g.w_off);
+    PAACB_LAUNCH_END(ctx, K_PACK, st);
+  }
+  return PAACB_OK;
+}
+
+int launch_pack_bf16_dgrad_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st) {
+  for (int l = 1; l < ctx->n_layers; ++l) {
+    const LayerGeom& g = ctx->layer[l];
+    const int64_t total = (int64_t)g.K * g.N;
+    PAACB_LAUNCH_BEGIN(ctx, K_PACK, st);
+    if (g.R == 1 && g.S == 1) {
+      pack_bf16_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(params + g.w_off, total, ctx->wb_d_hi + g.w_off,
+                                                                             ctx->wb_d_lo + g.w_off);
+    } else {
+      const int s = g.stride;
+      pack_bf16_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(params + g.w_off, g, g.R / s, g.S / s,
+                                                                              ctx->wb_d_hi + g.w_off, ctx->wb_d_lo + g.w_off);
+    }
+    PAACB_LAUNCH_END(ctx, K_PACK, st);
+  }
+  return PAACB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry of the five patch-resident GEMMs of the Nature network
+// ------------------------------------------------------------------------------------------------
+enum { G_FWD1 = 0, G_FWD2 = 1, G_FWD3 = 2, G_DG3 = 3, G_DG2 = 4 };
+
+template <int G>
+struct Geo;
+
+// conv1 forward: bf16 states [b,84,84,4], 8x8 stride 4 -> [b,20,20,32].  Unit = 4 pixels x 4 channels = 32 B; plane rho
+// holds the input rows ih = 4*q + rho; a K-step (16 elements) is half a filter row.
+template <>
+struct Geo<G_FWD1> {
+  static constexpr bool DGRAD = false, A_LO = false;
+  static constexpr int UB = 32, SWZ = SWZ_32B, PARTS = 4, WU = 21, HQ = 21, BOX_ROWS = 9, SLOT = 6144, NSLOTS = 8;
+  static constexpr int NACC = 1, BN = 32, KS = 4, KB = 4, OH = 20, OW = 20;
+  __host__ __device__ static constexpr int aoff(int t) { return ((t / 2) * 21 + (t % 2)) * 32; }
+  __host__ __device__ static constexpr int jw(int part, int t) { return (part + 4 * (t / 2)) * 2 + (t % 2); }
+};
+// conv2 forward: [b,20,20,32] 4x4 stride 2 -> [b,9,9,64].  Unit = 2 pixels x 32 channels = 128 B; 2 row-parity planes.
+template <>
+struct Geo<G_FWD2> {
+  static constexpr bool DGRAD = false, A_LO = true;
+  static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 2, WU = 10, HQ = 10, BOX_ROWS = 15, SLOT = 19456, NSLOTS = 5;
+  static constexpr int NACC = 1, BN = 64, KS = 16, KB = 8, OH = 9, OW = 9;
+  __host__ __device__ static constexpr int aoff(int t) { return ((t / 8) * 10 + ((t / 4) % 2)) * 128 + (t % 4) * 32; }
+  __host__ __device__ static constexpr int jw(int part, int t) { return ((part + 2 * (t / 8)) * 2 + ((t / 4) % 2)) * 4 + (t % 4); }
+};
+// conv3 forward: [b,9,9,64] 3x3 stride 1 -> [b,7,7,64].  Unit = 1 pixel x 64 channels = 128 B.
+template <>
+struct Geo<G_FWD3> {
+  static constexpr bool DGRAD = false, A_LO = true;
+  static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 9, HQ = 9, BOX_ROWS = 18, SLOT = 21504, NSLOTS = 3;
+  static constexpr int NACC = 1, BN = 64, KS = 36, KB = 9, OH = 7, OW = 7;
+  __host__ __device__ static constexpr int aoff(int t) { return (((t / 4) / 3) * 9 + ((t / 4) % 3)) * 128 + (t % 4) * 32; }
+  __host__ __device__ static constexpr int jw(int, int t) { return t; }
+};
+// conv3 data-gradient: dZ3 [b,7,7,64] -> dX [b,9,9,64]; one sample per tile, positions enumerated 11 wide over the
+// zero-padded dZ (TMA out-of-bounds fill), tap (kh, kw) reads position q + (2-kh)*11 + (2-kw).
+template <>
+struct Geo<G_DG3> {
+  static constexpr bool DGRAD = true, A_LO = true;
+  static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 9, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 4;
+  static constexpr int NACC = 1, BN = 64, KS = 36, KB = 9, OH = 9, OW = 9;       // OH/OW: valid rows/cols of the enumeration
+  static constexpr int PAD = 2, S = 1, XH = 9, XW = 9;
+  __host__ __device__ static constexpr int aoff(int t) { return ((2 - (t / 4) / 3) * 11 + (2 - (t / 4) % 3)) * 128 + (t % 4) * 32; }
+  __host__ __device__ static constexpr int jw(int, int t) { return t; }
+};
+// conv2 data-gradient: dZ2 [b,9,9,64] -> dX [b,20,20,32]; the four stride-parity classes are four accumulators over
+// the same resident dZ patch (class (ph, pw), tap (tj, ti) reads position q + (1-tj)*11 + (1-ti)).
+template <>
+struct Geo<G_DG2> {
+  static constexpr bool DGRAD = true, A_LO = true;
+  static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 10, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 5;
+  static constexpr int NACC = 4, BN = 32, KS = 16, KB = 4, OH = 10, OW = 10;
+  static constexpr int PAD = 1, S = 2, XH = 20, XW = 20;
+  __host__ __device__ static constexpr int aoff(int t) { return ((1 - (t / 4) / 2) * 11 + (1 - (t / 4) % 2)) * 128 + (t % 4) * 32; }
+  __host__ __device__ static constexpr int jw(int, int t) { return t; }
+};
+
+struct ConvKParams {
+  CUtensorMap tmA[2];      // source planes (hi, lo); forward: dims (unit, units/row, row parity, plane rows); dgrad: (C, OW, OH, b)
+  CUtensorMap tmW[2];      // packed weights (hi, lo): dims (K, rows)
+  int num_tiles;
+  int batch;
+  const float* bias;       // forward
+  float in_scale;          // forward: applied to the accumulator (1/255 for the uint8 layer, networks.py:115)
+  uint8_t* out_hi;         // output planes (bf16)
+  uint8_t* out_lo;
+  const uint8_t* mask_hi;  // dgrad: hi plane of the activation whose ReLU is differentiated (same shape as the output)
+  float* dbias;            // dgrad: += column sums of the output (the bias gradient of the layer that produced that activation)
+};
+
+template <int G>
+struct ConvKCfg {
+  using Ge = Geo<G>;
+  static constexpr int RING_BYTES = Ge::NSLOTS * Ge::SLOT;
+  static constexpr int ACC_W_BYTES = Ge::KB * Ge::BN * 128;                 // one accumulator's weights, one piece
+  static constexpr int PIECE_BYTES = Ge::NACC * ACC_W_BYTES;
+  static constexpr int W_BYTES = 2 * PIECE_BYTES;
+  static constexpr int BOX_BYTES = Ge::UB * Ge::WU * Ge::BOX_ROWS;
+  static constexpr int NBARS = 2 * Ge::NSLOTS + 1 + 4;
+  static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + 1024 /* alignment slack */ + NBARS * 8 + 16;
+  static constexpr int TMEM_COLS = 2 * Ge::NACC * Ge::BN;
+  static_assert(BOX_BYTES <= Ge::SLOT && Ge::SLOT % 1024 == 0, "slot too small");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
+};
+
+constexpr int kConvKThreads = 192;
+
+// lane j of the warp ends up with the sum over the warp's 32 lanes of v[j] (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int G>
+__global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_constant__ ConvKParams p) {
+  using Ge = Geo<G>;
+  using Cfg = ConvKCfg<G>;
+  constexpr int NSLOTS = Ge::NSLOTS, BN = Ge::BN, NACC = Ge::NACC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;
+  uint8_t* wsm = smem + Cfg::RING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + Cfg::W_BYTES);
+  uint64_t* full_bar = bars;                      // [NSLOTS] TMA -> MMA
+  uint64_t* empty_bar = bars + NSLOTS;            // [NSLOTS] MMA commit -> TMA
+  uint64_t* w_bar = bars + 2 * NSLOTS;            // weights resident
+  uint64_t* tfull_bar = w_bar + 1;                // [2] MMA commit -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSLOTS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmW[0]);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(w_bar, Cfg::W_BYTES);
+      for (int piece = 0; piece < 2; ++piece)
+        for (int acc = 0; acc < NACC; ++acc)
+          for (int kb = 0; kb < Ge::KB; ++kb)
+            tma_load_2d(wsm + piece * Cfg::PIECE_BYTES + (acc * Ge::KB + kb) * (BN * 128), &p.tmW[piece], kb * 64, acc * BN, w_bar);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int part = 0; part < Ge::PARTS; ++part) {
+#pragma unroll 1
+          for (int piece = 0; piece < (Ge::A_LO ? 2 : 1); ++piece) {
+            mbar_wait(&empty_bar[slot], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[slot], Cfg::BOX_BYTES);
+            uint8_t* dst = ring + slot * Ge::SLOT;
+            if constexpr (Ge::DGRAD) {
+              tma_load_4d(dst, &p.tmA[piece], 0, -Ge::PAD, -Ge::PAD, tile, &full_bar[slot]);
+            } else {
+              const int row0 = (int)(((int64_t)tile * 128) / Ge::WU);
+              tma_load_4d(dst, &p.tmA[piece], 0, 0, part, row0, &full_bar[slot]);
+            }
+            if (++slot == NSLOTS) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const bool leader = elect_one_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+    const uint64_t adesc0 = make_smem_desc(0, 16, 8 * Ge::UB, Ge::SWZ);
+    const uint64_t bdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
+    const uint32_t ring_a = smem_u32(ring);
+    const uint32_t w_hi = smem_u32(wsm), w_lo = w_hi + Cfg::PIECE_BYTES;
+    mbar_wait(w_bar, 0);
+    int slot = 0;
+    uint32_t phase = 0;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      const int ab = tl & 1;
+      const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+      mbar_wait(&tempty_bar[ab], aph ^ 1u);
+      tc_fence_after();
+      uint32_t rel = 0;
+      if constexpr (!Ge::DGRAD) rel = (uint32_t)(((int64_t)tile * 128) % Ge::WU) * Ge::UB;
+      const uint32_t d0 = tmem_base + (uint32_t)(ab * NACC * BN);
+#pragma unroll
+      for (int part = 0; part < Ge::PARTS; ++part) {
+#pragma unroll
+        for (int piece = 0; piece < (Ge::A_LO ? 2 : 1); ++piece) {
+          mbar_wait(&full_bar[slot], phase);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t a_base = ring_a + (uint32_t)(slot * Ge::SLOT) + rel;
+#pragma unroll
+            for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll
+              for (int t = 0; t < Ge::KS; ++t) {
+                const uint64_t ad = desc_with_addr(adesc0, a_base + (uint32_t)Ge::aoff(t));
+                const int jw = Ge::jw(part, t);
+                const uint32_t boff = (uint32_t)((acc * Ge::KB + jw / 4) * (BN * 128) + (jw % 4) * 32);
+                if (piece == 0) {
+                  umma_bf16(d0 + (uint32_t)(acc * BN), ad, desc_with_addr(bdesc0, w_hi + boff), idesc, (part | t) ? 1u : 0u);
+                  umma_bf16(d0 + (uint32_t)(acc * BN), ad, desc_with_addr(bdesc0, w_lo + boff), idesc, 1u);
+                } else {
+                  umma_bf16(d0 + (uint32_t)(acc * BN), ad, desc_with_addr(bdesc0, w_hi + boff), idesc, 1u);
+                }
+              }
+            }
+            umma_commit(&empty_bar[slot]);
+          }
+          __syncwarp();
+          if (++slot == NSLOTS) { slot = 0; phase ^= 1u; }
+        }
+      }
+      if (leader) umma_commit(&tfull_bar[ab]);
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int ew = warp & 3;                     // TMEM lane quarter this warp may access
+    const int r = ew * 32 + lane;                // tile row of this thread
+    float bsum[NACC == 1 ? BN / 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (NACC == 1 ? BN / 32 : 1); ++i) bsum[i] = 0.f;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      const int ab = tl & 1;
+      const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+      // row -> output pixel
+      bool ok;
+      int64_t pix = 0;          // forward: output pixel index; dgrad: (sample, qh, qw) resolved per class below
+      int qh = 0, qw = 0;
+      if constexpr (Ge::DGRAD) {
+        qh = r / Ge::WU;
+        qw = r - qh * Ge::WU;
+        ok = (qh < Ge::OH) && (qw < Ge::OW);
+      } else {
+        const int64_t q = (int64_t)tile * 128 + r;
+        const int64_t prow = q / Ge::WU;
+        const int ju = (int)(q - prow * Ge::WU);
+        const int64_t n = prow / Ge::HQ;
+        const int oh = (int)(prow - n * Ge::HQ);
+        ok = (ju < Ge::OW) && (oh < Ge::OH) && (n < p.batch);
+        pix = (n * Ge::OH + oh) * Ge::OW + ju;
+      }
+      mbar_wait(&tfull_bar[ab], aph);
+      tc_fence_after();
+#pragma unroll
+      for (int acc = 0; acc < NACC; ++acc) {
+        int64_t obase;          // element index of this row's first output channel
+        if constexpr (Ge::DGRAD) {
+          const int ih = Ge::S * qh + (NACC > 1 ? acc / 2 : 0), iw = Ge::S * qw + (NACC > 1 ? acc % 2 : 0);
+          obase = (((int64_t)tile * Ge::XH + ih) * Ge::XW + iw) * BN;
+        } else {
+          obase = pix * BN;
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * NACC * BN + acc * BN + c0), v);
+          tmem_ld_wait();
+          float o[32];
+          if constexpr (Ge::DGRAD) {
+            uint32_t mw[16];
+            if (ok) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask_hi + (obase + c0) * 2);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 m = __ldg(mp + j);
+                mw[4 * j] = m.x; mw[4 * j + 1] = m.y; mw[4 * j + 2] = m.z; mw[4 * j + 3] = m.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) mw[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              // bf16 > 0  <=>  sign clear and magnitude non-zero
+              const uint32_t a0 = mw[j] & 0xffffu, a1 = mw[j] >> 16;
+              o[2 * j] = (ok && a0 != 0u && a0 < 0x8000u) ? __uint_as_float(v[2 * j]) : 0.f;
+              o[2 * j + 1] = (ok && a1 != 0u && a1 < 0x8000u) ? __uint_as_float(v[2 * j + 1]) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(fmaf(__uint_as_float(v[j]), p.in_scale, __ldg(p.bias + c0 + j)), 0.f);
+          }
+          if (ok) {
+            uint32_t hw[16], lw[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_bf16x2(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + (obase + c0) * 2);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + (obase + c0) * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dh[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+              dl[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+            }
+          }
+          if constexpr (Ge::DGRAD) {
+            const float s = warp_transpose_sum(o, lane);      // column c0 + lane over this warp's 32 rows
+            bsum[NACC == 1 ? c0 / 32 : 0] += s;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[ab]);
+    }
+    if constexpr (Ge::DGRAD) {
+      if (p.dbias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < (NACC == 1 ? BN / 32 : 1); ++i) atomicAdd(p.dbias + i * 32 + lane, bsum[i]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+template <int G>
+static int launch_convk(const paacb_ctx* ctx, const ConvKParams& p, int slot, cudaStream_t st) {
+  using Cfg = ConvKCfg<G>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(convk_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("convk<%d>: cannot set %d bytes of dynamic shared memory", G, Cfg::SMEM_BYTES);
+      return PAACB_ECUDA;
+    }
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);
+  PAACB_LAUNCH_BEGIN(ctx, slot, st);
+  convk_kernel<G><<<grid, kConvKThreads, Cfg::SMEM_BYTES, st>>>(p);
+  PAACB_LAUNCH_END(ctx, slot, st);
+  return PAACB_OK;
+}
+
+static int weight_maps(const paacb_ctx* ctx, const uint16_t* hi, const uint16_t* lo, const LayerGeom& g, uint64_t kdim,
+                       uint64_t rows, uint32_t box_rows, CUtensorMap* out) {
+  const uint64_t dims[2] = {kdim, rows};
+  const uint64_t strides[1] = {kdim * 2};
+  const uint32_t box[2] = {64, box_rows};
+  int rc = encode_tmap_bf16(&out[0], hi + g.w_off, 2, dims, strides, box, 128);
+  if (rc != PAACB_OK) return rc;
+  return encode_tmap_bf16(&out[1], lo + g.w_off, 2, dims, strides, box, 128);
+}
+
+int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[l];
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = (int)batch;
+  p.bias = params + g.b_off;
+  p.in_scale = g.in_u8 ? 0.003921568859368563f : 1.0f;
+  const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, batch);
+  p.out_hi = out.hi;
+  p.out_lo = out.lo;
+  const uint8_t* in_hi;
+  const uint8_t* in_lo;
+  if (l == 0) {
+    in_hi = in_lo = reinterpret_cast<uint8_t*>(fwd_ws) + ctx->act_floats_per_sample * batch * 4;   // exact bf16 states, no lo plane
+  } else {
+    const Planes in = layer_planes(fwd_ws, g.in_act_off, (int64_t)g.H * g.W * g.C, batch);
+    in_hi = in.hi;
+    in_lo = in.lo;
+  }
+  const int s = g.stride;
+  const uint64_t unit = (uint64_t)s * g.C;                      // elements per unit
+  const uint64_t wu = (uint64_t)g.W / s, hq = (uint64_t)g.H / s;
+  const uint64_t dims[4] = {unit, wu, (uint64_t)s, (uint64_t)batch * hq};
+  const uint64_t strides[3] = {unit * 2, (uint64_t)g.W * g.C * 2, (uint64_t)s * g.W * g.C * 2};
+  int rc;
+#define PAACB_FWD_CASE(GE)                                                                                         \
+  {                                                                                                                \
+    using Ge = Geo<GE>;                                                                                            \
+    if ((int)unit * 2 != Ge::UB || (int)wu != Ge::WU || (int)hq != Ge::HQ || g.N != Ge::BN || g.K != Ge::KB * 64 ||  \
+        s != Ge::PARTS || g.OH != Ge::OH || g.OW != Ge::OW)                                                        \
+      return PAACB_EUNSUPPORTED;                                                                                   \
+    const uint32_t box[4] = {(uint32_t)unit, (uint32_t)Ge::WU, 1u, (uint32_t)Ge::BOX_ROWS};                        \
+    rc = encode_tmap_bf16(&p.tmA[0], in_hi, 4, dims, strides, box, Ge::UB);                                        \
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], in_lo, 4, dims, strides, box, Ge::UB);                    \
+    if (rc == PAACB_OK) rc = weight_maps(ctx, ctx->wb_f_hi, ctx->wb_f_lo, g, (uint64_t)g.K, (uint64_t)g.N, Ge::BN, p.tmW); \
+    if (rc != PAACB_OK) return rc;                                                                                 \
+    const int64_t q_total = batch * Ge::HQ * Ge::WU;                                                               \
+    p.num_tiles = (int)((q_total + 127) / 128);                                                                    \
+    return launch_convk<GE>(ctx, p, K_FWD0 + l, st);                                                               \
+  }
+  if (l == 0) PAACB_FWD_CASE(G_FWD1)
+  if (l == 1) PAACB_FWD_CASE(G_FWD2)
+  if (l == 2) PAACB_FWD_CASE(G_FWD3)
+#undef PAACB_FWD_CASE
+  return PAACB_EUNSUPPORTED;
+}
+
+// dX of layer l's input: A = dZ planes of layer l (bwd_ws), output = dZ planes of layer l-1, masked by layer l-1's activation
+int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,
+                           cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[l];
+  const LayerGeom& gp = ctx->layer[l - 1];
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = (int)batch;
+  p.num_tiles = (int)batch;
+  const Planes dz = layer_planes(bwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, batch);
+  const Planes dx = layer_planes(bwd_ws, gp.out_act_off, (int64_t)g.H * g.W * g.C, batch);
+  const Planes xa = layer_planes(const_cast<void*>(fwd_ws), gp.out_act_off, (int64_t)g.H * g.W * g.C, batch);
+  p.out_hi = dx.hi;
+  p.out_lo = dx.lo;
+  p.mask_hi = xa.hi;
+  p.dbias = grads + gp.b_off;
+  const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)batch};
+  const uint64_t strides[3] = {(uint64_t)g.N * 2, (uint64_t)g.OW * g.N * 2, (uint64_t)g.OH * g.OW * g.N * 2};
+  int rc;
+#define PAACB_DG_CASE(GE)                                                                                          \
+  {                                                                                                                \
+    using Ge = Geo<GE>;                                                                                            \
+    const int s = g.stride;                                                                                        \
+    if (g.N != 64 || g.C != Ge::BN || s != Ge::S || g.H != Ge::XH || g.W != Ge::XW || (g.R / s) * (g.S / s) * g.N != Ge::KB * 64 || \
+        (g.R - 1) / s != Ge::PAD || g.OH + 2 * Ge::PAD > Ge::BOX_ROWS + 0 || (g.H + s - 1) / s != Ge::OH)          \
+      return PAACB_EUNSUPPORTED;                                                                                   \
+    const uint32_t box[4] = {64u, (uint32_t)Ge::WU, (uint32_t)Ge::BOX_ROWS, 1u};                                   \
+    rc = encode_tmap_bf16(&p.tmA[0], dz.hi, 4, dims, strides, box, 128);                                           \
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], dz.lo, 4, dims, strides, box, 128);                       \
+    if (rc == PAACB_OK)                                                                                            \
+      rc = weight_maps(ctx, ctx->wb_d_hi, ctx->wb_d_lo, g, (uint64_t)(g.R / s) * (g.S / s) * g.N,                  \
+                       (uint64_t)s * s * g.C, Ge::BN, p.tmW);                                                      \
+    if (rc != PAACB_OK) return rc;                                                                                 \
+    return launch_convk<GE>(ctx, p, K_DGRAD0 + l, st);                                                             \
+  }
+  if (g.stride == 1) PAACB_DG_CASE(G_DG3)
+  if (g.stride == 2) PAACB_DG_CASE(G_DG2)
+#undef PAACB_DG_CASE
+  return PAACB_EUNSUPPORTED;
+}
+
+}  // namespace paacb

@@ -1,0 +1,392 @@
+// bf16-split tensor-core path, part 2: streaming GEMM for the fully connected layer (forward, data-gradient and
+// weight-gradient).  Both operands are re-staged per 64-wide K-block by the TMA engine (there is no spatial reuse to
+// exploit in an fc layer); three kind::f16 MMAs per K-step evaluate hi*hi + hi*lo + lo*hi (tc2_conv.cu).
+//
+//   forward : H[m, n]  = relu(sum_k X[m, k] W[k, n] + b[n])        A = X planes [M, K] (K-major), B = W^T image [N, K]
+//   dgrad   : dX[m, c] = (sum_n dZ[m, n] W[c, n]) * [X[m, c] > 0]  A = dZ planes [M, N],          B = W image   [C, N]
+//   wgrad   : dW[k, n] += sum_m X[m, k] dZ[m, n]                   A = X planes, B = dZ planes, both MN-major: the
+//             reduction index (samples) is the slow index of both as they lie in HBM, so the tiles are used as they
+//             land -- no transposition anywhere (the previous kernel transposed through registers with 4-byte stores).
+// Persistent CTA per SM: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue; double-buffered TMEM accumulator.
+#include "tc2.cuh"
+
+namespace paacb {
+
+enum { ST_FWD = 0, ST_DGRAD = 1, ST_WGRAD = 2 };
+
+struct StreamParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[2];
+  int m_tiles, n_tiles, k_splits;
+  int kblocks_per_split;     // 64-wide reduction blocks per unit
+  int kblocks_total;
+  int M, N;                  // valid output rows / columns
+  int ldo;                   // output row length in elements
+  const float* bias;
+  uint8_t* out_hi;
+  uint8_t* out_lo;
+  const uint8_t* mask_hi;
+  float* dbias;              // dgrad: += column sums, column c -> dbias[c % dbias_mod]
+  int dbias_mod;
+  float* dw;                 // wgrad target (fp32, atomics)
+};
+
+template <int BN, int MODE>
+struct StreamCfg {
+  static constexpr bool MN = (MODE == ST_WGRAD);
+  static constexpr int A_PIECE = 128 * 128;                 // 128 rows x 64 k (K-major) or 2 x (64 rows x 64 m) (MN-major)
+  static constexpr int B_PIECE = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_PIECE + 2 * B_PIECE;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static_assert(STAGES >= 2, "pipeline too shallow");
+};
+
+constexpr int kStreamThreads = 192;
+
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __grid_constant__ StreamParams p) {
+  using Cfg = StreamCfg<BN, MODE>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr bool MN = Cfg::MN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int units = p.m_tiles * p.n_tiles * p.k_splits;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB[0]);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit -> (split, m-tile, n-tile); n fastest so that CTAs running together share the A tile in L2
+  auto decode = [&](int u, int& split, int& mt, int& nt) {
+    nt = u % p.n_tiles;
+    const int rest = u / p.n_tiles;
+    mt = rest % p.m_tiles;
+    split = rest / p.m_tiles;
+  };
+  auto kb_range = [&](int split, int& kb0, int& kb1) {
+    kb0 = split * p.kblocks_per_split;
+    kb1 = kb0 + p.kblocks_per_split;
+    if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+  };
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int split, mt, nt, kb0, kb1;
+        decode(u, split, mt, nt);
+        kb_range(split, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int piece = 0; piece < 2; ++piece) {
+            uint8_t* a = st + piece * Cfg::A_PIECE;
+            uint8_t* b = st + 2 * Cfg::A_PIECE + piece * Cfg::B_PIECE;
+            if constexpr (MN) {
+              // boxes of (64 columns, 64 reduction rows): A columns = weight rows k, B columns = output channels n
+#pragma unroll
+              for (int i = 0; i < 2; ++i) tma_load_2d(a + i * 8192, &p.tmA[piece], mt * 128 + i * 64, kb * 64, &full_bar[stage]);
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i) tma_load_2d(b + i * 8192, &p.tmB[piece], nt * BN + i * 64, kb * 64, &full_bar[stage]);
+            } else {
+              tma_load_2d(a, &p.tmA[piece], kb * 64, mt * 128, &full_bar[stage]);      // box (64 k, 128 rows)
+              tma_load_2d(b, &p.tmB[piece], kb * 64, nt * BN, &full_bar[stage]);       // box (64 k, BN rows)
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const bool leader = elect_one_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(BN, MN ? 1 : 0, MN ? 1 : 0);
+    const uint64_t desc0 = MN ? make_smem_desc(0, 8192, 1024, SWZ_128B) : make_smem_desc(0, 16, 1024, SWZ_128B);
+    constexpr uint32_t kstep_bytes = MN ? 2048u : 32u;
+    int stage = 0;
+    uint32_t phase = 0;
+    int tl = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++tl) {
+      int split, mt, nt, kb0, kb1;
+      decode(u, split, mt, nt);
+      kb_range(split, kb0, kb1);
+      const int ab = tl & 1;
+      const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+      mbar_wait(&tempty_bar[ab], aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(ab * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + Cfg::A_PIECE;
+          const uint32_t b_hi = st + 2 * Cfg::A_PIECE, b_lo = b_hi + Cfg::B_PIECE;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t o = (uint32_t)ks * kstep_bytes;
+            umma_bf16(d, desc_with_addr(desc0, a_hi + o), desc_with_addr(desc0, b_hi + o), idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+            umma_bf16(d, desc_with_addr(desc0, a_hi + o), desc_with_addr(desc0, b_lo + o), idesc, 1u);
+            umma_bf16(d, desc_with_addr(desc0, a_lo + o), desc_with_addr(desc0, b_hi + o), idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) umma_commit(&tfull_bar[ab]);
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane;
+    // dgrad bias sums kept in registers across tiles when the column -> channel map is tile-invariant
+    // (channel = column % 64 and tiles start at multiples of 64): bsum[j] belongs to channel 32 * j + lane
+    float bsum[2] = {0.f, 0.f};
+    const bool reg_sums = (MODE == ST_DGRAD) && p.dbias != nullptr && p.dbias_mod == 64;
+    int tl = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++tl) {
+      int split, mt, nt;
+      decode(u, split, mt, nt);
+      const int ab = tl & 1;
+      const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+      const int m = mt * 128 + r;
+      const bool ok = m < p.M;
+      mbar_wait(&tfull_bar[ab], aph);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = nt * BN + c0;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * BN + c0), v);
+        tmem_ld_wait();
+        if (n0 >= p.N) continue;                 // warp-uniform: N is a multiple of 32
+        if constexpr (MODE == ST_WGRAD) {
+          if (ok) {
+            float* dst = p.dw + (int64_t)m * p.ldo + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
+        } else {
+          const int64_t obase = (int64_t)m * p.ldo + n0;
+          float o[32];
+          if constexpr (MODE == ST_DGRAD) {
+            uint32_t mw[16];
+            if (ok) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask_hi + obase * 2);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q = __ldg(mp + j);
+                mw[4 * j] = q.x; mw[4 * j + 1] = q.y; mw[4 * j + 2] = q.z; mw[4 * j + 3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) mw[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t a0 = mw[j] & 0xffffu, a1 = mw[j] >> 16;
+              o[2 * j] = (ok && a0 != 0u && a0 < 0x8000u) ? __uint_as_float(v[2 * j]) : 0.f;
+              o[2 * j + 1] = (ok && a1 != 0u && a1 < 0x8000u) ? __uint_as_float(v[2 * j + 1]) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(__uint_as_float(v[j]) + __ldg(p.bias + n0 + j), 0.f);
+          }
+          if (ok) {
+            uint32_t hw[16], lw[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_bf16x2(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase * 2);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dh[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+              dl[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+            }
+          }
+          if constexpr (MODE == ST_DGRAD) {
+            if (p.dbias != nullptr) {
+              const float s = warp_transpose_sum32(o, lane);
+              if (reg_sums) bsum[(c0 >> 5) & 1] += s;
+              else atomicAdd(p.dbias + ((n0 + lane) % p.dbias_mod), s);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[ab]);
+    }
+    if (reg_sums) {
+      atomicAdd(p.dbias + lane, bsum[0]);
+      atomicAdd(p.dbias + 32 + lane, bsum[1]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int MODE>
+static int launch_stream(const paacb_ctx* ctx, const StreamParams& p, int slot, cudaStream_t st) {
+  using Cfg = StreamCfg<BN, MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(stream_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      set_error("stream_gemm<%d,%d>: cannot set %d bytes of dynamic shared memory", BN, MODE, Cfg::SMEM_BYTES);
+      return PAACB_ECUDA;
+    }
+    attr_set = true;
+  }
+  const int units = p.m_tiles * p.n_tiles * p.k_splits;
+  const unsigned grid = (unsigned)(units < ctx->num_sms ? units : ctx->num_sms);
+  PAACB_LAUNCH_BEGIN(ctx, slot, st);
+  stream_gemm_kernel<BN, MODE><<<grid, kStreamThreads, Cfg::SMEM_BYTES, st>>>(p);
+  PAACB_LAUNCH_END(ctx, slot, st);
+  return PAACB_OK;
+}
+
+static int map2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+  const uint64_t dims[2] = {inner, rows};
+  const uint64_t strides[1] = {inner * 2};
+  const uint32_t box[2] = {box_inner, box_rows};
+  return encode_tmap_bf16(out, base, 2, dims, strides, box, 128);
+}
+
+constexpr int kFcBN = 128;
+
+int launch_fc_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[l];
+  if (g.K % 64 != 0 || g.N % kFcBN != 0) return PAACB_EUNSUPPORTED;
+  StreamParams p;
+  memset(&p, 0, sizeof(p));
+  const Planes x = layer_planes(fwd_ws, g.in_act_off, g.K, batch);
+  const Planes y = layer_planes(fwd_ws, g.out_act_off, g.N, batch);
+  int rc = map2d(&p.tmA[0], x.hi, (uint64_t)g.K, (uint64_t)batch, 64, 128);
+  if (rc == PAACB_OK) rc = map2d(&p.tmA[1], x.lo, (uint64_t)g.K, (uint64_t)batch, 64, 128);
+  if (rc == PAACB_OK) rc = map2d(&p.tmB[0], ctx->wb_f_hi + g.w_off, (uint64_t)g.K, (uint64_t)g.N, 64, kFcBN);
+  if (rc == PAACB_OK) rc = map2d(&p.tmB[1], ctx->wb_f_lo + g.w_off, (uint64_t)g.K, (uint64_t)g.N, 64, kFcBN);
+  if (rc != PAACB_OK) return rc;
+  p.m_tiles = (int)((batch + 127) / 128);
+  p.n_tiles = g.N / kFcBN;
+  p.k_splits = 1;
+  p.kblocks_total = p.kblocks_per_split = g.K / 64;
+  p.M = (int)batch;
+  p.N = g.N;
+  p.ldo = g.N;
+  p.bias = params + g.b_off;
+  p.out_hi = y.hi;
+  p.out_lo = y.lo;
+  return launch_stream<kFcBN, ST_FWD>(ctx, p, K_FWD0 + l, st);
+}
+
+int launch_fc_dgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,
+                         cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[l];
+  const LayerGeom& gp = ctx->layer[l - 1];
+  if (g.N % 64 != 0 || g.K % 32 != 0) return PAACB_EUNSUPPORTED;
+  StreamParams p;
+  memset(&p, 0, sizeof(p));
+  const Planes dz = layer_planes(bwd_ws, g.out_act_off, g.N, batch);
+  const Planes dx = layer_planes(bwd_ws, gp.out_act_off, g.K, batch);
+  const Planes xa = layer_planes(const_cast<void*>(fwd_ws), gp.out_act_off, g.K, batch);
+  int rc = map2d(&p.tmA[0], dz.hi, (uint64_t)g.N, (uint64_t)batch, 64, 128);
+  if (rc == PAACB_OK) rc = map2d(&p.tmA[1], dz.lo, (uint64_t)g.N, (uint64_t)batch, 64, 128);
+  if (rc == PAACB_OK) rc = map2d(&p.tmB[0], ctx->wb_d_hi + g.w_off, (uint64_t)g.N, (uint64_t)g.K, 64, kFcBN);
+  if (rc == PAACB_OK) rc = map2d(&p.tmB[1], ctx->wb_d_lo + g.w_off, (uint64_t)g.N, (uint64_t)g.K, 64, kFcBN);
+  if (rc != PAACB_OK) return rc;
+  p.m_tiles = (int)((batch + 127) / 128);
+  p.n_tiles = (g.K + kFcBN - 1) / kFcBN;
+  p.k_splits = 1;
+  p.kblocks_total = p.kblocks_per_split = g.N / 64;
+  p.M = (int)batch;
+  p.N = g.K;
+  p.ldo = g.K;
+  p.out_hi = dx.hi;
+  p.out_lo = dx.lo;
+  p.mask_hi = xa.hi;
+  p.dbias = grads + gp.b_off;
+  p.dbias_mod = gp.N;
+  return launch_stream<kFcBN, ST_DGRAD>(ctx, p, K_DGRAD0 + l, st);
+}
+
+int launch_fc_wgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, const void* bwd_ws, float* grads, int64_t batch,
+                         cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[l];
+  if (g.N % kFcBN != 0 || g.K % 64 != 0) return PAACB_EUNSUPPORTED;
+  StreamParams p;
+  memset(&p, 0, sizeof(p));
+  const Planes x = layer_planes(const_cast<void*>(fwd_ws), g.in_act_off, g.K, batch);
+  const Planes dz = layer_planes(const_cast<void*>(bwd_ws), g.out_act_off, g.N, batch);
+  int rc = map2d(&p.tmA[0], x.hi, (uint64_t)g.K, (uint64_t)batch, 64, 64);
+  if (rc == PAACB_OK) rc = map2d(&p.tmA[1], x.lo, (uint64_t)g.K, (uint64_t)batch, 64, 64);
+  if (rc == PAACB_OK) rc = map2d(&p.tmB[0], dz.hi, (uint64_t)g.N, (uint64_t)batch, 64, 64);
+  if (rc == PAACB_OK) rc = map2d(&p.tmB[1], dz.lo, (uint64_t)g.N, (uint64_t)batch, 64, 64);
+  if (rc != PAACB_OK) return rc;
+  p.m_tiles = (g.K + 127) / 128;
+  p.n_tiles = g.N / kFcBN;
+  p.kblocks_total = (int)((batch + 63) / 64);
+  int splits = (2 * ctx->num_sms + p.m_tiles * p.n_tiles - 1) / (p.m_tiles * p.n_tiles);
+  if (splits > p.kblocks_total) splits = p.kblocks_total;
+  if (splits < 1) splits = 1;
+  p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
+  p.k_splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.M = g.K;
+  p.N = g.N;
+  p.ldo = g.N;
+  p.dw = grads + g.w_off;
+  return launch_stream<kFcBN, ST_WGRAD>(ctx, p, K_WGRAD0 + l, st);
+}
+
+}  // namespace paacb

@@ -1,0 +1,329 @@
+// bf16-split tensor-core path, part 3: conv weight gradients as patch-resident GEMMs with MN-major operands.
+//
+//   dW[k = (kh, kw, ci), co] = sum over (sample, oh, ow) of  X[sample, s*oh + kh, s*ow + kw, ci] * dZ[sample, oh, ow, co]
+//
+// The 128-row MMA dimension is a tile of k, N = Cout, and the reduction runs over output positions.  Both operands
+// have the reduction index as their slow (row) index in HBM, which is exactly the MN-major shared-memory layout, so
+// the TMA boxes are used as they land.  As in tc2_conv.cu the positions are enumerated over the INPUT grid
+// (row-parity plane by row-parity plane) so every filter tap is a start-address offset into ONE resident input patch;
+// dZ is fetched with a box one row/column larger than the tensor so the positions that are not real outputs read
+// zeros (TMA out-of-bounds fill), and the rows of a slot the box never writes are zeroed once at kernel start.
+// All k-tile accumulators of the layer stay in TMEM for the whole kernel (conv2: 4 x 64 columns, conv3: 5 x 64,
+// conv1: 4 x 32); every CTA reduces a contiguous range of samples and adds its partial sums to dW with fp32 atomics
+// once, at the end.  Bias gradients are produced by the kernels that write dZ (tc2_conv.cu, tc2_stream.cu, heads.cu).
+#include "tc2.cuh"
+
+namespace paacb {
+
+template <int L>
+struct Wg;
+
+// conv1: X = bf16 states [b,84,84,4] (exact, one piece), dZ1 [b,20,20,32].  Stage = half a sample (224 positions).
+// Units are 32 B (4 pixels x 4 channels): MN groups of 16 k.  A k-tile (kh / 4, kw / 4) takes its 4 groups from the
+// 4 row-parity planes (LBO = plane slot stride); groups 4-7 of the 128-row MMA are unused (rows discarded).
+template <>
+struct Wg<0> {
+  static constexpr int A_PARTS = 4, A_PIECES = 1, A_SLOT = 9216, A_BOX = 16 * 2 * 21 * 13, B_SLOT = 16384, B_BOX = 64 * 21 * 12;
+  static constexpr int STAGES = 3, KT = 4, BN = 32, KSTEPS = 14, A_KSTEP = 512, B_KSTEP = 1024;
+  static constexpr int A_SWZ = SWZ_32B, A_SBO = 256, B_SWZ = SWZ_64B, B_SBO = 512;
+  static constexpr int STAGES_PER_SAMPLE = 2, SAMPLES_PER_STAGE = 1;
+  static constexpr int K = 256;
+  __device__ static int a_off(int kt) { return ((kt >> 1) * 21 + (kt & 1)) * 32; }          // within plane 0's slot
+  __device__ static int a_lbo(int) { return A_SLOT; }
+  // row m of k-tile kt -> weight row k (or -1)
+  __device__ static int k_of(int kt, int m) { return (m < 64) ? (4 * (kt >> 1) + (m >> 4)) * 32 + (kt & 1) * 16 + (m & 15) : -1; }
+};
+// conv2: X1 [b,20,20,32] (hi, lo), dZ2 [b,9,9,64].  Stage = one sample, 100 positions (10 x 10 over the parity plane).
+template <>
+struct Wg<1> {
+  static constexpr int A_PARTS = 2, A_PIECES = 2, A_SLOT = 15360, A_BOX = 128 * 10 * 12, B_SLOT = 14336, B_BOX = 128 * 10 * 10;
+  static constexpr int STAGES = 2, KT = 4, BN = 64, KSTEPS = 7, A_KSTEP = 2048, B_KSTEP = 2048;
+  static constexpr int A_SWZ = SWZ_128B, A_SBO = 1024, B_SWZ = SWZ_128B, B_SBO = 1024;
+  static constexpr int STAGES_PER_SAMPLE = 1, SAMPLES_PER_STAGE = 1;
+  static constexpr int K = 512;
+  __device__ static int a_off(int kt) { return (kt >> 1) * 10 * 128; }                       // kh = kt: plane kt & 1, row offset kt / 2
+  __device__ static int a_lbo(int) { return 128; }
+  __device__ static int k_of(int kt, int m) { return kt * 128 + m; }
+};
+// conv3: X2 [b,9,9,64] (hi, lo), dZ3 [b,7,7,64].  Stage = two samples, 162 positions (9 x 9 each).
+template <>
+struct Wg<2> {
+  static constexpr int A_PARTS = 1, A_PIECES = 2, A_SLOT = 24576, A_BOX = 128 * 9 * 21, B_SLOT = 22528, B_BOX = 128 * 9 * 9 * 2;
+  static constexpr int STAGES = 2, KT = 5, BN = 64, KSTEPS = 11, A_KSTEP = 2048, B_KSTEP = 2048;
+  static constexpr int A_SWZ = SWZ_128B, A_SBO = 1024, B_SWZ = SWZ_128B, B_SBO = 1024;
+  static constexpr int STAGES_PER_SAMPLE = 1, SAMPLES_PER_STAGE = 2;
+  static constexpr int K = 576;
+  __device__ static int tap_off(int tap) { return ((tap / 3) * 9 + (tap % 3)) * 128; }
+  __device__ static int a_off(int kt) { return tap_off(2 * kt); }
+  __device__ static int a_lbo(int kt) { return kt < 4 ? tap_off(2 * kt + 1) - tap_off(2 * kt) : 128; }
+  __device__ static int k_of(int kt, int m) { return (kt * 128 + m < K) ? kt * 128 + m : -1; }
+};
+
+struct Wg2Params {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[2];
+  int stages_total;
+  int batch;
+  float* dw;              // [K, BN] fp32
+  float w_scale;          // 1/255 for the uint8 layer (the operand holds the raw pixel values), else 1
+};
+
+template <int L>
+struct Wg2Cfg {
+  using W = Wg<L>;
+  static constexpr int A_STAGE = W::A_PARTS * W::A_PIECES * W::A_SLOT;
+  static constexpr int B_STAGE = 2 * W::B_SLOT;
+  static constexpr int A_BYTES = W::STAGES * A_STAGE;
+  static constexpr int DATA_BYTES = A_BYTES + W::STAGES * B_STAGE;
+  static constexpr int TX_BYTES = W::A_PARTS * W::A_PIECES * W::A_BOX + 2 * W::B_BOX;
+  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + (2 * W::STAGES + 1) * 8 + 16;
+  static constexpr int TMEM_COLS = (W::KT * W::BN <= 128) ? 128 : ((W::KT * W::BN <= 256) ? 256 : 512);
+  static_assert(W::A_BOX <= W::A_SLOT && W::B_BOX <= W::B_SLOT, "slot too small");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+constexpr int kWg2Threads = 192;
+
+template <int L>
+__global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_constant__ Wg2Params p) {
+  using W = Wg<L>;
+  using Cfg = Wg2Cfg<L>;
+  constexpr int STAGES = W::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_sm = smem;                                  // [STAGES][A_PARTS][A_PIECES][A_SLOT]
+  uint8_t* b_sm = smem + Cfg::A_BYTES;                   // [STAGES][2][B_SLOT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* done_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  // contiguous range of stages of this CTA
+  const int per = (p.stages_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int s_begin = (int)blockIdx.x * per;
+  const int s_end = (s_begin + per < p.stages_total) ? s_begin + per : p.stages_total;
+
+  // zero the operand area once: rows of a slot the TMA boxes never write must read as 0 (dZ) / finite (X)
+  for (int i = tid * 16; i < Cfg::DATA_BYTES; i += kWg2Threads * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB[0]);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = s_begin; s < s_end; ++s) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
+        uint8_t* a = a_sm + stage * Cfg::A_STAGE;
+        uint8_t* b = b_sm + stage * Cfg::B_STAGE;
+        if constexpr (L == 0) {
+          const int n = s >> 1, h = s & 1;
+#pragma unroll
+          for (int part = 0; part < 4; ++part) tma_load_4d(a + part * W::A_SLOT, &p.tmA[0], 0, 0, part, n * 21 + 10 * h, &full_bar[stage]);
+#pragma unroll
+          for (int piece = 0; piece < 2; ++piece) tma_load_4d(b + piece * W::B_SLOT, &p.tmB[piece], 0, 0, 10 * h, n, &full_bar[stage]);
+        } else if constexpr (L == 1) {
+#pragma unroll
+          for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int piece = 0; piece < 2; ++piece)
+              tma_load_4d(a + (part * 2 + piece) * W::A_SLOT, &p.tmA[piece], 0, 0, part, s * 10, &full_bar[stage]);
+#pragma unroll
+          for (int piece = 0; piece < 2; ++piece) tma_load_4d(b + piece * W::B_SLOT, &p.tmB[piece], 0, 0, 0, s, &full_bar[stage]);
+        } else {
+#pragma unroll
+          for (int piece = 0; piece < 2; ++piece) tma_load_3d(a + piece * W::A_SLOT, &p.tmA[piece], 0, 0, s * 18, &full_bar[stage]);
+#pragma unroll
+          for (int piece = 0; piece < 2; ++piece) tma_load_4d(b + piece * W::B_SLOT, &p.tmB[piece], 0, 0, 0, s * 2, &full_bar[stage]);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const bool leader = elect_one_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(W::BN, 1, 1);
+    const uint64_t bdesc0 = make_smem_desc(0, 16, W::B_SBO, W::B_SWZ);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = s_begin; s < s_end; ++s) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t a_st = smem_u32(a_sm + stage * Cfg::A_STAGE);
+        const uint32_t b_st = smem_u32(b_sm + stage * Cfg::B_STAGE);
+        uint32_t a_rel = 0, b_rel = 0;
+        if constexpr (L == 0) {
+          if (s & 1) { a_rel = 14 * 32; b_rel = 14 * 64; }      // second half of the sample starts at position 224 = 10 * 21 + 14
+        }
+        const uint32_t first = (s == s_begin) ? 0u : 1u;
+#pragma unroll
+        for (int kt = 0; kt < W::KT; ++kt) {
+          const uint32_t d = tmem_base + (uint32_t)(kt * W::BN);
+          const uint64_t adesc0 = make_smem_desc(0, (uint32_t)W::a_lbo(kt), W::A_SBO, W::A_SWZ);
+          uint32_t a_hi, a_lo = 0;
+          if constexpr (L == 0) {
+            a_hi = a_st + a_rel + (uint32_t)W::a_off(kt);
+          } else if constexpr (L == 1) {
+            a_hi = a_st + (uint32_t)((kt & 1) * 2 * W::A_SLOT) + (uint32_t)W::a_off(kt);
+            a_lo = a_hi + W::A_SLOT;
+          } else {
+            a_hi = a_st + (uint32_t)W::a_off(kt);
+            a_lo = a_hi + W::A_SLOT;
+          }
+          const uint32_t b_hi = b_st + b_rel, b_lo = b_hi + W::B_SLOT;
+#pragma unroll
+          for (int t = 0; t < W::KSTEPS; ++t) {
+            const uint32_t ao = (uint32_t)(t * W::A_KSTEP), bo = (uint32_t)(t * W::B_KSTEP);
+            umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, t > 0 ? 1u : first);
+            umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_lo + bo), idesc, 1u);
+            if constexpr (W::A_PIECES == 2)
+              umma_bf16(d, desc_with_addr(adesc0, a_lo + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+    if (leader) umma_commit(done_bar);
+    __syncwarp();
+  } else if (s_end > s_begin) {
+    // =========================== epilogue: add this CTA's partial sums into dW ===========================
+    const int ew = warp & 3;
+    const int m = ew * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int kt = 0; kt < W::KT; ++kt) {
+      const int k = W::k_of(kt, m);
+#pragma unroll
+      for (int c0 = 0; c0 < W::BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(kt * W::BN + c0), v);
+        tmem_ld_wait();
+        if (k >= 0) {
+          float* dst = p.dw + (int64_t)k * W::BN + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]) * p.w_scale);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int L>
+static int launch_wg2(const paacb_ctx* ctx, const Wg2Params& p, cudaStream_t st) {
+  using Cfg = Wg2Cfg<L>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad2_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("wgrad2<%d>: cannot set %d bytes of dynamic shared memory", L, Cfg::SMEM_BYTES);
+      return PAACB_ECUDA;
+    }
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)(p.stages_total < ctx->num_sms ? p.stages_total : ctx->num_sms);
+  PAACB_LAUNCH_BEGIN(ctx, K_WGRAD0 + L, st);
+  wgrad2_kernel<L><<<grid, kWg2Threads, Cfg::SMEM_BYTES, st>>>(p);
+  PAACB_LAUNCH_END(ctx, K_WGRAD0 + L, st);
+  return PAACB_OK;
+}
+
+int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, const void* bwd_ws, float* grads, int64_t batch,
+                           cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[l];
+  if (batch == 0) return PAACB_OK;
+  Wg2Params p;
+  memset(&p, 0, sizeof(p));
+  p.batch = (int)batch;
+  p.dw = grads + g.w_off;
+  p.w_scale = g.in_u8 ? 0.003921568859368563f : 1.0f;
+  const uint8_t* x_hi;
+  const uint8_t* x_lo;
+  if (l == 0) {
+    x_hi = x_lo = reinterpret_cast<const uint8_t*>(fwd_ws) + ctx->act_floats_per_sample * batch * 4;
+  } else {
+    const Planes x = layer_planes(const_cast<void*>(fwd_ws), g.in_act_off, (int64_t)g.H * g.W * g.C, batch);
+    x_hi = x.hi;
+    x_lo = x.lo;
+  }
+  const Planes dz = layer_planes(const_cast<void*>(bwd_ws), g.out_act_off, (int64_t)g.OH * g.OW * g.N, batch);
+  const int s = g.stride;
+  const uint64_t unit = (uint64_t)s * g.C, wu = (uint64_t)g.W / s, hq = (uint64_t)g.H / s;
+  const uint64_t bdims[4] = {(uint64_t)g.N, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)batch};
+  const uint64_t bstr[3] = {(uint64_t)g.N * 2, (uint64_t)g.OW * g.N * 2, (uint64_t)g.OH * g.OW * g.N * 2};
+  int rc;
+  if (l == 0) {
+    if (g.C != 4 || s != 4 || g.R != 8 || g.N != 32 || g.H != 84 || g.OH != 20) return PAACB_EUNSUPPORTED;
+    const uint64_t adims[4] = {unit, wu, (uint64_t)s, (uint64_t)batch * hq};
+    const uint64_t astr[3] = {unit * 2, (uint64_t)g.W * g.C * 2, (uint64_t)s * g.W * g.C * 2};
+    const uint32_t abox[4] = {16u, 21u, 1u, 13u};
+    const uint32_t bbox[4] = {32u, 21u, 12u, 1u};
+    rc = encode_tmap_bf16(&p.tmA[0], x_hi, 4, adims, astr, abox, 32);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], x_lo, 4, adims, astr, abox, 32);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[0], dz.hi, 4, bdims, bstr, bbox, 64);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[1], dz.lo, 4, bdims, bstr, bbox, 64);
+    if (rc != PAACB_OK) return rc;
+    p.stages_total = (int)batch * 2;
+    return launch_wg2<0>(ctx, p, st);
+  }
+  if (l == 1) {
+    if (g.C != 32 || s != 2 || g.R != 4 || g.N != 64 || g.H != 20 || g.OH != 9) return PAACB_EUNSUPPORTED;
+    const uint64_t adims[4] = {unit, wu, (uint64_t)s, (uint64_t)batch * hq};
+    const uint64_t astr[3] = {unit * 2, (uint64_t)g.W * g.C * 2, (uint64_t)s * g.W * g.C * 2};
+    const uint32_t abox[4] = {64u, 10u, 1u, 12u};
+    const uint32_t bbox[4] = {64u, 10u, 10u, 1u};
+    rc = encode_tmap_bf16(&p.tmA[0], x_hi, 4, adims, astr, abox, 128);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], x_lo, 4, adims, astr, abox, 128);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[0], dz.hi, 4, bdims, bstr, bbox, 128);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[1], dz.lo, 4, bdims, bstr, bbox, 128);
+    if (rc != PAACB_OK) return rc;
+    p.stages_total = (int)batch;
+    return launch_wg2<1>(ctx, p, st);
+  }
+  if (l == 2) {
+    if (g.C != 64 || s != 1 || g.R != 3 || g.N != 64 || g.H != 9 || g.OH != 7) return PAACB_EUNSUPPORTED;
+    const uint64_t adims[3] = {64u, 9u, (uint64_t)batch * 9};
+    const uint64_t astr[2] = {128u, 1152u};
+    const uint32_t abox[3] = {64u, 9u, 21u};
+    const uint32_t bbox[4] = {64u, 9u, 9u, 2u};
+    rc = encode_tmap_bf16(&p.tmA[0], x_hi, 3, adims, astr, abox, 128);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], x_lo, 3, adims, astr, abox, 128);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[0], dz.hi, 4, bdims, bstr, bbox, 128);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[1], dz.lo, 4, bdims, bstr, bbox, 128);
+    if (rc != PAACB_OK) return rc;
+    p.stages_total = (int)((batch + 1) / 2);
+    return launch_wg2<2>(ctx, p, st);
+  }
+  return PAACB_EUNSUPPORTED;
+}
+
+}  // namespace paacb

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cuda_bf16.h>
 
 namespace paacb {
 
@@ -161,6 +162,83 @@ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) { return r
 // Instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = n.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+}  // namespace paacb
+
+// =====================================================================================================
+// bf16-split path (PAACB_MATH_BF16X3): kind::f16 MMAs on bf16 operand planes staged by the TMA engine.
+// Descriptor semantics below were MEASURED on B200 with tools/probe (profiles/r01_umma_descriptor_probe.json):
+// the swizzle XOR is a function of the absolute shared-memory address (address bits [7,10) into bits [4,7) for
+// SWIZZLE_128B, [7,9) -> [4,6) for 64B, bit 7 -> bit 4 for 32B), for K-major and MN-major operands alike, for ANY
+// 16-byte aligned start address and any LBO/SBO, with the descriptor's base_offset field left 0.  A filter tap of an
+// implicit GEMM is therefore just a start-address offset into a resident activation patch.
+// =====================================================================================================
+namespace paacb {
+
+enum { SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };   // descriptor layout_type field
+
+// Shared-memory matrix descriptor with explicit leading / stride byte offsets (16-byte units inside).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+// the invariant upper 32 bits + LBO; add ((addr >> 4) & 0x3FFF) for the start address
+__device__ __forceinline__ uint64_t desc_with_addr(uint64_t desc_base, uint32_t smem_addr) {
+  return desc_base | (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+}
+
+// Instruction descriptor, kind::f16: D = f32, A = B = bf16, M = 128, N = n; a_mn / b_mn = 1 for MN-major operands.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 operands), K = 16 per instruction; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// TMA tiled loads global -> shared (box of a CUtensorMap), completing bytes on an mbarrier.  Coordinates innermost first.
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): |x - hi - lo| <= 2^-18 |x| (round to nearest twice)
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
+// two floats -> packed (hi plane word, lo plane word); element 0 in the low half
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi_word, uint32_t& lo_word) {
+  uint16_t h0, l0, h1, l1;
+  split_bf16(x0, h0, l0);
+  split_bf16(x1, h1, l1);
+  hi_word = (uint32_t)h0 | ((uint32_t)h1 << 16);
+  lo_word = (uint32_t)l0 | ((uint32_t)l1 << 16);
 }
 
 }  // namespace paacb

@@ -97,7 +97,8 @@ class Network(object):
         self.initialize(self.seed)
 
     def set_math(self, math):
-        mode = {'fp32': _lib.MATH_FP32, 'tf32x3': _lib.MATH_TF32X3, 'tf32': _lib.MATH_TF32}[str(math).lower()]
+        mode = {'fp32': _lib.MATH_FP32, 'tf32x3': _lib.MATH_TF32X3, 'tf32': _lib.MATH_TF32,
+                'bf16x3': _lib.MATH_BF16X3}[str(math).lower()]
         _lib.check(self._lib.paacb_set_math(self.ctx, mode), 'paacb_set_math')
         self.math = str(math).lower()
 
@@ -126,6 +127,24 @@ class Network(object):
 
     def get_params(self):
         return self.params.detach().cpu().numpy().copy()
+
+    LAYER_SHAPES = None      # per-sample shapes of the workspace activations, set by the subclasses
+
+    def layer_tensors(self, ws, batch):
+        """Per-layer fp32 views/copies [batch, ...] of a forward (activations) or backward (dZ) workspace.
+        fp32 / tf32 modes store floats; 'bf16x3' stores each tensor as two bf16 planes, value = hi + lo."""
+        out, off = [], 0
+        raw = ws.view(torch.uint8)
+        for shp in self.LAYER_SHAPES:
+            e = int(np.prod(shp)) * batch
+            if self.math == 'bf16x3':
+                hi = raw[off * 4: off * 4 + e * 2].view(torch.bfloat16).float()
+                lo = raw[off * 4 + e * 2: off * 4 + e * 4].view(torch.bfloat16).float()
+                out.append((hi + lo).view((batch,) + tuple(shp)))
+            else:
+                out.append(ws[off:off + e].view((batch,) + tuple(shp)))
+            off += e
+        return out
 
     def workspace_floats(self, batch):
         return int(self._lib.paacb_forward_workspace_floats(self.ctx, int(batch)))
@@ -166,6 +185,7 @@ class Network(object):
 class NIPSNetwork(Network):
     """networks.py:138-151: 84x84x4 -conv8/4-> 20x20x16 -conv4/2-> 9x9x32 -> fc 256."""
     ARCH = 'NIPS'
+    LAYER_SHAPES = [(20, 20, 16), (9, 9, 32), (256,)]
 
     def __init__(self, conf):
         super(NIPSNetwork, self).__init__(conf)
@@ -175,6 +195,7 @@ class NIPSNetwork(Network):
 class NatureNetwork(Network):
     """networks.py:154-169: -conv8/4-> 20x20x32 -conv4/2-> 9x9x64 -conv3/1-> 7x7x64 -> fc 512."""
     ARCH = 'NATURE'
+    LAYER_SHAPES = [(20, 20, 32), (9, 9, 64), (7, 7, 64), (512,)]
 
     def __init__(self, conf):
         super(NatureNetwork, self).__init__(conf)

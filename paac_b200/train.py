@@ -1,6 +1,6 @@
 """train.py mirror (train.py:14-109): same flag names, dests and defaults, same
 ``get_network_and_environment_creator`` / ``main``.  Additions are additive flags only:
-``--math`` (fp32 | tf32x3 | tf32), ``--raw_frames``, ``--synthetic_actions``, and multi-GPU launch through
+``--math`` (fp32 | tf32x3 | tf32 | bf16x3), ``--raw_frames``, ``--synthetic_actions``, and multi-GPU launch through
 torchrun (one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK read from the environment).
 
     python -m paac_b200.train -g synthetic -d /gpu:0 --arch NATURE -ec 32 -ew 8
@@ -114,7 +114,7 @@ def get_arg_parser():
     parser.add_argument('-df', '--debugging_folder', default='logs/', type=str, help="Folder where to save the debugging information.", dest="debugging_folder")
     parser.add_argument('-rs', '--random_start', default=True, type=bool_arg, help="Whether or not to start with 30 noops for each env. Default True", dest="random_start")
     # ---- additions (not in the reference) ----
-    parser.add_argument('--math', default='fp32', choices=['fp32', 'tf32x3', 'tf32'], help="Arithmetic of the conv/fc contractions", dest="math")
+    parser.add_argument('--math', default='fp32', choices=['fp32', 'tf32x3', 'tf32', 'bf16x3'], help="Arithmetic of the conv/fc contractions", dest="math")
     parser.add_argument('--raw_frames', default=True, type=bool_arg, help="Workers write raw frame pairs; the GPU does max-pool/resize/stack", dest="raw_frames")
     parser.add_argument('--synthetic_actions', default=6, type=int, help="num_actions of the synthetic environment", dest="synthetic_actions")
     return parser

@@ -58,13 +58,7 @@ def forward(net, states, uniforms=None):
 
 def layer_acts(net, ws, b):
     """Split the forward workspace into per-layer activations [b, ...] (conv NHWC, then hidden fc)."""
-    shapes = ([(20, 20, 16), (9, 9, 32), (256,)] if net.ARCH == 'NIPS' else [(20, 20, 32), (9, 9, 64), (7, 7, 64), (512,)])
-    out, off = [], 0
-    for s in shapes:
-        n = int(np.prod(s)) * b
-        out.append(ws[off:off + n].view((b,) + s).cpu().numpy())
-        off += n
-    return out
+    return [t.cpu().numpy() for t in net.layer_tensors(ws, b)]
 
 
 def returns_loss_grad(net, rewards, over, values, boot, actions, pi, v, gamma, beta):

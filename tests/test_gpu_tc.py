@@ -1,6 +1,6 @@
-"""GPU: the tcgen05 tensor-core path (PAACB_MATH_TF32X3 = parity mode, PAACB_MATH_TF32 = speed mode) against the oracle.
-Tolerances: TF32X3 meets the 1e-4 bar (scaled max error, see util.py); plain TF32 rounds operands to 11 bits and is
-held to 3e-3 -- it is reported as a speed mode, not as a parity mode."""
+"""GPU: the tcgen05 tensor-core paths against the oracle.  PAACB_MATH_BF16X3 (bf16-split operands, TMA-fed
+patch-resident implicit GEMMs; Nature architecture) and PAACB_MATH_TF32X3 are parity modes and meet the 1e-4 bar
+(scaled max error, see util.py); plain TF32 rounds operands to 11 bits and is held to 3e-3 -- a speed mode only."""
 import numpy as np
 import pytest
 import torch
@@ -12,12 +12,19 @@ import gpu_util as G
 
 pytestmark = pytest.mark.gpu
 
-TOL = {'tf32x3': 1e-4, 'tf32': 3e-3}
+TOL = {'bf16x3': 1e-4, 'tf32x3': 1e-4, 'tf32': 3e-3}
+MODES = ['bf16x3', 'tf32x3', 'tf32']
 
 
-@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+def skip_unsupported(math, arch):
+    if math == 'bf16x3' and arch == 'NIPS':
+        pytest.skip('PAACB_MATH_BF16X3 covers the Nature architecture (see test_bf16x3_rejects_nips)')
+
+
+@pytest.mark.parametrize('math', MODES)
 @pytest.mark.parametrize('arch,A,b', [('NATURE', 6, 1), ('NATURE', 6, 130), ('NIPS', 4, 33), ('NATURE', 18, 517)])
 def test_forward_tc_vs_oracle(math, arch, A, b):
+    skip_unsupported(math, arch)
     net = G.make_net(arch, A, seed=3, math=math)
     params = network.unflatten_params(net.get_params(), arch, A)
     rng = np.random.RandomState(b)
@@ -32,11 +39,12 @@ def test_forward_tc_vs_oracle(math, arch, A, b):
     assert_close(out['v'].cpu().numpy(), ref['v'].numpy(), TOL[math], 'v')
 
 
-@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('math', MODES)
 @pytest.mark.parametrize('arch,A,b', [('NATURE', 6, 5), ('NATURE', 6, 160), ('NIPS', 4, 97), ('NATURE', 4, 1111)])
 def test_backward_tc_vs_autograd(math, arch, A, b):
     """Gradients (and every layer's dZ) against fp64 autograd whose ReLU masks are the GPU's own activations
     (oracle.network.masked_loss_and_grads): like-for-like, immune to a pre-activation rounding across zero."""
+    skip_unsupported(math, arch)
     net = G.make_net(arch, A, seed=11, math=math)
     params = network.unflatten_params(net.get_params(), arch, A)
     rng = np.random.RandomState(b + A)
@@ -51,15 +59,20 @@ def test_backward_tc_vs_autograd(math, arch, A, b):
     got = network.unflatten_params(flat, arch, A)
     for name, _, _ in network.param_specs(arch, A):
         assert_close(got[name], g64[name], TOL[math], name)
-    off = 0
-    for i, d in enumerate(dzs):
-        assert_close(bws[off:off + d.size].cpu().numpy().reshape(d.shape), d, TOL[math], 'dZ of layer %d' % i)
-        off += d.size
+    for i, (d, got_dz) in enumerate(zip(dzs, G.layer_acts(net, bws, b))):
+        assert_close(got_dz.reshape(d.shape), d, TOL[math], 'dZ of layer %d' % i)
 
 
-def test_engine_update_tf32x3_vs_oracle_composite():
+def test_bf16x3_rejects_nips():
+    from paac_b200 import _lib
+    with pytest.raises(_lib.PaacbError):
+        G.make_net('NIPS', 4, seed=3, math='bf16x3')
+
+
+@pytest.mark.parametrize('math', ['bf16x3', 'tf32x3'])
+def test_engine_update_tc_vs_oracle_composite(math):
     arch, A, N, T = 'NATURE', 6, 16, 5
-    net = G.make_net(arch, A, seed=5, math='tf32x3')
+    net = G.make_net(arch, A, seed=5, math=math)
     eng = RolloutEngine(net, N, T, seed=9)
     rng = np.random.RandomState(0)
     states = rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)
