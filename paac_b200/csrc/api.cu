@@ -309,8 +309,8 @@ int paacb_tensor_info(const paacb_ctx* ctx, int index, char* name, int name_cap,
 }
 
 int64_t paacb_forward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
-  // activations (fp32, or two bf16 planes per tensor: the same bytes) + the bf16 image of the states (BF16X3 mode)
-  return ctx ? (ctx->act_floats_per_sample + kStateElems / 2) * batch : PAACB_EINVAL;
+  // activations as fp32, or as two bf16 planes per tensor (PAACB_MATH_BF16X3): the same bytes
+  return ctx ? ctx->act_floats_per_sample * batch : PAACB_EINVAL;
 }
 int64_t paacb_backward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
   return ctx ? ctx->act_floats_per_sample * batch : PAACB_EINVAL;
@@ -354,9 +354,7 @@ int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint
     if (batch == 0) return PAACB_OK;
     const int L = ctx->n_layers;
     int rc = launch_pack_bf16_weights(ctx, d_params, st);      // the caller may have changed the parameters
-    if (rc == PAACB_OK)
-      rc = launch_states_to_bf16(ctx, d_states, reinterpret_cast<uint8_t*>(d_fwd_ws) + ctx->act_floats_per_sample * batch * 4, batch, st);
-    for (int l = 0; l < L - 1 && rc == PAACB_OK; ++l) rc = launch_conv_fwd_bf16(ctx, l, d_params, d_fwd_ws, batch, st);
+    for (int l = 0; l < L - 1 && rc == PAACB_OK; ++l) rc = launch_conv_fwd_bf16(ctx, l, d_params, d_states, d_fwd_ws, batch, st);
     if (rc == PAACB_OK) rc = launch_fc_fwd_bf16(ctx, L - 1, d_params, d_fwd_ws, batch, st);
     if (rc != PAACB_OK) return rc;
     const Planes hp = layer_planes(d_fwd_ws, ctx->layer[L - 1].out_act_off, ctx->feat, batch);
@@ -420,7 +418,7 @@ int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d
     if (rc == PAACB_OK) rc = launch_fc_dgrad_bf16(ctx, L - 1, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
     for (int l = L - 2; l >= 1 && rc == PAACB_OK; --l) rc = launch_conv_dgrad_bf16(ctx, l, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
     if (rc == PAACB_OK) rc = launch_fc_wgrad_bf16(ctx, L - 1, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
-    for (int l = L - 2; l >= 0 && rc == PAACB_OK; --l) rc = launch_conv_wgrad_bf16(ctx, l, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
+    for (int l = L - 2; l >= 0 && rc == PAACB_OK; --l) rc = launch_conv_wgrad_bf16(ctx, l, d_states, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
     return rc;
   }
   const float* h = d_fwd_ws + ctx->layer[L - 1].out_act_off * batch;

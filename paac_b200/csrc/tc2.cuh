@@ -10,12 +10,13 @@ namespace paacb {
 // ---- host: tensor maps ------------------------------------------------------------------------------
 // rank-`rank` bf16 tensor, dims innermost first, strides in bytes for dims 1..rank-1, zero fill out of bounds.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle_bytes /* 32, 64, 128 */);
+                     const uint32_t* box, int swizzle_bytes /* 0, 32, 64, 128 */);
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes /* 1: uint8, 2: bf16 */, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 // ---- workspace layout (bytes) -------------------------------------------------------------------------
 // forward / backward workspace, bf16-split mode: for layer l the region [out_act_off(l) * batch * 4, +E_l * batch * 4)
 // holds the hi plane (E_l * batch bf16) followed by the lo plane; value = float(hi) + float(lo).
-// The forward workspace additionally holds the bf16 image of the uint8 states after all activations.
 struct Planes {
   uint8_t* hi;
   uint8_t* lo;
@@ -30,17 +31,20 @@ constexpr int64_t kStateElems = (int64_t)PAACB_OBS * PAACB_OBS * PAACB_STACK;   
 
 // ---- launchers (tc2_*.cu) ---------------------------------------------------------------------------
 bool bf16x3_supported(const paacb_ctx* ctx);
-int launch_states_to_bf16(const paacb_ctx* ctx, const uint8_t* states, void* out_bf16, int64_t batch, cudaStream_t st);
 int launch_pack_bf16_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st);          // forward images
 int launch_pack_bf16_dgrad_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st);    // data-gradient images
-int launch_conv_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st);
+int launch_conv_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
+                         cudaStream_t st);
+int launch_pack_conv1_i8(const paacb_ctx* ctx, const float* params, cudaStream_t st);              // int8 digit image of conv1
+int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
+                        cudaStream_t st);
 int launch_fc_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st);
 int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,
                            cudaStream_t st);
 int launch_fc_dgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,
                          cudaStream_t st);
-int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, const void* bwd_ws, float* grads,
-                           int64_t batch, cudaStream_t st);
+int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int layer, const uint8_t* states, const void* fwd_ws, const void* bwd_ws,
+                           float* grads, int64_t batch, cudaStream_t st);
 int launch_fc_wgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, const void* bwd_ws, float* grads,
                          int64_t batch, cudaStream_t st);
 

@@ -43,6 +43,11 @@ static EncodeTiledFn encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes) {
+  return encode_tmap(out, base, 2, rank, dims, strides_bytes, box, swizzle_bytes);
+}
+
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -60,7 +65,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
-  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  const CUresult r = fn(out, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -77,37 +82,6 @@ bool bf16x3_supported(const paacb_ctx* ctx) { return ctx->arch == PAACB_ARCH_NAT
 // ------------------------------------------------------------------------------------------------
 // operand producers
 // ------------------------------------------------------------------------------------------------
-// uint8 NHWC states -> bf16 (exact), 16 pixels-channels per thread
-__global__ void states_to_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n16) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint4 v = __ldg(in + i);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float f0 = (float)(w[j] & 0xffu), f1 = (float)((w[j] >> 8) & 0xffu), f2 = (float)((w[j] >> 16) & 0xffu),
-                  f3 = (float)(w[j] >> 24);
-      o[2 * j] = (__float_as_uint(f0) >> 16) | (__float_as_uint(f1) & 0xffff0000u);      // small integers: truncation is exact
-      o[2 * j + 1] = (__float_as_uint(f2) >> 16) | (__float_as_uint(f3) & 0xffff0000u);
-    }
-    out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
-    out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
-  }
-}
-
-int launch_states_to_bf16(const paacb_ctx* ctx, const uint8_t* states, void* out_bf16, int64_t batch, cudaStream_t st) {
-  const int64_t n16 = batch * kStateElems / 16;
-  if (n16 == 0) return PAACB_OK;
-  int64_t blocks = (n16 + 255) / 256;
-  const int64_t cap = (int64_t)ctx->num_sms * 16;
-  if (blocks > cap) blocks = cap;
-  PAACB_LAUNCH_BEGIN(ctx, K_PACK, st);
-  states_to_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(states),
-                                                          reinterpret_cast<uint4*>(out_bf16), n16);
-  PAACB_LAUNCH_END(ctx, K_PACK, st);
-  return PAACB_OK;
-}
-
 // forward image: Wp[n][k] = W[k][n] as (hi, lo) bf16, row-major [N][K] (the B operand, K-major)
 __global__ void pack_bf16_transpose_kernel(const float* __restrict__ w, int K, int N, uint16_t* __restrict__ hi,
                                            uint16_t* __restrict__ lo) {
@@ -183,21 +157,11 @@ int launch_pack_bf16_dgrad_weights(const paacb_ctx* ctx, const float* params, cu
 // ------------------------------------------------------------------------------------------------
 // geometry of the five patch-resident GEMMs of the Nature network
 // ------------------------------------------------------------------------------------------------
-enum { G_FWD1 = 0, G_FWD2 = 1, G_FWD3 = 2, G_DG3 = 3, G_DG2 = 4 };
+enum { G_FWD2 = 1, G_FWD3 = 2, G_DG3 = 3, G_DG2 = 4 };      // conv1 forward has its own int8 kernel (tc2_conv1.cu)
 
 template <int G>
 struct Geo;
 
-// conv1 forward: bf16 states [b,84,84,4], 8x8 stride 4 -> [b,20,20,32].  Unit = 4 pixels x 4 channels = 32 B; plane rho
-// holds the input rows ih = 4*q + rho; a K-step (16 elements) is half a filter row.
-template <>
-struct Geo<G_FWD1> {
-  static constexpr bool DGRAD = false, A_LO = false;
-  static constexpr int UB = 32, SWZ = SWZ_32B, PARTS = 4, WU = 21, HQ = 21, BOX_ROWS = 9, SLOT = 6144, NSLOTS = 8;
-  static constexpr int NACC = 1, BN = 32, KS = 4, KB = 4, OH = 20, OW = 20;
-  __host__ __device__ static constexpr int aoff(int t) { return ((t / 2) * 21 + (t % 2)) * 32; }
-  __host__ __device__ static constexpr int jw(int part, int t) { return (part + 4 * (t / 2)) * 2 + (t % 2); }
-};
 // conv2 forward: [b,20,20,32] 4x4 stride 2 -> [b,9,9,64].  Unit = 2 pixels x 32 channels = 128 B; 2 row-parity planes.
 template <>
 struct Geo<G_FWD2> {
@@ -256,19 +220,24 @@ template <int G>
 struct ConvKCfg {
   using Ge = Geo<G>;
   static constexpr int RING_BYTES = Ge::NSLOTS * Ge::SLOT;
-  static constexpr int ACC_W_BYTES = Ge::KB * Ge::BN * 128;                 // one accumulator's weights, one piece
-  static constexpr int PIECE_BYTES = Ge::NACC * ACC_W_BYTES;
-  static constexpr int W_BYTES = 2 * PIECE_BYTES;
+  // resident weights: per 64-wide K-block one K-major tile of 2 * NT rows: the hi pieces of all accumulators, then the
+  // lo pieces.  One MMA of N = 2 * NT evaluates A_hi * [W_hi | W_lo] (the operand A is read from shared memory once:
+  // with N <= 64 an SS-mode MMA is bound by its 4 KB A read, not by the tensor pipe), a second of N = NT adds A_lo * W_hi.
+  static constexpr int NT = Ge::NACC * Ge::BN;
+  static constexpr int KB_BYTES = 2 * NT * 128;
+  static constexpr int W_BYTES = Ge::KB * KB_BYTES;
   static constexpr int BOX_BYTES = Ge::UB * Ge::WU * Ge::BOX_ROWS;
   static constexpr int NBARS = 2 * Ge::NSLOTS + 1 + 4;
   static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + 1024 /* alignment slack */ + NBARS * 8 + 16;
-  static constexpr int TMEM_COLS = 2 * Ge::NACC * Ge::BN;
+  static constexpr int TMEM_COLS = 4 * NT;                                  // two accumulator buffers of 2 * NT columns
   static_assert(BOX_BYTES <= Ge::SLOT && Ge::SLOT % 1024 == 0, "slot too small");
+  // TMA warp, MMA warp, two epilogue groups of four warps (one per accumulator buffer)
+  static constexpr int THREADS = 64 + 256;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
+  static_assert(2 * NT <= 256, "MMA N");
 };
 
-constexpr int kConvKThreads = 192;
 
 // lane j of the warp ends up with the sum over the warp's 32 lanes of v[j] (31 shuffles)
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
@@ -286,7 +255,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 }
 
 template <int G>
-__global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_constant__ ConvKParams p) {
+__global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __grid_constant__ ConvKParams p) {
   using Ge = Geo<G>;
   using Cfg = ConvKCfg<G>;
   constexpr int NSLOTS = Ge::NSLOTS, BN = Ge::BN, NACC = Ge::NACC;
@@ -313,7 +282,7 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
     mbar_init(w_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 128);        // the four warps of the epilogue group that owns buffer s
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA[0]);
@@ -332,7 +301,7 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
       for (int piece = 0; piece < 2; ++piece)
         for (int acc = 0; acc < NACC; ++acc)
           for (int kb = 0; kb < Ge::KB; ++kb)
-            tma_load_2d(wsm + piece * Cfg::PIECE_BYTES + (acc * Ge::KB + kb) * (BN * 128), &p.tmW[piece], kb * 64, acc * BN, w_bar);
+            tma_load_2d(wsm + kb * Cfg::KB_BYTES + (piece * NACC + acc) * (BN * 128), &p.tmW[piece], kb * 64, acc * BN, w_bar);
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -357,11 +326,12 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     const bool leader = elect_one_sync();
-    constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+    constexpr uint32_t idesc_full = make_idesc_bf16(2 * Cfg::NT, 0, 0);
+    constexpr uint32_t idesc_half = make_idesc_bf16(Cfg::NT, 0, 0);
     const uint64_t adesc0 = make_smem_desc(0, 16, 8 * Ge::UB, Ge::SWZ);
     const uint64_t bdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
     const uint32_t ring_a = smem_u32(ring);
-    const uint32_t w_hi = smem_u32(wsm), w_lo = w_hi + Cfg::PIECE_BYTES;
+    const uint32_t w_a = smem_u32(wsm);
     mbar_wait(w_bar, 0);
     int slot = 0;
     uint32_t phase = 0;
@@ -373,7 +343,7 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
       tc_fence_after();
       uint32_t rel = 0;
       if constexpr (!Ge::DGRAD) rel = (uint32_t)(((int64_t)tile * 128) % Ge::WU) * Ge::UB;
-      const uint32_t d0 = tmem_base + (uint32_t)(ab * NACC * BN);
+      const uint32_t d0 = tmem_base + (uint32_t)(ab * 2 * Cfg::NT);
 #pragma unroll
       for (int part = 0; part < Ge::PARTS; ++part) {
 #pragma unroll
@@ -383,19 +353,12 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
           if (leader) {
             const uint32_t a_base = ring_a + (uint32_t)(slot * Ge::SLOT) + rel;
 #pragma unroll
-            for (int acc = 0; acc < NACC; ++acc) {
-#pragma unroll
-              for (int t = 0; t < Ge::KS; ++t) {
-                const uint64_t ad = desc_with_addr(adesc0, a_base + (uint32_t)Ge::aoff(t));
-                const int jw = Ge::jw(part, t);
-                const uint32_t boff = (uint32_t)((acc * Ge::KB + jw / 4) * (BN * 128) + (jw % 4) * 32);
-                if (piece == 0) {
-                  umma_bf16(d0 + (uint32_t)(acc * BN), ad, desc_with_addr(bdesc0, w_hi + boff), idesc, (part | t) ? 1u : 0u);
-                  umma_bf16(d0 + (uint32_t)(acc * BN), ad, desc_with_addr(bdesc0, w_lo + boff), idesc, 1u);
-                } else {
-                  umma_bf16(d0 + (uint32_t)(acc * BN), ad, desc_with_addr(bdesc0, w_hi + boff), idesc, 1u);
-                }
-              }
+            for (int t = 0; t < Ge::KS; ++t) {
+              const uint64_t ad = desc_with_addr(adesc0, a_base + (uint32_t)Ge::aoff(t));
+              const int jw = Ge::jw(part, t);
+              const uint64_t bd = desc_with_addr(bdesc0, w_a + (uint32_t)((jw / 4) * Cfg::KB_BYTES + (jw % 4) * 32));
+              if (piece == 0) umma_bf16(d0, ad, bd, idesc_full, (part | t) ? 1u : 0u);    // A_hi * [W_hi | W_lo]
+              else umma_bf16(d0, ad, bd, idesc_half, 1u);                                  // A_lo * W_hi
             }
             umma_commit(&empty_bar[slot]);
           }
@@ -410,12 +373,17 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
     // =========================== epilogue ===========================
     const int ew = warp & 3;                     // TMEM lane quarter this warp may access
     const int r = ew * 32 + lane;                // tile row of this thread
+    const int grp = (warp - 2) >> 2;             // epilogue group = accumulator buffer it drains (tiles tl with tl & 1 == grp)
     float bsum[NACC == 1 ? BN / 32 : 1];
 #pragma unroll
     for (int i = 0; i < (NACC == 1 ? BN / 32 : 1); ++i) bsum[i] = 0.f;
-    int tl = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
-      const int ab = tl & 1;
+    float breg[Ge::DGRAD ? 1 : BN];              // forward: the bias row lives in registers
+    if constexpr (!Ge::DGRAD) {
+#pragma unroll
+      for (int j = 0; j < BN; ++j) breg[j] = __ldg(p.bias + j);
+    }
+    for (int tl = grp, tile = blockIdx.x + grp * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x, tl += 2) {
+      const int ab = grp;
       const uint32_t aph = (uint32_t)((tl >> 1) & 1);
       // row -> output pixel
       bool ok;
@@ -426,13 +394,31 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
         qw = r - qh * Ge::WU;
         ok = (qh < Ge::OH) && (qw < Ge::OW);
       } else {
-        const int64_t q = (int64_t)tile * 128 + r;
-        const int64_t prow = q / Ge::WU;
-        const int ju = (int)(q - prow * Ge::WU);
-        const int64_t n = prow / Ge::HQ;
-        const int oh = (int)(prow - n * Ge::HQ);
-        ok = (ju < Ge::OW) && (oh < Ge::OH) && (n < p.batch);
-        pix = (n * Ge::OH + oh) * Ge::OW + ju;
+        const uint32_t q = (uint32_t)tile * 128u + (uint32_t)r;      // < 2^31 (checked by the launcher)
+        const uint32_t prow = q / (uint32_t)Ge::WU;
+        const int ju = (int)(q - prow * (uint32_t)Ge::WU);
+        const uint32_t n = prow / (uint32_t)Ge::HQ;
+        const int oh = (int)(prow - n * (uint32_t)Ge::HQ);
+        ok = (ju < Ge::OW) && (oh < Ge::OH) && ((int)n < p.batch);
+        pix = ((int64_t)n * Ge::OH + oh) * Ge::OW + ju;
+      }
+      // dgrad: the ReLU-mask words of the whole tile row do not depend on the accumulator: fetch them before waiting
+      // for the MMAs so that their DRAM latency overlaps the mainloop (they were the top stall of the first version)
+      uint4 mk[Ge::DGRAD ? NACC : 1][Ge::DGRAD ? BN / 32 : 1][4];
+      if constexpr (Ge::DGRAD) {
+#pragma unroll
+        for (int acc = 0; acc < NACC; ++acc) {
+          const int ih = Ge::S * qh + (NACC > 1 ? acc / 2 : 0), iw = Ge::S * qw + (NACC > 1 ? acc % 2 : 0);
+          const int64_t ob = (((int64_t)tile * Ge::XH + ih) * Ge::XW + iw) * BN;
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              mk[acc][c][j] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok) mk[acc][c][j] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + (ob + c * 32) * 2) + j);
+            }
+          }
+        }
       }
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
@@ -447,22 +433,20 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
         }
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * NACC * BN + acc * BN + c0), v);
+          uint32_t v[32], v2[32];
+          const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * 2 * Cfg::NT + acc * BN + c0);
+          tmem_ld32(tcol, v);                                   // A_hi * W_hi + A_lo * W_hi
+          tmem_ld32(tcol + (uint32_t)Cfg::NT, v2);              // A_hi * W_lo
           tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
           float o[32];
           if constexpr (Ge::DGRAD) {
             uint32_t mw[16];
-            if (ok) {
-              const uint4* mp = reinterpret_cast<const uint4*>(p.mask_hi + (obase + c0) * 2);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 m = __ldg(mp + j);
-                mw[4 * j] = m.x; mw[4 * j + 1] = m.y; mw[4 * j + 2] = m.z; mw[4 * j + 3] = m.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) mw[j] = 0u;
+            for (int j = 0; j < 4; ++j) {
+              const uint4 m = mk[acc][c0 / 32][j];
+              mw[4 * j] = m.x; mw[4 * j + 1] = m.y; mw[4 * j + 2] = m.z; mw[4 * j + 3] = m.w;
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -473,7 +457,7 @@ __global__ void __launch_bounds__(kConvKThreads, 1) convk_kernel(const __grid_co
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = fmaxf(fmaf(__uint_as_float(v[j]), p.in_scale, __ldg(p.bias + c0 + j)), 0.f);
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(fmaf(__uint_as_float(v[j]), p.in_scale, breg[c0 + j]), 0.f);
           }
           if (ok) {
             uint32_t hw[16], lw[16];
@@ -529,7 +513,7 @@ static int launch_convk(const paacb_ctx* ctx, const ConvKParams& p, int slot, cu
   }
   const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, slot, st);
-  convk_kernel<G><<<grid, kConvKThreads, Cfg::SMEM_BYTES, st>>>(p);
+  convk_kernel<G><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
   PAACB_LAUNCH_END(ctx, slot, st);
   return PAACB_OK;
 }
@@ -544,7 +528,8 @@ static int weight_maps(const paacb_ctx* ctx, const uint16_t* hi, const uint16_t*
   return encode_tmap_bf16(&out[1], lo + g.w_off, 2, dims, strides, box, 128);
 }
 
-int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st) {
+int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
+                         cudaStream_t st) {
   const LayerGeom& g = ctx->layer[l];
   ConvKParams p;
   memset(&p, 0, sizeof(p));
@@ -557,7 +542,7 @@ int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void*
   const uint8_t* in_hi;
   const uint8_t* in_lo;
   if (l == 0) {
-    in_hi = in_lo = reinterpret_cast<uint8_t*>(fwd_ws) + ctx->act_floats_per_sample * batch * 4;   // exact bf16 states, no lo plane
+    in_hi = in_lo = nullptr;                    // conv1 converts the uint8 states itself
   } else {
     const Planes in = layer_planes(fwd_ws, g.in_act_off, (int64_t)g.H * g.W * g.C, batch);
     in_hi = in.hi;
@@ -581,10 +566,11 @@ int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void*
     if (rc == PAACB_OK) rc = weight_maps(ctx, ctx->wb_f_hi, ctx->wb_f_lo, g, (uint64_t)g.K, (uint64_t)g.N, Ge::BN, p.tmW); \
     if (rc != PAACB_OK) return rc;                                                                                 \
     const int64_t q_total = batch * Ge::HQ * Ge::WU;                                                               \
+    if (q_total >= (1LL << 31) - 256) return PAACB_EUNSUPPORTED;                                                   \
     p.num_tiles = (int)((q_total + 127) / 128);                                                                    \
     return launch_convk<GE>(ctx, p, K_FWD0 + l, st);                                                               \
   }
-  if (l == 0) PAACB_FWD_CASE(G_FWD1)
+  if (l == 0) return launch_conv1_fwd_i8(ctx, params, states, fwd_ws, batch, st);
   if (l == 1) PAACB_FWD_CASE(G_FWD2)
   if (l == 2) PAACB_FWD_CASE(G_FWD3)
 #undef PAACB_FWD_CASE

@@ -39,7 +39,8 @@ struct StreamCfg {
   static constexpr int STAGE_BYTES = 2 * A_PIECE + 2 * B_PIECE;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + (2 * STAGES + 4) * 8 + 16;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 4 * BN;                  // two buffers of [A_hi*B_hi + A_lo*B_hi | A_hi*B_lo]
+  static_assert(2 * BN <= 256, "MMA N");
   static_assert(STAGES >= 2, "pipeline too shallow");
 };
 
@@ -144,7 +145,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     const bool leader = elect_one_sync();
-    constexpr uint32_t idesc = make_idesc_bf16(BN, MN ? 1 : 0, MN ? 1 : 0);
+    // B_hi and B_lo lie back to back in the stage: one MMA of N = 2 * BN evaluates A_hi * [B_hi | B_lo] (A is read from
+    // shared memory once), a second of N = BN adds A_lo * B_hi into the first half; the epilogue adds the halves.
+    constexpr uint32_t idesc_full = make_idesc_bf16(2 * BN, MN ? 1 : 0, MN ? 1 : 0);
+    constexpr uint32_t idesc_half = make_idesc_bf16(BN, MN ? 1 : 0, MN ? 1 : 0);
     const uint64_t desc0 = MN ? make_smem_desc(0, 8192, 1024, SWZ_128B) : make_smem_desc(0, 16, 1024, SWZ_128B);
     constexpr uint32_t kstep_bytes = MN ? 2048u : 32u;
     int stage = 0;
@@ -158,20 +162,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
       const uint32_t aph = (uint32_t)((tl >> 1) & 1);
       mbar_wait(&tempty_bar[ab], aph ^ 1u);
       tc_fence_after();
-      const uint32_t d = tmem_base + (uint32_t)(ab * BN);
+      const uint32_t d = tmem_base + (uint32_t)(ab * 2 * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (leader) {
           const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t a_hi = st, a_lo = st + Cfg::A_PIECE;
-          const uint32_t b_hi = st + 2 * Cfg::A_PIECE, b_lo = b_hi + Cfg::B_PIECE;
+          const uint32_t b_hi = st + 2 * Cfg::A_PIECE;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t o = (uint32_t)ks * kstep_bytes;
-            umma_bf16(d, desc_with_addr(desc0, a_hi + o), desc_with_addr(desc0, b_hi + o), idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
-            umma_bf16(d, desc_with_addr(desc0, a_hi + o), desc_with_addr(desc0, b_lo + o), idesc, 1u);
-            umma_bf16(d, desc_with_addr(desc0, a_lo + o), desc_with_addr(desc0, b_hi + o), idesc, 1u);
+            const uint64_t bd = desc_with_addr(desc0, b_hi + o);
+            umma_bf16(d, desc_with_addr(desc0, a_hi + o), bd, idesc_full, (kb > kb0 || ks > 0) ? 1u : 0u);
+            umma_bf16(d, desc_with_addr(desc0, a_lo + o), bd, idesc_half, 1u);
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -197,14 +201,31 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
       const uint32_t aph = (uint32_t)((tl >> 1) & 1);
       const int m = mt * 128 + r;
       const bool ok = m < p.M;
+      // dgrad: prefetch the ReLU-mask words of this row before waiting for the MMAs (their latency overlaps the mainloop)
+      uint4 mk[MODE == ST_DGRAD ? BN / 32 : 1][4];
+      if constexpr (MODE == ST_DGRAD) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = nt * BN + c * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mk[c][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok && n0 < p.N) mk[c][j] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + ((int64_t)m * p.ldo + n0) * 2) + j);
+          }
+        }
+      }
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const int n0 = nt * BN + c0;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * BN + c0), v);
+        uint32_t v[32], v2[32];
+        const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * 2 * BN + c0);
+        tmem_ld32(tcol, v);
+        tmem_ld32(tcol + (uint32_t)BN, v2);
         tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
         if (n0 >= p.N) continue;                 // warp-uniform: N is a multiple of 32
         if constexpr (MODE == ST_WGRAD) {
           if (ok) {
@@ -217,16 +238,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
           float o[32];
           if constexpr (MODE == ST_DGRAD) {
             uint32_t mw[16];
-            if (ok) {
-              const uint4* mp = reinterpret_cast<const uint4*>(p.mask_hi + obase * 2);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 q = __ldg(mp + j);
-                mw[4 * j] = q.x; mw[4 * j + 1] = q.y; mw[4 * j + 2] = q.z; mw[4 * j + 3] = q.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) mw[j] = 0u;
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = mk[c0 / 32][j];
+              mw[4 * j] = q.x; mw[4 * j + 1] = q.y; mw[4 * j + 2] = q.z; mw[4 * j + 3] = q.w;
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {

@@ -64,6 +64,7 @@ struct Wg2Params {
   CUtensorMap tmB[2];
   int stages_total;
   int batch;
+  const uint8_t* a_u8;    // conv1: the uint8 states [b, 84, 84, 4], converted to bf16 in shared memory, instead of tmA
   float* dw;              // [K, BN] fp32
   float w_scale;          // 1/255 for the uint8 layer (the operand holds the raw pixel values), else 1
 };
@@ -75,17 +76,23 @@ struct Wg2Cfg {
   static constexpr int B_STAGE = 2 * W::B_SLOT;
   static constexpr int A_BYTES = W::STAGES * A_STAGE;
   static constexpr int DATA_BYTES = A_BYTES + W::STAGES * B_STAGE;
-  static constexpr int TX_BYTES = W::A_PARTS * W::A_PIECES * W::A_BOX + 2 * W::B_BOX;
+  static constexpr bool U8_A = (L == 0);                 // conv1: eight converter warps produce the X operand from the uint8 states
+  static constexpr int TX_BYTES = (U8_A ? 0 : W::A_PARTS * W::A_PIECES * W::A_BOX) + 2 * W::B_BOX;
+  static constexpr int THREADS = 192 + (U8_A ? 256 : 0);
   static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + (2 * W::STAGES + 1) * 8 + 16;
-  static constexpr int TMEM_COLS = (W::KT * W::BN <= 128) ? 128 : ((W::KT * W::BN <= 256) ? 256 : 512);
+  // dZ_hi and dZ_lo slots lie back to back: one MMA of N = 2 * BN evaluates X_hi^T * [dZ_hi | dZ_lo] (X is read from shared
+  // memory once), a second of N = BN adds X_lo^T * dZ_hi.  conv3 has 5 k-tiles: 5 * 128 columns do not fit in TMEM, it
+  // keeps three MMAs of N = BN per K-step.
+  static constexpr bool CONCAT = (W::KT * 2 * W::BN <= 512);
+  static constexpr int ACC_COLS = CONCAT ? 2 * W::BN : W::BN;
+  static constexpr int TMEM_COLS = (W::KT * ACC_COLS <= 128) ? 128 : ((W::KT * ACC_COLS <= 256) ? 256 : 512);
   static_assert(W::A_BOX <= W::A_SLOT && W::B_BOX <= W::B_SLOT, "slot too small");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-constexpr int kWg2Threads = 192;
 
 template <int L>
-__global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_constant__ Wg2Params p) {
+__global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __grid_constant__ Wg2Params p) {
   using W = Wg<L>;
   using Cfg = Wg2Cfg<L>;
   constexpr int STAGES = W::STAGES;
@@ -107,10 +114,10 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_con
   const int s_end = (s_begin + per < p.stages_total) ? s_begin + per : p.stages_total;
 
   // zero the operand area once: rows of a slot the TMA boxes never write must read as 0 (dZ) / finite (X)
-  for (int i = tid * 16; i < Cfg::DATA_BYTES; i += kWg2Threads * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid * 16; i < Cfg::DATA_BYTES; i += Cfg::THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], Cfg::U8_A ? 257 : 1);      // TMA producer (+ 256 converter threads)
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(done_bar, 1);
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_con
         if constexpr (L == 0) {
           const int n = s >> 1, h = s & 1;
 #pragma unroll
-          for (int part = 0; part < 4; ++part) tma_load_4d(a + part * W::A_SLOT, &p.tmA[0], 0, 0, part, n * 21 + 10 * h, &full_bar[stage]);
+          (void)a;                                    // the X operand is written by the converter warps
 #pragma unroll
           for (int piece = 0; piece < 2; ++piece) tma_load_4d(b + piece * W::B_SLOT, &p.tmB[piece], 0, 0, 10 * h, n, &full_bar[stage]);
         } else if constexpr (L == 1) {
@@ -162,7 +169,8 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_con
     // =========================== MMA issuer ===========================
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc = make_idesc_bf16(W::BN, 1, 1);
-    const uint64_t bdesc0 = make_smem_desc(0, 16, W::B_SBO, W::B_SWZ);
+    constexpr uint32_t idesc_full = make_idesc_bf16(2 * W::BN, 1, 1);
+    const uint64_t bdesc0 = make_smem_desc(0, Cfg::CONCAT ? W::B_SLOT : 16, W::B_SBO, W::B_SWZ);
     int stage = 0;
     uint32_t phase = 0;
     for (int s = s_begin; s < s_end; ++s) {
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_con
         const uint32_t first = (s == s_begin) ? 0u : 1u;
 #pragma unroll
         for (int kt = 0; kt < W::KT; ++kt) {
-          const uint32_t d = tmem_base + (uint32_t)(kt * W::BN);
+          const uint32_t d = tmem_base + (uint32_t)(kt * Cfg::ACC_COLS);
           const uint64_t adesc0 = make_smem_desc(0, (uint32_t)W::a_lbo(kt), W::A_SBO, W::A_SWZ);
           uint32_t a_hi, a_lo = 0;
           if constexpr (L == 0) {
@@ -194,8 +202,12 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_con
 #pragma unroll
           for (int t = 0; t < W::KSTEPS; ++t) {
             const uint32_t ao = (uint32_t)(t * W::A_KSTEP), bo = (uint32_t)(t * W::B_KSTEP);
-            umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, t > 0 ? 1u : first);
-            umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_lo + bo), idesc, 1u);
+            if constexpr (Cfg::CONCAT) {
+              umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc_full, t > 0 ? 1u : first);
+            } else {
+              umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, t > 0 ? 1u : first);
+              umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_lo + bo), idesc, 1u);
+            }
             if constexpr (W::A_PIECES == 2)
               umma_bf16(d, desc_with_addr(adesc0, a_lo + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, 1u);
           }
@@ -207,6 +219,71 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_con
     }
     if (leader) umma_commit(done_bar);
     __syncwarp();
+  } else if (Cfg::U8_A && warp >= 6) {
+    // =========================== uint8 -> bf16 converters (conv1) ===========================
+    // A stage needs 13 plane rows of each of the 4 row-parity planes: 273 units (4 pixels x 4 channels) per plane.
+    // 256 threads: thread c converts units c and c + 256 of every plane, loaded one stage ahead into registers.
+    if constexpr (Cfg::U8_A) {
+      constexpr int UNITS = 13 * 21;
+      const int ct = tid - 192;
+      auto load_stage = [&](int s, uint4 (&b)[4][2]) {
+        const int row0 = (s >> 1) * 21 + 10 * (s & 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int w = ct + i * 256;
+          const int R = row0 + w / 21, u = w % 21;
+          const int n = R / 21, q = R - n * 21;
+          const bool ok = (w < UNITS) && (s < s_end) && (n < p.batch);
+#pragma unroll
+          for (int part = 0; part < 4; ++part) {
+            b[part][i] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) b[part][i] = __ldg(reinterpret_cast<const uint4*>(p.a_u8 + (((int64_t)n * 84 + 4 * q + part) * 84 + 4 * u) * 4));
+          }
+        }
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      auto store_stage = [&](const uint4 (&b)[4][2]) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        const uint32_t base = smem_u32(a_sm + stage * Cfg::A_STAGE);
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int w = ct + i * 256;
+            if (w < UNITS) {
+              const uint32_t wd[4] = {b[part][i].x, b[part][i].y, b[part][i].z, b[part][i].w};
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float f0 = u8_to_f32(wd[j], 0), f1 = u8_to_f32(wd[j], 1), f2 = u8_to_f32(wd[j], 2), f3 = u8_to_f32(wd[j], 3);
+                o[2 * j] = (__float_as_uint(f0) >> 16) | (__float_as_uint(f1) & 0xffff0000u);
+                o[2 * j + 1] = (__float_as_uint(f2) >> 16) | (__float_as_uint(f3) & 0xffff0000u);
+              }
+              const uint32_t a0 = base + (uint32_t)(part * W::A_SLOT) + (uint32_t)w * 32u;
+              const uint32_t sw = ((a0 >> 7) & 1u) << 4;       // SWIZZLE_32B on the absolute address
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0 ^ sw), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"((a0 + 16u) ^ sw), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      };
+      uint4 bufa[4][2], bufb[4][2];
+      int s = s_begin;
+      load_stage(s, bufa);
+      load_stage(s + 1, bufb);
+      for (; s < s_end; s += 2) {
+        store_stage(bufa);
+        load_stage(s + 2, bufa);
+        if (s + 1 < s_end) {
+          store_stage(bufb);
+          load_stage(s + 3, bufb);
+        }
+      }
+    }
   } else if (s_end > s_begin) {
     // =========================== epilogue: add this CTA's partial sums into dW ===========================
     const int ew = warp & 3;
@@ -219,8 +296,17 @@ __global__ void __launch_bounds__(kWg2Threads, 1) wgrad2_kernel(const __grid_con
 #pragma unroll
       for (int c0 = 0; c0 < W::BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(kt * W::BN + c0), v);
-        tmem_ld_wait();
+        const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(kt * Cfg::ACC_COLS + c0);
+        tmem_ld32(tcol, v);
+        if constexpr (Cfg::CONCAT) {
+          uint32_t v2[32];
+          tmem_ld32(tcol + (uint32_t)W::BN, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         if (k >= 0) {
           float* dst = p.dw + (int64_t)k * W::BN + c0;
 #pragma unroll
@@ -252,13 +338,13 @@ static int launch_wg2(const paacb_ctx* ctx, const Wg2Params& p, cudaStream_t st)
   }
   const unsigned grid = (unsigned)(p.stages_total < ctx->num_sms ? p.stages_total : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, K_WGRAD0 + L, st);
-  wgrad2_kernel<L><<<grid, kWg2Threads, Cfg::SMEM_BYTES, st>>>(p);
+  wgrad2_kernel<L><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
   PAACB_LAUNCH_END(ctx, K_WGRAD0 + L, st);
   return PAACB_OK;
 }
 
-int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, const void* bwd_ws, float* grads, int64_t batch,
-                           cudaStream_t st) {
+int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int l, const uint8_t* states, const void* fwd_ws, const void* bwd_ws,
+                           float* grads, int64_t batch, cudaStream_t st) {
   const LayerGeom& g = ctx->layer[l];
   if (batch == 0) return PAACB_OK;
   Wg2Params p;
@@ -269,7 +355,7 @@ int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, cons
   const uint8_t* x_hi;
   const uint8_t* x_lo;
   if (l == 0) {
-    x_hi = x_lo = reinterpret_cast<const uint8_t*>(fwd_ws) + ctx->act_floats_per_sample * batch * 4;
+    x_hi = x_lo = nullptr;                       // conv1 converts the uint8 states itself
   } else {
     const Planes x = layer_planes(const_cast<void*>(fwd_ws), g.in_act_off, (int64_t)g.H * g.W * g.C, batch);
     x_hi = x.hi;
@@ -287,9 +373,9 @@ int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, cons
     const uint64_t astr[3] = {unit * 2, (uint64_t)g.W * g.C * 2, (uint64_t)s * g.W * g.C * 2};
     const uint32_t abox[4] = {16u, 21u, 1u, 13u};
     const uint32_t bbox[4] = {32u, 21u, 12u, 1u};
-    rc = encode_tmap_bf16(&p.tmA[0], x_hi, 4, adims, astr, abox, 32);
-    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], x_lo, 4, adims, astr, abox, 32);
-    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[0], dz.hi, 4, bdims, bstr, bbox, 64);
+    (void)adims; (void)astr; (void)abox; (void)x_lo; (void)x_hi;
+    p.a_u8 = states;
+    rc = encode_tmap_bf16(&p.tmB[0], dz.hi, 4, bdims, bstr, bbox, 64);
     if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[1], dz.lo, 4, bdims, bstr, bbox, 64);
     if (rc != PAACB_OK) return rc;
     p.stages_total = (int)batch * 2;
