@@ -167,6 +167,8 @@ int paacb_destroy(paacb_ctx* ctx) {
   if (ctx->wb_f_lo != nullptr) cudaFree(ctx->wb_f_lo);
   if (ctx->wb_d_hi != nullptr) cudaFree(ctx->wb_d_hi);
   if (ctx->wb_d_lo != nullptr) cudaFree(ctx->wb_d_lo);
+  if (ctx->wq_i8 != nullptr) cudaFree(ctx->wq_i8);
+  if (ctx->wq_scale != nullptr) cudaFree(ctx->wq_scale);
   delete ctx;
   return PAACB_OK;
 }
@@ -248,8 +250,10 @@ int paacb_set_math(paacb_ctx* ctx, int math_mode) {
       const cudaError_t e2 = cudaMalloc(&ctx->wb_f_lo, bytes);
       const cudaError_t e3 = cudaMalloc(&ctx->wb_d_hi, bytes);
       const cudaError_t e4 = cudaMalloc(&ctx->wb_d_lo, bytes);
+      const cudaError_t e5 = cudaMalloc(&ctx->wq_i8, (size_t)3 * ctx->layer[0].N * ctx->layer[0].K);
+      const cudaError_t e6 = cudaMalloc(&ctx->wq_scale, (size_t)ctx->layer[0].N * sizeof(float));
       cudaSetDevice(cur);
-      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess) {
         cudaGetLastError();
         set_error("paacb_set_math: cannot allocate %zu bytes for the bf16 weight images", 4 * bytes);
         return PAACB_ECUDA;

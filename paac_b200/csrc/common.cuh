@@ -82,6 +82,8 @@ struct paacb_ctx {
   uint16_t* wb_f_lo;
   uint16_t* wb_d_hi;
   uint16_t* wb_d_lo;
+  int8_t* wq_i8;                // conv1 forward: three int8 digit images of the weights [3][Cout][K] + per-channel scale
+  float* wq_scale;
   int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };
 

@@ -11,7 +11,7 @@ namespace paacb {
 // rank-`rank` bf16 tensor, dims innermost first, strides in bytes for dims 1..rank-1, zero fill out of bounds.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes /* 0, 32, 64, 128 */);
-int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes /* 1: uint8, 2: bf16 */, int rank, const uint64_t* dims,
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes /* 1: uint8, 2: bf16, 4: uint32 */, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 // ---- workspace layout (bytes) -------------------------------------------------------------------------

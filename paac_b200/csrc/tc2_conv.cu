@@ -65,7 +65,9 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
-  const CUresult r = fn(out, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                 : elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -82,16 +84,29 @@ bool bf16x3_supported(const paacb_ctx* ctx) { return ctx->arch == PAACB_ARCH_NAT
 // ------------------------------------------------------------------------------------------------
 // operand producers
 // ------------------------------------------------------------------------------------------------
-// forward image: Wp[n][k] = W[k][n] as (hi, lo) bf16, row-major [N][K] (the B operand, K-major)
-__global__ void pack_bf16_transpose_kernel(const float* __restrict__ w, int K, int N, uint16_t* __restrict__ hi,
-                                           uint16_t* __restrict__ lo) {
-  const int64_t total = (int64_t)K * N;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i / N), n = (int)(i - (int64_t)k * N);       // coalesced reads of W
-    uint16_t h, l;
-    split_bf16(__ldg(w + i), h, l);
-    hi[(int64_t)n * K + k] = h;
-    lo[(int64_t)n * K + k] = l;
+// forward image: Wp[n][k] = W[k][n] as (hi, lo) bf16, row-major [N][K] (the B operand, K-major).  32 x 32 tiles through
+// shared memory so that both the fp32 reads and the bf16 writes are coalesced (the fc layer has 1.6 M weights and the
+// image is rebuilt on every forward call).
+__global__ void __launch_bounds__(256) pack_bf16_transpose_kernel(const float* __restrict__ w, int K, int N,
+                                                                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 8 rows per pass
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    tile[r][tx] = (k < K && n < N) ? __ldg(w + (int64_t)k * N + n) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    if (n < N && k < K) {
+      uint16_t h, l;
+      split_bf16(tile[tx][r], h, l);
+      hi[(int64_t)n * K + k] = h;
+      lo[(int64_t)n * K + k] = l;
+    }
   }
 }
 // same orientation as stored (fc data-gradient: rows = inputs, K = outputs)
@@ -125,12 +140,13 @@ __global__ void pack_bf16_dgrad_kernel(const float* __restrict__ w, LayerGeom g,
 }
 
 int launch_pack_bf16_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st) {
-  for (int l = 0; l < ctx->n_layers; ++l) {
+  const int rc = launch_pack_conv1_i8(ctx, params, st);      // conv1 runs on the int8 pipe (tc2_conv1.cu)
+  if (rc != PAACB_OK) return rc;
+  for (int l = 1; l < ctx->n_layers; ++l) {
     const LayerGeom& g = ctx->layer[l];
-    const int64_t total = (int64_t)g.K * g.N;
+    const dim3 grid((unsigned)((g.N + 31) / 32), (unsigned)((g.K + 31) / 32));
     PAACB_LAUNCH_BEGIN(ctx, K_PACK, st);
-    pack_bf16_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(params + g.w_off, g.K, g.N,
-                                                                                ctx->wb_f_hi + g.w_off, ctx->wb_f_lo + g.w_off);
+    pack_bf16_transpose_kernel<<<grid, 256, 0, st>>>(params + g.w_off, g.K, g.N, ctx->wb_f_hi + g.w_off, ctx->wb_f_lo + g.w_off);
     PAACB_LAUNCH_END(ctx, K_PACK, st);
   }
   return PAACB_OK;

@@ -1,0 +1,288 @@
+// bf16-split tensor-core path, part 4: the first conv layer forward as an INT8 patch-resident implicit GEMM.
+//
+//   Y[p, co] = relu( (1/255) * sum_{kh, kw, c} X[p; kh, kw, c] * W[kh, kw, c, co] + b[co] )      networks.py:115, 12-21
+//
+// The layer's input is the uint8 state itself.  Instead of converting 28 KB of pixels per sample to a floating type
+// (the first version spent more time on that than on the MMAs), the pixels feed tcgen05.mma.kind::i8 as they are and the
+// WEIGHTS are moved to integers: per output channel, w = s_c/63 * (d0 + d1/64 + d2/4096) with three signed digits
+// |d0| <= 63, |d1|, |d2| <= 32 -- a fixed-point image of w with error <= 2^-19 of the channel's largest weight (the
+// bf16-split weights of the other layers carry 2^-18 of EACH weight).  The three digit images are three groups of N
+// columns of ONE MMA (N = 96): int32 accumulation is exact (|acc| <= 255 * 63 * 256 < 2^22), and the epilogue forms
+// s_c / (63 * 255) * (acc0 + acc1/64 + acc2/4096) + b in fp32.
+//
+// A row of the GEMM is an output position, enumerated over the input grid as in tc2_conv.cu: the patch of a tile is
+// 9 rows of each of the 4 row-parity planes of the state (input row ih = 4 q + rho), landed by the TMA engine WITHOUT
+// swizzle as 16-byte units (4 pixels x 4 channels).  Consecutive output positions are 16 bytes apart and a filter row
+// (8 pixels x 4 channels = 32 bytes = one K = 32 MMA) spans two consecutive units, which is exactly the no-swizzle
+// K-major canonical layout with LBO = 16 (the second 16-byte K chunk of row r IS the first chunk of row r + 1) and
+// SBO = 128: the overlapping windows of the convolution cost nothing.  Filter row kh is plane kh & 3 at a row offset.
+#include "tc2.cuh"
+
+namespace paacb {
+
+constexpr int kC1_N = 32;            // output channels
+constexpr int kC1_ND = 3 * kC1_N;    // MMA N: three digit images
+constexpr int kC1_WU = 21, kC1_HQ = 21, kC1_ROWS = 9, kC1_OH = 20, kC1_OW = 20;
+constexpr int kC1_PLANE = 16 * kC1_WU * kC1_ROWS;      // 3,024 bytes per parity plane patch
+constexpr int kC1_BOX = 4 * kC1_PLANE;                 // one TMA box per tile: [4 parities][9 plane rows][336 bytes]
+constexpr int kC1_SLOT = 12288;
+constexpr int kC1_NSLOTS = 6;                            // six tiles of patches in flight
+constexpr int kC1_WBYTES = 2 * kC1_ND * 128;             // K = 256 bytes per row: two 128-byte K-blocks of 96 rows
+constexpr int kC1_SMEM = kC1_NSLOTS * kC1_SLOT + kC1_WBYTES + 1024 + (2 * kC1_NSLOTS + 5) * 8 + 16;
+constexpr int kC1_THREADS = 64 + 256;
+constexpr int kC1_TMEM = 256;                            // two accumulator buffers of 96 columns at 0 and 128
+
+struct Conv1Params {
+  CUtensorMap tmA;         // uint8 states as (84 words = one 336-byte image row, b * 21 plane rows, 4 row parities)
+  CUtensorMap tmW;         // int8 digit image [96 rows = (digit, co)][256 k]
+  int num_tiles;
+  int batch;
+  const float* bias;
+  const float* wscale;     // [32]: s_c / (63 * 255)
+  uint8_t* out_hi;
+  uint8_t* out_lo;
+};
+
+// weights -> three int8 digit images + per-channel scale.  One block per output channel, one thread per k.
+__global__ void __launch_bounds__(256) pack_conv1_i8_kernel(const float* __restrict__ w, int8_t* __restrict__ wq,
+                                                            float* __restrict__ wscale) {
+  __shared__ float red[8];
+  const int c = blockIdx.x, k = threadIdx.x;
+  const float v = __ldg(w + k * kC1_N + c);
+  float m = fabsf(v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((k & 31) == 0) red[k >> 5] = m;
+  __syncthreads();
+  float s = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) s = fmaxf(s, red[i]);
+  // double arithmetic: the digits must reproduce x = 63 w / s to 2^-13 absolute
+  const double x = (s > 0.f) ? 63.0 * (double)v / (double)s : 0.0;
+  const double d0 = rint(x);
+  const double r1 = (x - d0) * 64.0;
+  const double d1 = rint(r1);
+  const double d2 = rint((r1 - d1) * 64.0);
+  wq[(0 * kC1_N + c) * 256 + k] = (int8_t)d0;
+  wq[(1 * kC1_N + c) * 256 + k] = (int8_t)d1;
+  wq[(2 * kC1_N + c) * 256 + k] = (int8_t)d2;
+  if (k == 0) wscale[c] = s / (63.0f * 255.0f);
+}
+
+int launch_pack_conv1_i8(const paacb_ctx* ctx, const float* params, cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[0];
+  if (g.K != 256 || g.N != kC1_N) return PAACB_EUNSUPPORTED;
+  PAACB_LAUNCH_BEGIN(ctx, K_PACK, st);
+  pack_conv1_i8_kernel<<<kC1_N, 256, 0, st>>>(params + g.w_off, ctx->wq_i8, ctx->wq_scale);
+  PAACB_LAUNCH_END(ctx, K_PACK, st);
+  return PAACB_OK;
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::i8 (uint8 x int8 -> int32), K = 32 per instruction
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D = int32, A = unsigned 8-bit, B = signed 8-bit, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_i8(int n) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_constant__ Conv1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;
+  uint8_t* wsm = smem + kC1_NSLOTS * kC1_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + kC1_WBYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kC1_NSLOTS;
+  uint64_t* w_bar = bars + 2 * kC1_NSLOTS;
+  uint64_t* tfull_bar = w_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kC1_NSLOTS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmW);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kC1_TMEM);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(w_bar, kC1_WBYTES);
+      tma_load_2d(wsm, &p.tmW, 0, 0, w_bar);
+      tma_load_2d(wsm + kC1_ND * 128, &p.tmW, 128, 0, w_bar);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int row0 = (int)(((int64_t)tile * 128) / kC1_WU);
+        mbar_wait(&empty_bar[slot], phase ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[slot], kC1_BOX);
+        tma_load_3d(ring + slot * kC1_SLOT, &p.tmA, 0, row0, 0, &full_bar[slot]);
+        if (++slot == kC1_NSLOTS) { slot = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const bool leader = elect_one_sync();
+    constexpr uint32_t idesc = make_idesc_i8(kC1_ND);
+    const uint64_t adesc0 = make_smem_desc(0, 16, 128, SWZ_NONE);       // rows 16 B apart, K chunks 16 B apart (overlapping windows)
+    const uint64_t bdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
+    const uint32_t ring_a = smem_u32(ring), w_a = smem_u32(wsm);
+    mbar_wait(w_bar, 0);
+    int slot = 0;
+    uint32_t phase = 0;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      const int ab = tl & 1;
+      const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+      mbar_wait(&tempty_bar[ab], aph ^ 1u);
+      tc_fence_after();
+      const uint32_t rel = (uint32_t)(((int64_t)tile * 128) % kC1_WU) * 16u;
+      const uint32_t d0 = tmem_base + (uint32_t)(ab * 128);
+      mbar_wait(&full_bar[slot], phase);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int kh = 0; kh < 8; ++kh) {           // filter row kh: parity plane kh & 3, one plane row further down for kh >= 4
+          const uint32_t a = ring_a + (uint32_t)(slot * kC1_SLOT + (kh & 3) * kC1_PLANE + (kh >> 2) * kC1_WU * 16) + rel;
+          const uint64_t bd = desc_with_addr(bdesc0, w_a + (uint32_t)((kh / 4) * (kC1_ND * 128) + (kh % 4) * 32));
+          umma_i8(d0, desc_with_addr(adesc0, a), bd, idesc, kh ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[slot]);
+      }
+      __syncwarp();
+      if (++slot == kC1_NSLOTS) { slot = 0; phase ^= 1u; }
+      if (leader) umma_commit(&tfull_bar[ab]);
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane;
+    const int grp = (warp - 2) >> 2;
+    float breg[kC1_N], sreg[kC1_N];
+#pragma unroll
+    for (int j = 0; j < kC1_N; ++j) {
+      breg[j] = __ldg(p.bias + j);
+      sreg[j] = __ldg(p.wscale + j);
+    }
+    for (int tl = grp, tile = blockIdx.x + grp * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x, tl += 2) {
+      const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+      const uint32_t q = (uint32_t)tile * 128u + (uint32_t)r;
+      const uint32_t prow = q / (uint32_t)kC1_WU;
+      const int ju = (int)(q - prow * (uint32_t)kC1_WU);
+      const uint32_t n = prow / (uint32_t)kC1_HQ;
+      const int oh = (int)(prow - n * (uint32_t)kC1_HQ);
+      const bool ok = (ju < kC1_OW) && (oh < kC1_OH) && ((int)n < p.batch);
+      const int64_t obase = (((int64_t)n * kC1_OH + oh) * kC1_OW + ju) * kC1_N;
+      mbar_wait(&tfull_bar[grp], aph);
+      tc_fence_after();
+      uint32_t v0[32], v1[32], v2[32];
+      const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(grp * 128);
+      tmem_ld32(tcol, v0);
+      tmem_ld32(tcol + 32u, v1);
+      tmem_ld32(tcol + 64u, v2);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[grp]);           // the accumulator is in registers: release the buffer before the arithmetic
+      if (ok) {
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          // |acc| < 2^22: int -> float exactly on the integer + FMA pipes (the conversion pipe issues at a quarter rate)
+          const float f0 = __uint_as_float(v0[j] + 0x4B400000u) - 12582912.0f;
+          const float f1 = __uint_as_float(v1[j] + 0x4B400000u) - 12582912.0f;
+          const float f2 = __uint_as_float(v2[j] + 0x4B400000u) - 12582912.0f;
+          const float t = fmaf(f2, 1.0f / 4096.0f, fmaf(f1, 1.0f / 64.0f, f0));
+          o[j] = fmaxf(fmaf(t, sreg[j], breg[j]), 0.f);
+        }
+        uint32_t hw[16], lw[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) split_bf16x2(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
+        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase * 2);
+        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dh[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+          dl[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kC1_TMEM);
+  }
+}
+
+int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
+                        cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[0];
+  if (g.C != 4 || g.stride != 4 || g.R != 8 || g.S != 8 || g.N != kC1_N || g.H != 84 || g.W != 84 || g.OH != kC1_OH)
+    return PAACB_EUNSUPPORTED;
+  const int64_t q_total = batch * kC1_HQ * kC1_WU;
+  if (q_total >= (1LL << 31) - 256) return PAACB_EUNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv1_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1_SMEM) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("conv1_i8: cannot set %d bytes of dynamic shared memory", kC1_SMEM);
+      return PAACB_ECUDA;
+    }
+    attr_set = true;
+  }
+  Conv1Params p;
+  memset(&p, 0, sizeof(p));
+  // an image row (84 pixels x 4 channels = 336 bytes) is ONE inner box row of 84 32-bit words (box dimensions are limited
+  // to 256 elements); plane row q = ih / 4 and row parity rho are separate dimensions (ih = 4 q + rho), parity slowest,
+  // so one box lands the four parity planes of a tile one after the other
+  const uint64_t adims[3] = {84u, (uint64_t)batch * kC1_HQ, 4u};
+  const uint64_t astr[2] = {4u * 336u, 336u};
+  const uint32_t abox[3] = {84u, (uint32_t)kC1_ROWS, 4u};
+  int rc = encode_tmap(&p.tmA, states, 4, 3, adims, astr, abox, 0);
+  const uint64_t wdims[2] = {256u, (uint64_t)kC1_ND};
+  const uint64_t wstr[1] = {256u};
+  const uint32_t wbox[2] = {128u, (uint32_t)kC1_ND};
+  if (rc == PAACB_OK) rc = encode_tmap(&p.tmW, ctx->wq_i8, 1, 2, wdims, wstr, wbox, 128);
+  if (rc != PAACB_OK) return rc;
+  p.num_tiles = (int)((q_total + 127) / 128);
+  p.batch = (int)batch;
+  p.bias = params + g.b_off;
+  p.wscale = ctx->wq_scale;
+  const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, batch);
+  p.out_hi = out.hi;
+  p.out_lo = out.lo;
+  const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);
+  PAACB_LAUNCH_BEGIN(ctx, K_FWD0, st);
+  conv1_i8_kernel<<<grid, kC1_THREADS, kC1_SMEM, st>>>(p);
+  PAACB_LAUNCH_END(ctx, K_FWD0, st);
+  return PAACB_OK;
+}
+
+}  // namespace paacb

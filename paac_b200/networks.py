@@ -97,6 +97,11 @@ class Network(object):
         self.initialize(self.seed)
 
     def set_math(self, math):
+        """'fp32' (SIMT, the parity anchor) | 'bf16x3' (tensor cores on bf16-split operands: the fast parity-grade path, Nature
+        architecture) | 'tf32x3' (tensor cores on tf32-split operands, both architectures) | 'tf32' (speed mode, not parity
+        grade) | 'auto' (bf16x3 for Nature, tf32x3 for NIPS)."""
+        if str(math).lower() == 'auto':
+            math = 'bf16x3' if self.ARCH == 'NATURE' else 'tf32x3'
         mode = {'fp32': _lib.MATH_FP32, 'tf32x3': _lib.MATH_TF32X3, 'tf32': _lib.MATH_TF32,
                 'bf16x3': _lib.MATH_BF16X3}[str(math).lower()]
         _lib.check(self._lib.paacb_set_math(self.ctx, mode), 'paacb_set_math')

@@ -75,7 +75,7 @@ def get_network_and_environment_creator(args, random_seed=3):
                     'device': args.device,
                     'clip_norm': args.clip_norm,
                     'clip_norm_type': args.clip_norm_type,
-                    'math': getattr(args, 'math', 'fp32'),
+                    'math': getattr(args, 'math', 'auto'),
                     'seed': random_seed}
     if args.arch == 'NIPS':
         network = NIPSPolicyVNetwork
@@ -114,7 +114,7 @@ def get_arg_parser():
     parser.add_argument('-df', '--debugging_folder', default='logs/', type=str, help="Folder where to save the debugging information.", dest="debugging_folder")
     parser.add_argument('-rs', '--random_start', default=True, type=bool_arg, help="Whether or not to start with 30 noops for each env. Default True", dest="random_start")
     # ---- additions (not in the reference) ----
-    parser.add_argument('--math', default='fp32', choices=['fp32', 'tf32x3', 'tf32', 'bf16x3'], help="Arithmetic of the conv/fc contractions", dest="math")
+    parser.add_argument('--math', default='auto', choices=['auto', 'fp32', 'tf32x3', 'tf32', 'bf16x3'], help="Arithmetic of the conv/fc contractions", dest="math")
     parser.add_argument('--raw_frames', default=True, type=bool_arg, help="Workers write raw frame pairs; the GPU does max-pool/resize/stack", dest="raw_frames")
     parser.add_argument('--synthetic_actions', default=6, type=int, help="num_actions of the synthetic environment", dest="synthetic_actions")
     return parser

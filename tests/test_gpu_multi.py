@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('math', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('math', ['fp32', 'tf32x3', 'bf16x3'])
 def test_two_rank_nccl_update_equals_single_rank(math):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
