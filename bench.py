@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--frame_pool', type=int, default=8, help='device frame buffers rotated between env steps')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
+    ap.add_argument('--e2e_slices', type=int, default=2, help='environment slices pipelined in the end-to-end arm')
     ap.add_argument('--ref_envs', type=int, default=64, help='--impl reference: envs per step (bounded sample)')
     return ap.parse_args()
 
@@ -305,15 +306,33 @@ def run_b200(args):
         host_onehot = torch.empty((N, A), dtype=torch.float32).pin_memory()
         host_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
         stream = torch.cuda.current_stream(dev)
+        io_stream = torch.cuda.Stream(dev)
+        S = max(1, min(args.e2e_slices, N))
+        bounds = [(c * N // S, (c + 1) * N // S) for c in range(S)]       # contiguous env slices, like the runners' workers
+        ev_act = [torch.cuda.Event() for _ in bounds]
+        ev_obs = [torch.cuda.Event() for _ in bounds]
 
         def step_host():
+            # Lock-step PAAC with the environment slices pipelined: slice c's actions go back to the host as soon as its
+            # forward is done, its environments step (here: the pre-generated frames), and its frame ingestion (PCIe-bound)
+            # overlaps the next slice's forward.  Every slice still sees act -> step -> observe in order: same results.
             eng.draw_uniforms()
             for t in range(T):
-                eng.act(t)
-                host_onehot.copy_(eng.onehot, non_blocking=True)          # the environments need the actions
-                stream.synchronize()
-                # this env step's raw frames: read by the kernel from pinned host memory inside the timed region
-                eng.observe_frames(t, host_frames[t & 1].data_ptr(), 1, None, host_rew[t], host_over[t])
+                for c, (lo, hi) in enumerate(bounds):
+                    if t > 0:
+                        stream.wait_event(ev_obs[c])                          # states[t] of this slice are complete
+                    eng.act(t, lo, hi)
+                    host_onehot[lo:hi].copy_(eng.onehot[lo:hi], non_blocking=True)      # the environments need the actions
+                    ev_act[c].record(stream)
+                for c, (lo, hi) in enumerate(bounds):
+                    ev_act[c].synchronize()                                   # host has this slice's actions: its envs step
+                    with torch.cuda.stream(io_stream):
+                        # the raw frames are read by the kernel from pinned host memory inside the timed region
+                        eng.observe_frames(t, host_frames[t & 1].data_ptr() + lo * FRAME_PAIR_BYTES, 1, None, host_rew[t],
+                                           host_over[t], lo, hi)
+                        ev_obs[c].record(io_stream)
+            for c in range(S):
+                stream.wait_event(ev_obs[c])
             eng.update(lr)
             host_loss.copy_(eng.loss, non_blocking=True)
             stream.synchronize()
@@ -325,7 +344,7 @@ def run_b200(args):
         e2e = {'value': world * N * T * e_steps / (e_ms / 1e3), 'unit': UNIT, 'steps': e_steps,
                'ms_per_step': e_ms / e_steps,
                'h2d_bytes_per_step': T * (N * 2 * 84 * 160 + 2 * 4 * N), 'd2h_bytes_per_step': T * N * A * 4 + 4,
-               'host_bytes_per_step': T * N * FRAME_PAIR_BYTES,
+               'host_bytes_per_step': T * N * FRAME_PAIR_BYTES, 'env_slices': S,
                'api': 'RolloutEngine.act / observe_frames / update over the C ABI; every env step the raw 210x160 frame '
                       'pairs are read by paacb_preprocess_u8 directly from pinned mapped host memory (zero-copy: the 84 '
                       'selected rows of both frames cross PCIe = h2d_bytes_per_step) and the sampled one-hot actions are '

@@ -6,7 +6,7 @@
 //   ObservationPool.new_observation / get_pooled_observations   environment.py:66-71
 //   reset -> fresh 4-plane stack               emulator_runner.py:26-27 + atari_emulator.py:88-96
 //
-// One CTA per env.  Phase 1 streams only the 84 source rows nearest-sampling selects (2 frames x 84 x
+// One CTA per env (grid-stride when the launcher narrows the grid).  Phase 1 streams only the 84 source rows nearest-sampling selects (2 frames x 84 x
 // 160 B, 16-byte loads, byte-wise max with __vmaxu4) into shared memory.  Phase 2 gathers the 84
 // selected columns from shared memory and merges them into the NHWC uint8 stack: a non-reset step is
 // (prev >> 8) | (new << 24) per pixel word (drop the oldest frame, append the newest as channel 3).
@@ -25,16 +25,16 @@ __device__ __forceinline__ uint4 shr8(uint4 v) { return make_uint4(v.x >> 8, v.y
 
 __global__ void __launch_bounds__(kThreads)
 preprocess_u8_kernel(const uint8_t* __restrict__ frames, int pairs, const uint8_t* __restrict__ reset,
-                     const uint8_t* prev, uint8_t* next, ResizeTables tabs) {
+                     const uint8_t* prev, uint8_t* next, ResizeTables tabs, int64_t n_envs) {
   __shared__ __align__(16) uint8_t plane[PAACB_OBS * PAACB_FRAME_W];
   __shared__ int s_row[PAACB_OBS];
   __shared__ int s_col[PAACB_OBS];
   const int tid = threadIdx.x;
-  const int64_t env = blockIdx.x;
   if (tid < PAACB_OBS) {
     s_row[tid] = tabs.row[tid] * PAACB_FRAME_W;
     s_col[tid] = tabs.col[tid];
   }
+  for (int64_t env = blockIdx.x; env < n_envs; env += gridDim.x) {
   const bool rst = (reset != nullptr) && (pairs >= PAACB_STACK) && (reset[env] != 0);
   const uint4* prev4 = reinterpret_cast<const uint4*>(prev + env * (int64_t)(kStateVec * 16));
   uint4* next4 = reinterpret_cast<uint4*>(next + env * (int64_t)(kStateVec * 16));
@@ -82,13 +82,25 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int pairs, const uint8_
     const int idx = tid + i * kThreads;
     if (idx < kStateVec) next4[idx] = acc[i];
   }
+  }
 }
 
 int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
                       const uint8_t* prev, uint8_t* next, int64_t n, cudaStream_t st) {
   if (n == 0) return PAACB_OK;
+  // Frames in pinned, mapped HOST memory (the runners' buffers, read zero-copy): the kernel is PCIe-bound and needs only
+  // ~100 KB of loads in flight, so it runs as a narrow grid-stride grid (one CTA on a subset of the SMs) that leaves
+  // room for the persistent tensor-core kernels of the next environment slice to run beside it.  Device-resident frames:
+  // HBM-bound, one CTA per environment.
+  unsigned grid = (unsigned)n;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess) {
+    if (attr.type == cudaMemoryTypeHost && n > 96) grid = 96;
+  } else {
+    cudaGetLastError();
+  }
   PAACB_LAUNCH_BEGIN(ctx, K_PREPROCESS, st);
-  preprocess_u8_kernel<<<(unsigned)n, kThreads, 0, st>>>(frames, pairs, reset, prev, next, ctx->tabs);
+  preprocess_u8_kernel<<<grid, kThreads, 0, st>>>(frames, pairs, reset, prev, next, ctx->tabs, n);
   PAACB_LAUNCH_END(ctx, K_PREPROCESS, st);
   return PAACB_OK;
 }

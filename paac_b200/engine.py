@@ -78,8 +78,7 @@ class RolloutEngine(object):
         self.opt_ws = torch.empty((int(self.lib.paacb_optimizer_workspace_floats(self.ctx)),), **f32)
         self.gen = torch.Generator(device=d)
         self.gen.manual_seed(int(seed))
-        self._graph = None
-        self._lr_dev = None
+        self._slice_ws = {}        # forward workspaces of environment slices (act(t, lo, hi))
 
     # ---- helpers ----------------------------------------------------------------------------------
     def _stream(self):
@@ -92,19 +91,36 @@ class RolloutEngine(object):
         self.uniforms.clamp_(max=float(np.nextafter(np.float32(1.0), np.float32(0.0))))
 
     # ---- rollout ----------------------------------------------------------------------------------
-    def act(self, t):
-        """Forward on states[t] + categorical sampling; fills actions[t], values[t], onehot, pi_act."""
-        self.net.forward(self.states[t], self.pi_act, self.values[t], self.act_ws, uniforms=self.uniforms[t],
-                         actions=self.actions[t], onehot=self.onehot)
+    def act(self, t, lo=0, hi=None):
+        """Forward on states[t] + categorical sampling; fills actions[t], values[t], onehot, pi_act.
+        [lo, hi) restricts the call to a contiguous slice of the environments (the runner protocol hands every worker
+        a contiguous slice, runners.py:17-18): slices can be issued on different streams so that the next slice's
+        forward overlaps this slice's frame ingestion."""
+        if hi is None:
+            hi = self.N
+        if lo == 0 and hi == self.N:
+            ws = self.act_ws
+        else:
+            ws = self._slice_ws.get((lo, hi))
+            if ws is None:
+                ws = self._slice_ws[(lo, hi)] = torch.empty((self.net.workspace_floats(hi - lo),), dtype=torch.float32,
+                                                            device=self.dev)
+        self.net.forward(self.states[t, lo:hi], self.pi_act[lo:hi], self.values[t, lo:hi], ws,
+                         uniforms=self.uniforms[t, lo:hi], actions=self.actions[t, lo:hi], onehot=self.onehot[lo:hi])
 
-    def observe_frames(self, t, frames_ptr, pairs_per_env, reset_u8, rewards, over):
-        """Raw-frame protocol: states[t+1] <- preprocess(frames | states[t]); rewards/over: device tensors."""
+    def observe_frames(self, t, frames_ptr, pairs_per_env, reset_u8, rewards, over, lo=0, hi=None):
+        """Raw-frame protocol: states[t+1] <- preprocess(frames | states[t]); rewards/over: device or pinned host tensors.
+        frames_ptr addresses the slot of environment `lo`; it may point into pinned, mapped HOST memory (the kernel then
+        reads the rows it needs zero-copy over PCIe)."""
+        if hi is None:
+            hi = self.N
         p = _lib.ptr
-        _lib.check(self.lib.paacb_preprocess_u8(self.ctx, C.c_void_p(frames_ptr), int(pairs_per_env), p(reset_u8),
-                                                p(self.states[t]), p(self.states[t + 1]), self.N, self._stream()),
-                   'paacb_preprocess_u8')
-        self.rewards[t].copy_(rewards, non_blocking=True)
-        self.over[t].copy_(over, non_blocking=True)
+        _lib.check(self.lib.paacb_preprocess_u8(self.ctx, C.c_void_p(frames_ptr), int(pairs_per_env),
+                                                p(reset_u8[lo:hi]) if reset_u8 is not None else None,
+                                                p(self.states[t, lo:hi]), p(self.states[t + 1, lo:hi]), hi - lo,
+                                                self._stream()), 'paacb_preprocess_u8')
+        self.rewards[t, lo:hi].copy_(rewards[lo:hi] if rewards.shape[0] == self.N else rewards, non_blocking=True)
+        self.over[t, lo:hi].copy_(over[lo:hi] if over.shape[0] == self.N else over, non_blocking=True)
 
     def observe_states(self, t, states, rewards, over):
         """Classic protocol: the environments produced stacked 84x84x4 observations themselves."""

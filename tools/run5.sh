@@ -1,2 +1,1 @@
-timeout 600 python bench.py --no_cpu_baseline > gpurun_out/bench_bf16x3.log 2> gpurun_out/bench_bf16x3.err; echo bench rc=$?
-tail -2 gpurun_out/bench_bf16x3.err
+for s in 1 2 4; do timeout 600 python bench.py --no_cpu_baseline --e2e_slices $s > gpurun_out/bench_e2e_s$s.log 2> gpurun_out/bench_e2e_s$s.err; echo bench s=$s rc=$?; done
