@@ -181,7 +181,7 @@ struct Geo;
 // conv2 forward: [b,20,20,32] 4x4 stride 2 -> [b,9,9,64].  Unit = 2 pixels x 32 channels = 128 B; 2 row-parity planes.
 template <>
 struct Geo<G_FWD2> {
-  static constexpr bool DGRAD = false, A_LO = true;
+  static constexpr bool DGRAD = false, A_LO = true, STAGED = false;
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 2, WU = 10, HQ = 10, BOX_ROWS = 15, SLOT = 19456, NSLOTS = 5;
   static constexpr int NACC = 1, BN = 64, KS = 16, KB = 8, OH = 9, OW = 9;
   __host__ __device__ static constexpr int aoff(int t) { return ((t / 8) * 10 + ((t / 4) % 2)) * 128 + (t % 4) * 32; }
@@ -190,7 +190,7 @@ struct Geo<G_FWD2> {
 // conv3 forward: [b,9,9,64] 3x3 stride 1 -> [b,7,7,64].  Unit = 1 pixel x 64 channels = 128 B.
 template <>
 struct Geo<G_FWD3> {
-  static constexpr bool DGRAD = false, A_LO = true;
+  static constexpr bool DGRAD = false, A_LO = true, STAGED = false;
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 9, HQ = 9, BOX_ROWS = 18, SLOT = 21504, NSLOTS = 3;
   static constexpr int NACC = 1, BN = 64, KS = 36, KB = 9, OH = 7, OW = 7;
   __host__ __device__ static constexpr int aoff(int t) { return (((t / 4) / 3) * 9 + ((t / 4) % 3)) * 128 + (t % 4) * 32; }
@@ -200,7 +200,7 @@ struct Geo<G_FWD3> {
 // zero-padded dZ (TMA out-of-bounds fill), tap (kh, kw) reads position q + (2-kh)*11 + (2-kw).
 template <>
 struct Geo<G_DG3> {
-  static constexpr bool DGRAD = true, A_LO = true;
+  static constexpr bool DGRAD = true, A_LO = true, STAGED = false;
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 9, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 4;
   static constexpr int NACC = 1, BN = 64, KS = 36, KB = 9, OH = 9, OW = 9;       // OH/OW: valid rows/cols of the enumeration
   static constexpr int PAD = 2, S = 1, XH = 9, XW = 9;
@@ -209,10 +209,14 @@ struct Geo<G_DG3> {
 };
 // conv2 data-gradient: dZ2 [b,9,9,64] -> dX [b,20,20,32]; the four stride-parity classes are four accumulators over
 // the same resident dZ patch (class (ph, pw), tap (tj, ti) reads position q + (1-tj)*11 + (1-ti)).
+// STAGED epilogue: a thread's outputs of the two classes (ph, 0), (ph, 1) are one 128-byte row (2 pixels x 32 channels)
+// of a [10 x 10 rows] x 128 B tile per output-row parity ph; written straight to HBM every warp store touched 32
+// different cache lines (the first version was bound by LSU wavefronts: 34 % tensor-pipe activity).  The rows go to a
+// swizzled shared-memory tile instead and the TMA engine stores the tile.
 template <>
 struct Geo<G_DG2> {
-  static constexpr bool DGRAD = true, A_LO = true;
-  static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 10, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 5;
+  static constexpr bool DGRAD = true, A_LO = true, STAGED = true;
+  static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 10, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 4;
   static constexpr int NACC = 4, BN = 32, KS = 16, KB = 4, OH = 10, OW = 10;
   static constexpr int PAD = 1, S = 2, XH = 20, XW = 20;
   __host__ __device__ static constexpr int aoff(int t) { return ((1 - (t / 4) / 2) * 11 + (1 - (t / 4) % 2)) * 128 + (t % 4) * 32; }
@@ -222,6 +226,7 @@ struct Geo<G_DG2> {
 struct ConvKParams {
   CUtensorMap tmA[2];      // source planes (hi, lo); forward: dims (unit, units/row, row parity, plane rows); dgrad: (C, OW, OH, b)
   CUtensorMap tmW[2];      // packed weights (hi, lo): dims (K, rows)
+  CUtensorMap tmOut[2];    // staged epilogue: output planes (hi, lo) as (2 px x C, W/2, row parity, b * H/2)
   int num_tiles;
   int batch;
   const float* bias;       // forward
@@ -243,11 +248,14 @@ struct ConvKCfg {
   static constexpr int KB_BYTES = 2 * NT * 128;
   static constexpr int W_BYTES = Ge::KB * KB_BYTES;
   static constexpr int BOX_BYTES = Ge::UB * Ge::WU * Ge::BOX_ROWS;
-  static constexpr int NBARS = 2 * Ge::NSLOTS + 1 + 4;
-  static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + 1024 /* alignment slack */ + NBARS * 8 + 16;
+  static constexpr int STG_TILE = 13 * 1024;                                // 100 rows x 128 B, 1024-byte aligned
+  static constexpr int STG_BYTES = Ge::STAGED ? 2 * STG_TILE : 0;            // one tile per output-row parity: hi plane, then lo plane
+  static constexpr int NBARS = 2 * Ge::NSLOTS + 1 + 4 + 1;
+  static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + STG_BYTES + 1024 /* alignment slack */ + NBARS * 8 + 16;
   static constexpr int TMEM_COLS = 4 * NT;                                  // two accumulator buffers of 2 * NT columns
   static_assert(BOX_BYTES <= Ge::SLOT && Ge::SLOT % 1024 == 0, "slot too small");
-  // TMA warp, MMA warp, two epilogue groups of four warps (one per accumulator buffer)
+  // TMA warp, MMA warp, two epilogue groups of four warps (one per accumulator buffer; the staged epilogue splits every
+  // tile between the groups: output-row parity 0 / 1)
   static constexpr int THREADS = 64 + 256;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
@@ -279,13 +287,15 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
   uint8_t* wsm = smem + Cfg::RING_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + Cfg::W_BYTES);
+  uint8_t* stg = wsm + Cfg::W_BYTES;              // staged epilogue tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + Cfg::STG_BYTES);
   uint64_t* full_bar = bars;                      // [NSLOTS] TMA -> MMA
   uint64_t* empty_bar = bars + NSLOTS;            // [NSLOTS] MMA commit -> TMA
   uint64_t* w_bar = bars + 2 * NSLOTS;            // weights resident
   uint64_t* tfull_bar = w_bar + 1;                // [2] MMA commit -> epilogue
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* mask_bar = tempty_bar + 2;            // staged epilogue: the staging tiles have been read out by the TMA stores
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -296,9 +306,10 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(w_bar, 1);
+    mbar_init(mask_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);        // the four warps of the epilogue group that owns buffer s
+      mbar_init(&tempty_bar[s], Ge::STAGED ? 256 : 128);     // the epilogue warps that drain buffer s
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA[0]);
@@ -384,6 +395,112 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
       }
       if (leader) umma_commit(&tfull_bar[ab]);
       __syncwarp();
+    }
+  } else if (Ge::STAGED) {
+    // =========================== staged epilogue (conv2 data-gradient) ===========================
+    if constexpr (Ge::STAGED) {
+      const int ew = warp & 3;
+      const int r = ew * 32 + lane;
+      const int qh = r / Ge::WU, qw = r - qh * Ge::WU;
+      const bool ok = (qh < Ge::OH) && (qw < Ge::OW);
+      const uint32_t srow = (uint32_t)(qh * Ge::OW + qw);                  // row of the 100 x 128 B staging tile
+      const uint32_t stg_a = smem_u32(stg);
+      const int ph = (warp - 2) >> 2;                                       // this warp's output-row parity: classes (ph, 0), (ph, 1)
+      const bool io = (tid == 64 + 128 * ph);                               // issues the TMA stores of this group's tile
+      float bsum = 0.f;
+      // the ReLU-mask words of this thread's two output pixels, software-pipelined ONE TILE AHEAD: a load issued in the
+      // tile it is used in exposed a DRAM round trip per tile (it was the top stall of the staged epilogue's first version)
+      uint4 mk[2][4], mkn[2][4];
+      auto load_mask = [&](int tile, uint4 (&m)[2][4]) {
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+          const int64_t ob = (((int64_t)tile * Ge::XH + Ge::S * qh + ph) * Ge::XW + Ge::S * qw + pw) * BN;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m[pw][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok && tile < p.num_tiles) m[pw][j] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + ob * 2) + j);
+          }
+        }
+      };
+      load_mask((int)blockIdx.x, mkn);
+      int tl = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+        const int ab = tl & 1;
+        const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mk[pw][j] = mkn[pw][j];
+        load_mask(tile + (int)gridDim.x, mkn);
+        mbar_wait(&tfull_bar[ab], aph);
+        tc_fence_after();
+        float o[2][32];
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+          uint32_t v[32], v2[32];
+          const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * 2 * Cfg::NT + (ph * 2 + pw) * BN);
+          tmem_ld32(tcol, v);
+          tmem_ld32(tcol + (uint32_t)Cfg::NT, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t mw[4] = {mk[pw][c].x, mk[pw][c].y, mk[pw][c].z, mk[pw][c].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = c * 8 + j * 2;
+              // bf16 > 0  <=>  the 16 bits, as a signed integer in the top half of a word, are > 0
+              const bool p0 = ok && ((int32_t)(mw[j] << 16) > 0), p1 = ok && ((int32_t)(mw[j] & 0xffff0000u) > 0);
+              o[pw][e] = p0 ? __uint_as_float(v[e]) + __uint_as_float(v2[e]) : 0.f;
+              o[pw][e + 1] = p1 ? __uint_as_float(v[e + 1]) + __uint_as_float(v2[e + 1]) : 0.f;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[ab]);                                       // accumulator drained: the MMAs of tile tl + 2 may start
+        // This group's 100 x 128 B staging tile carries the hi plane, then the lo plane (shared memory is needed for a
+        // 4-deep patch ring: with 2 slots the kernel was bound by the TMA round trip).  io = the group's first thread.
+        uint8_t* tile_p = stg + ph * Cfg::STG_TILE;
+        const uint32_t t_row = stg_a + (uint32_t)(ph * Cfg::STG_TILE) + srow * 128u;
+        uint32_t lw[2][16];
+        if (io) tma_store_wait_read();                                      // previous tile's lo plane has been read out
+        named_bar_sync(1 + ph, 128);
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+          uint32_t hw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_bf16x2(o[pw][2 * j], o[pw][2 * j + 1], hw[j], lw[pw][j]);
+          if (ok) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)                                     // 16-byte chunk pw * 4 + c of the row, swizzled
+              sts128(t_row + ((((uint32_t)(pw * 4 + c)) ^ (srow & 7u)) << 4), make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]));
+          }
+        }
+        fence_proxy_async();                                                // staging writes -> visible to the TMA engine
+        named_bar_sync(1 + ph, 128);
+        if (io) {
+          tma_store_4d(&p.tmOut[0], tile_p, 0, 0, ph, tile * Ge::OH);
+          tma_store_commit();
+        }
+        // bias gradient: channel = lane for both classes (the shuffles overlap the TMA engine reading the tile)
+        bsum += warp_transpose_sum(o[0], lane) + warp_transpose_sum(o[1], lane);
+        if (io) tma_store_wait_read();
+        named_bar_sync(1 + ph, 128);
+        if (ok) {
+#pragma unroll
+          for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              sts128(t_row + ((((uint32_t)(pw * 4 + c)) ^ (srow & 7u)) << 4), make_uint4(lw[pw][4 * c], lw[pw][4 * c + 1], lw[pw][4 * c + 2], lw[pw][4 * c + 3]));
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + ph, 128);
+        if (io) {
+          tma_store_4d(&p.tmOut[1], tile_p, 0, 0, ph, tile * Ge::OH);
+          tma_store_commit();
+        }
+      }
+      if (io) tma_store_wait_all();
+      if (p.dbias != nullptr) atomicAdd(p.dbias + lane, bsum);
     }
   } else {
     // =========================== epilogue ===========================
@@ -625,6 +742,13 @@ int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, void
     if (rc == PAACB_OK)                                                                                            \
       rc = weight_maps(ctx, ctx->wb_d_hi, ctx->wb_d_lo, g, (uint64_t)(g.R / s) * (g.S / s) * g.N,                  \
                        (uint64_t)s * s * g.C, Ge::BN, p.tmW);                                                      \
+    if (rc == PAACB_OK && Ge::STAGED) {                                                                            \
+      const uint64_t od[4] = {(uint64_t)2 * g.C, (uint64_t)g.W / 2, 2u, (uint64_t)batch * (g.H / 2)};              \
+      const uint64_t os[3] = {(uint64_t)2 * g.C * 2, (uint64_t)g.W * g.C * 2, (uint64_t)2 * g.W * g.C * 2};        \
+      const uint32_t ob[4] = {(uint32_t)(2 * g.C), (uint32_t)(g.W / 2), 1u, (uint32_t)(g.H / 2)};                  \
+      rc = encode_tmap_bf16(&p.tmOut[0], dx.hi, 4, od, os, ob, 128);                                               \
+      if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmOut[1], dx.lo, 4, od, os, ob, 128);                           \
+    }                                                                                                              \
     if (rc != PAACB_OK) return rc;                                                                                 \
     return launch_convk<GE>(ctx, p, K_DGRAD0 + l, st);                                                             \
   }

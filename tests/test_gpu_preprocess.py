@@ -80,3 +80,21 @@ def test_large_batch_properties(net):
     mx = torch.maximum(frames[:, 0, 0], frames[:, 0, 1])
     row = torch.as_tensor(ROW, device='cuda', dtype=torch.long); col = torch.as_tensor(COL, device='cuda', dtype=torch.long)
     assert torch.equal(out[..., 3], mx[:, row][:, :, col])
+
+
+@pytest.mark.parametrize('n', [5, 300])
+def test_zero_copy_from_pinned_host_frames(net, n):
+    """The runners' frame buffers live in pinned, mapped host memory (Runners.pin()); the kernel reads them in place
+    (narrow grid-stride launch for n > 96).  Same bytes as with device-resident frames."""
+    from paac_b200 import _lib
+    rng = np.random.RandomState(100 + n)
+    frames = torch.from_numpy(rng.randint(0, 256, (n, 4, 2, 210, 160)).astype(np.uint8)).pin_memory()
+    prev = rng.randint(0, 256, (n, 84, 84, 4)).astype(np.uint8)
+    reset = (rng.random_sample(n) < 0.3).astype(np.uint8)
+    want = opre.step_states(prev, frames.numpy(), reset, ROW, COL)
+    p, r = G.dev(prev), G.dev(reset)
+    out = torch.empty_like(p)
+    _lib.check(net._lib.paacb_preprocess_u8(net.ctx, frames.data_ptr(), 4, _lib.ptr(r), _lib.ptr(p), _lib.ptr(out), n,
+                                            G.stream()), 'paacb_preprocess_u8')
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)

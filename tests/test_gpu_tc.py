@@ -106,3 +106,30 @@ def test_engine_update_tc_vs_oracle_composite(math):
     got = net.get_params()
     assert_close(got, want, 1e-5, 'post-RMSProp weights')
     assert_close(got - p0, want - p0, 2e-3, 'weight delta')
+
+
+def test_sliced_act_observe_equals_whole_batch():
+    """RolloutEngine.act / observe_frames on contiguous environment slices (what the pipelined end-to-end loop issues on
+    two streams) produce the same actions, values and states as the whole-batch calls."""
+    arch, A, N, T = 'NATURE', 6, 24, 2
+    rng = np.random.RandomState(7)
+    s0 = rng.randint(0, 256, (N, 84, 84, 4)).astype(np.uint8)
+    frames = G.dev(rng.randint(0, 256, (T, N, 1, 2, 210, 160)).astype(np.uint8))
+    rew = G.dev(rng.choice([-1.0, 0.0, 1.0], size=(T, N)).astype(np.float32))
+    over = G.dev(np.zeros((T, N), np.float32))
+    outs = []
+    for slices in ([(0, N)], [(0, 8), (8, 24)]):
+        net = G.make_net(arch, A, seed=5, math='bf16x3')
+        eng = RolloutEngine(net, N, T, seed=9)
+        eng.states[0].copy_(G.dev(s0))
+        eng.draw_uniforms()
+        for t in range(T):
+            for lo, hi in slices:
+                eng.act(t, lo, hi)
+            for lo, hi in slices:
+                eng.observe_frames(t, frames[t, lo].data_ptr(), 1, None, rew[t], over[t], lo, hi)
+        torch.cuda.synchronize()
+        outs.append((eng.actions.cpu().numpy(), eng.values.cpu().numpy(), eng.states.cpu().numpy(), eng.rewards.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][2], outs[1][2])
+    assert np.array_equal(outs[0][3], outs[1][3])
+    assert_close(outs[1][1], outs[0][1], 1e-6, 'values of sliced vs whole-batch forward')
