@@ -41,7 +41,7 @@ K1_ALGO_BYTES = 33936            # 84 rows x 160 B x 2 frames read + 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='environments per GPU')
@@ -102,7 +102,7 @@ class ClockSampler(object):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -169,6 +169,28 @@ def read_profile(net):
     return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank on the CPUs that are local to its GPU, BEFORE the pinned frame buffers are allocated: the kernel reads
+    them over PCIe, and first-touch puts the pages on the node of the allocating thread.  Without it two ranks on one host
+    halved each other's end-to-end rate (remote-socket reads).  Best effort: silently skipped where NVML says nothing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        index = int(visible.split(',')[local]) if visible and visible.split(',')[local].isdigit() else local
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = [i for i in range(ncpu) if ((mask[i // 64] >> (i % 64)) & 1) and i in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -181,6 +203,8 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)')
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -344,7 +368,7 @@ def run_b200(args):
         e2e = {'value': world * N * T * e_steps / (e_ms / 1e3), 'unit': UNIT, 'steps': e_steps,
                'ms_per_step': e_ms / e_steps,
                'h2d_bytes_per_step': T * (N * 2 * 84 * 160 + 2 * 4 * N), 'd2h_bytes_per_step': T * N * A * 4 + 4,
-               'host_bytes_per_step': T * N * FRAME_PAIR_BYTES, 'env_slices': S,
+               'host_bytes_per_step': T * N * FRAME_PAIR_BYTES, 'env_slices': S, 'cpus_bound_to_gpu_node': numa_cpus,
                'api': 'RolloutEngine.act / observe_frames / update over the C ABI; every env step the raw 210x160 frame '
                       'pairs are read by paacb_preprocess_u8 directly from pinned mapped host memory (zero-copy: the 84 '
                       'selected rows of both frames cross PCIe = h2d_bytes_per_step) and the sampled one-hot actions are '
@@ -353,6 +377,7 @@ def run_b200(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)               # the CPU baseline gets every host core again
         from oracle import cpu_baseline
         c_envs = 32
         sps, cms, done, cores = cpu_baseline.time_cycles(args.arch, c_envs, T, A, steps=1000, warmup=1, max_seconds=15)
