@@ -157,6 +157,21 @@ def layer_macs(arch):
     return [('conv1', 400 * 256 * 16, False), ('conv2', 81 * 256 * 32, True), ('fc3', 2592 * 256, True)]
 
 
+def layer_bytes(arch, kind, li, elem_in, state_bytes=28224):
+    """Compulsory HBM bytes per sample of one conv/fc kernel: operands read once + result written once, at the storage
+    widths of the arithmetic mode (activations / dZ: 4 bytes per element in every mode -- fp32, or two bf16 planes; the
+    uint8 state: 1 byte; the ReLU-mask plane a data-gradient kernel reads: 2 bytes per element in bf16x3, 4 otherwise)."""
+    if arch == 'NATURE':
+        elems = [20 * 20 * 32, 9 * 9 * 64, 7 * 7 * 64, 512]
+    else:
+        elems = [20 * 20 * 16, 9 * 9 * 32, 256]
+    x_in = state_bytes if li == 0 else 4 * elems[li - 1]
+    y_out = 4 * elems[li]
+    if kind in ('fwd', 'wgrad'):
+        return x_in + y_out                       # fwd: read X, write Y; wgrad: read X and dZ (the small dW is atomics in L2)
+    return y_out + elem_in * elems[li - 1] + 4 * elems[li - 1]      # dgrad: read dZ + mask plane of X, write dX
+
+
 def read_profile(net):
     lib = net._lib
     out = {}
@@ -288,9 +303,18 @@ def run_b200(args):
             if key in prof and samples:
                 ms, cnt = prof[key]
                 ach = 2.0 * macs * samples / (ms / 1e3) / 1e12
-                kernels.append({'name': key, 'ms': ms, 'launches': cnt, 'bound': 'tensor', 'achieved': ach,
-                                'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': ach / tf32_peak,
-                                'algo_per_launch': 2.0 * macs * samples / cnt})
+                nbytes = float(layer_bytes(args.arch, kind, li, 2 if bf16_math else 4)) * samples
+                ach_b = nbytes / (ms / 1e3) / 1e9
+                row = {'name': key, 'ms': ms, 'launches': cnt, 'frac_tensor': ach / tf32_peak, 'tflops': ach,
+                       'frac_hbm': ach_b / hbm_peak, 'gbs': ach_b}
+                # the roofline that binds this kernel is the one it is closer to
+                if row['frac_hbm'] >= row['frac_tensor']:
+                    row.update(bound='hbm', achieved=ach_b, peak=hbm_peak, unit='GB/s', frac=row['frac_hbm'],
+                               algo_per_launch=nbytes / cnt)
+                else:
+                    row.update(bound='tensor', achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=row['frac_tensor'],
+                               algo_per_launch=2.0 * macs * samples / cnt)
+                kernels.append(row)
     def hbm_row(key, bytes_total):
         if key in prof:
             ms, cnt = prof[key]
@@ -304,17 +328,33 @@ def run_b200(args):
     F = 512 if args.arch == 'NATURE' else 256
     hbm_row('heads_fwd', 4.0 * F * (T * N + N + B) * args.steps)       # reads the hidden activations once
     hbm_row('heads_bwd', 8.0 * F * B * args.steps)                     # reads h, writes dh
+    # measured DRAM traffic (dram__bytes_read + write from `ncu --set full`, tools/ncu_dram_table.py) per unit, committed
+    # under profiles/: traffic per launch = bytes per sample x the samples an average launch of that kernel processes
+    dram_table, dram_src = {}, None
+    try:
+        dj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_dram_bytes.json')))
+        dram_table, dram_src = dj['kernels'], dj['source']
+    except Exception:
+        pass
+    units_total = {'preprocess_u8': N * T * args.steps, 'heads_fwd': fwd_samples, 'heads_bwd': B * args.steps}
+    for k in kernels:
+        kind = k['name'].rsplit('_', 1)[-1]
+        units = units_total.get(k['name'], fwd_samples if kind == 'fwd' else B * args.steps)
+        if bf16_math and k['name'] in dram_table:
+            k['traffic'] = dram_table[k['name']]['dram_bytes_per_unit'] * units / k['launches']
     accounted = sum(k['ms'] for k in kernels)
     for k in kernels:
         k['share_of_step'] = k['ms'] / ms_total
     kernels.sort(key=lambda k: -k['ms'])
     dom = kernels[0]
     roofline = {'kernel': dom['name'], 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'],
-                'unit': dom['unit'], 'frac': dom['frac'], 'traffic': None, 'share_of_step': dom['share_of_step'],
+                'unit': dom['unit'], 'frac': dom['frac'], 'traffic': dom.get('traffic'), 'traffic_source': dram_src,
+                'share_of_step': dom['share_of_step'],
                 'launches': dom['launches'], 'avg_launch_ms': dom['ms'] / dom['launches'],
                 'algo_per_launch': dom['algo_per_launch'],
+                'frac_tensor': dom.get('frac_tensor'), 'frac_hbm': dom.get('frac_hbm'),
                 'peak_source': ('%s: MEASURED_PEAKS.json ' % peak_kind) +
-                               (peak_note if dom['bound'] == 'tensor' else 'hbm_gbs')}
+                               (peak_note if dom['bound'] == 'tensor' else 'hbm_gbs (copy bandwidth)')}
     # nominal whole-step fraction: contract flops per env-step / tf32 peak
     flops_per_env_step = 71.96e6 if args.arch == 'NATURE' else 21.65e6
     step_frac = (value / world) * flops_per_env_step / 1e12 / tf32_peak

@@ -18,9 +18,18 @@ grads = torch.zeros((net.param_count,), device='cuda')
 dl = torch.randn((b, A), device='cuda') * 1e-4; dv = torch.randn((b,), device='cuda') * 1e-4
 p = _lib.ptr
 import ctypes as C
+ne = min(b, 4096)
+frames = torch.randint(0, 256, (ne, 1, 2, 210, 160), dtype=torch.uint8, device='cuda')
+nxt = torch.empty((ne, 84, 84, 4), dtype=torch.uint8, device='cuda')
 for it in range(2):
+    if it == 1:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()          # ncu --profile-from-start off: capture exactly the second pass
+    _lib.check(net._lib.paacb_preprocess_u8(net.ctx, p(frames), 1, None, p(st[:ne]), p(nxt), ne,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'k1')
     net.forward(st, pi, v, ws)
     _lib.check(net._lib.paacb_backward(net.ctx, p(net.params), p(st), b, p(ws), p(dl), p(dv), p(bws), p(grads),
                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'bwd')
     torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print('profile_step done', float(grads.abs().sum()))
