@@ -225,6 +225,15 @@ def main():
                           input_scale=float(tf_graph._const(g.nodes['local_learning/scalar'])))
     with open(os.path.join(OUT, 'tf_graph_pins.json'), 'w') as f:
         json.dump(pins, f, indent=1, sort_keys=True)
+
+    # ---------------- 5. the shipped checkpoint-bundle index tables (TF 1.0.1 Saver output, ~1.3 KB each) -----------
+    # data artefacts, copied verbatim: tests/test_tf_bundle.py parses them and re-serialises them byte for byte
+    import shutil
+    for game in sorted(os.listdir(os.path.join(REF, 'pretrained'))):
+        ck = os.path.join(REF, 'pretrained', game, 'checkpoints')
+        idx = [f for f in os.listdir(ck) if f.endswith('.index')] if os.path.isdir(ck) else []
+        if idx:
+            shutil.copyfile(os.path.join(ck, idx[0]), os.path.join(OUT, 'tf_index_%s.index' % game))
     print('golden written to', OUT, {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})
 
 

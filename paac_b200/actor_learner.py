@@ -58,9 +58,10 @@ class ActorLearner(Process):
 
         self.session = Session()
 
-        self.network_saver = Saver(self._get_network_state, self._set_network_state)
+        scope = getattr(self.network, 'name', 'local_learning')
+        self.network_saver = Saver(self._get_network_state, self._set_network_state, scope=scope)
         self.optimizer_saver = Saver(self._get_optimizer_state, self._set_optimizer_state, max_to_keep=1,
-                                     name='OptimizerSaver')
+                                     name='OptimizerSaver', scope=scope)
 
     # ---- checkpoint payloads: TF variable names, reference layouts -----------------
     def _get_network_state(self):

@@ -4,7 +4,7 @@ The reference drives its TF graph through ``session.run(fetches, feed_dict)`` (p
 163-165) and checkpoints through ``tf.train.Saver`` (actor_learner.py:79-93).  ``Session.run`` here
 understands exactly the fetches that appear on the hot path -- the network's ``output_layer_v`` /
 ``output_layer_pi`` given ``{network.input_ph: states}`` -- and dispatches them to the C-ABI forward.
-``Saver`` stores the flat parameter buffer with the TF variable names via torch.save.
+``Saver`` stores the variables as a TensorFlow-1 tensor bundle under the reference's names (tf_bundle.py).
 """
 import glob
 import os
@@ -57,26 +57,62 @@ def forward_numpy(net, states, uniforms=None):
 
 
 class Saver(object):
-    """tf.train.Saver stand-in: ``<folder>-<step>.pt`` files, newest wins, ``max_to_keep`` honoured."""
+    """tf.train.Saver stand-in (actor_learner.py:79-93).  Checkpoints are TensorFlow-1 tensor bundles
+    (``<folder>/-<step>.index`` + ``.data-00000-of-00001`` + the ``checkpoint`` state file, tf_bundle.py) holding the
+    variables under the reference's names -- ``<name>_1/conv1_weights`` ... for the trunk, ``<name>_2/actor_output_*`` /
+    ``critic_output_*`` for the heads, ``.../OptimizerVariables[_1]`` for the RMSProp slots -- so the
+    folders are interchangeable with the reference's ``pretrained/*`` layout.  ``max_to_keep`` honoured; ``.pt`` files
+    written by earlier versions are still restored."""
 
-    def __init__(self, get_state, set_state, max_to_keep=5, name='Saver'):
-        self.get_state, self.set_state, self.max_to_keep, self.name = get_state, set_state, max_to_keep, name
+    def __init__(self, get_state, set_state, max_to_keep=5, name='Saver', scope='local_learning'):
+        self.get_state, self.set_state, self.max_to_keep, self.name, self.scope = get_state, set_state, max_to_keep, name, scope
+
+    def _tf_name(self, key):
+        base = key.split('/')[0]
+        head = base.startswith('actor_output') or base.startswith('critic_output')
+        return '%s_%d/%s' % (self.scope, 2 if head else 1, key)
+
+    @staticmethod
+    def _step_of(path):
+        return int(os.path.basename(path)[1:].split('.')[0])
 
     @staticmethod
     def latest_checkpoint(folder):
-        files = glob.glob(os.path.join(folder, '-*.pt'))
+        state = os.path.join(folder, 'checkpoint')
+        if os.path.exists(state):
+            for line in open(state):
+                if line.startswith('model_checkpoint_path:'):
+                    prefix = os.path.join(folder, line.split('"')[1])
+                    if os.path.exists(prefix + '.index'):
+                        return prefix
+        files = [f[:-len('.index')] for f in glob.glob(os.path.join(folder, '-*.index'))]
+        files += glob.glob(os.path.join(folder, '-*.pt'))
         if not files:
             return None
-        return max(files, key=lambda f: int(os.path.basename(f)[1:].split('.')[0]))
+        return max(files, key=Saver._step_of)
 
     def save(self, session, folder, global_step):
+        from . import tf_bundle
         os.makedirs(folder, exist_ok=True)
-        path = os.path.join(folder, '-%d.pt' % int(global_step))
-        torch.save(self.get_state(), path)
-        files = sorted(glob.glob(os.path.join(folder, '-*.pt')), key=lambda f: int(os.path.basename(f)[1:].split('.')[0]))
-        for old in files[:-self.max_to_keep]:
-            os.remove(old)
-        return path
+        prefix = os.path.join(folder, '-%d' % int(global_step))
+        tf_bundle.write_bundle(prefix, {self._tf_name(k): v.numpy() for k, v in self.get_state().items()})
+        tf_bundle.write_checkpoint_state(folder, '-%d' % int(global_step))
+        kept = sorted((f[:-len('.index')] for f in glob.glob(os.path.join(folder, '-*.index'))), key=Saver._step_of)
+        for old in kept[:-self.max_to_keep]:
+            for ext in ('.index', '.data-00000-of-00001'):
+                if os.path.exists(old + ext):
+                    os.remove(old + ext)
+        return prefix
 
     def restore(self, session, path):
-        self.set_state(torch.load(path, map_location='cpu'))
+        if path.endswith('.pt'):
+            self.set_state(torch.load(path, map_location='cpu'))
+            return
+        from . import tf_bundle
+        tensors = tf_bundle.read_bundle(path)
+        wanted = self.get_state().keys()
+        by_key = {name.split('/', 1)[1]: torch.from_numpy(a) for name, a in tensors.items() if '/' in name}
+        missing = [k for k in wanted if k not in by_key]
+        if missing:
+            raise KeyError('checkpoint %s lacks variables %s' % (path, missing[:4]))
+        self.set_state({k: by_key[k] for k in wanted})

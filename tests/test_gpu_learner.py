@@ -52,3 +52,28 @@ def test_checkpoint_resume(tmp_path):
     step0 = l2.init_network()
     assert step0 == 8 * 5 * 3 and np.array_equal(l2.network.get_params(), w)
     assert abs(float(l2.engine.ms.mean().item()) - 1.0) > 0          # optimizer slots restored, no longer all ones
+
+
+@pytest.mark.timeout(300)
+def test_evaluation_loop_restores_tf_bundle_checkpoint(tmp_path):
+    """test.py mirror: train a little, checkpoint (TensorFlow-1 bundle layout under <df>/checkpoints), then the evaluation
+    loop restores the newest checkpoint from args.json + folder alone and plays episodes to the end."""
+    import os
+    from paac_b200 import logger_utils, tf_bundle, train
+    from paac_b200 import test as evaluation
+    from paac_b200.paac import PAACLearner
+    args = _args(tmp_path, True)
+    logger_utils.save_args(args, args.debugging_folder)
+    nc, ec = train.get_network_and_environment_creator(args)
+    learner = PAACLearner(nc, ec, args)
+    learner.train()
+    learner.cleanup()
+    w = learner.network.get_params()
+    ck = os.path.join(args.debugging_folder, 'checkpoints')
+    assert os.path.exists(os.path.join(ck, 'checkpoint')) and os.path.exists(os.path.join(ck, '-120.index'))
+    _, entries = tf_bundle.read_index(os.path.join(ck, '-120.index'))
+    assert entries['local_learning_1/conv1_weights'].shape == (8, 8, 4, 32)
+    assert entries['local_learning_2/actor_output_weights'].shape == (512, 6)
+    eargs = evaluation.get_arg_parser().parse_args(['-f', args.debugging_folder, '-tc', '3', '-np', '2'])
+    rewards = evaluation.evaluate(eargs)
+    assert rewards.shape == (3,) and np.all(np.isfinite(rewards))
