@@ -120,6 +120,16 @@ def test_saver_roundtrip(tmp_path):
     sv.save(None, str(tmp_path) + '/', 10)
     sv.save(None, str(tmp_path) + '/', 1000000)
     path = Saver.latest_checkpoint(str(tmp_path) + '/')
-    assert path.endswith('-1000000.pt') and len(os.listdir(tmp_path)) == 1
+    # a TensorFlow-1 bundle prefix (tf.train.latest_checkpoint returns the prefix too): .index + .data + `checkpoint`
+    assert path.endswith('-1000000') and sorted(os.listdir(tmp_path)) == ['-1000000.data-00000-of-00001', '-1000000.index',
+                                                                           'checkpoint']
+    sv.restore(None, path)
+    # checkpoints written by earlier versions of this package (torch.save) still restore
+    torch.save({'w': torch.arange(6.0) + 1}, str(tmp_path / '-2000000.pt'))
+    os.remove(str(tmp_path / 'checkpoint'))
+    legacy = Saver.latest_checkpoint(str(tmp_path) + '/')
+    assert legacy.endswith('-2000000.pt')
+    sv.restore(None, legacy)
+    assert torch.equal(holder['w'], torch.arange(6.0) + 1)
     sv.restore(None, path)
     assert int(path[path.rindex('-') + 1:].split('.')[0]) == 1000000 and torch.equal(holder['w'], state['w'])
