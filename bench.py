@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--frame_pool', type=int, default=8, help='device frame buffers rotated between env steps')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
+    ap.add_argument('--no_variants', action='store_true')
     ap.add_argument('--e2e_slices', type=int, default=2, help='environment slices pipelined in the end-to-end arm')
     ap.add_argument('--ref_envs', type=int, default=64, help='--impl reference: envs per step (bounded sample)')
     return ap.parse_args()
@@ -359,6 +360,21 @@ def run_b200(args):
     flops_per_env_step = 71.96e6 if args.arch == 'NATURE' else 21.65e6
     step_frac = (value / world) * flops_per_env_step / 1e12 / tf32_peak
 
+    # ---- variant: the acting forwards write the training workspace, update() runs no second forward -----------
+    # (same bits, tests/test_gpu_tc.py::test_training_forward_schedules_are_bit_identical).  Reported beside the headline,
+    # never as it: `value` above keeps the reference's schedule with the full training forward inside the timed region.
+    variants = {}
+    if not args.no_variants:
+        eng.set_train_forward('reuse')
+        for _ in range(3):
+            step_device()
+        r_ms = timed(step_device, args.steps)
+        variants['reuse_acting_activations'] = {
+            'value': world * N * T * args.steps / (r_ms / 1e3), 'unit': UNIT, 'ms_per_step': r_ms / args.steps,
+            'note': "RolloutEngine(train_forward='reuse'): act(t) stores its activations in the training workspace "
+                    '(paacb_policy_forward_at) and the update skips the redundant training forward; bit-identical results'}
+        eng.set_train_forward('batched')
+
     # ---- end-to-end arm: host buffers in, actions / loss out ---------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -371,6 +387,11 @@ def run_b200(args):
         host_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
         stream = torch.cuda.current_stream(dev)
         io_stream = torch.cuda.Stream(dev)
+        tf_stream = torch.cuda.Stream(dev)
+        ev_tf = torch.cuda.Event()
+        # the FULL training forward runs, but step by step on a side stream while the frames of the next env step cross
+        # PCIe (the SMs are otherwise idle then) instead of in one piece inside update(): same work, same bits
+        eng.set_train_forward('stepwise')
         S = max(1, min(args.e2e_slices, N))
         bounds = [(c * N // S, (c + 1) * N // S) for c in range(S)]       # contiguous env slices, like the runners' workers
         ev_act = [torch.cuda.Event() for _ in bounds]
@@ -388,6 +409,9 @@ def run_b200(args):
                     eng.act(t, lo, hi)
                     host_onehot[lo:hi].copy_(eng.onehot[lo:hi], non_blocking=True)      # the environments need the actions
                     ev_act[c].record(stream)
+                tf_stream.wait_event(ev_act[S - 1])                           # states[t] complete (every slice's act waited for it)
+                with torch.cuda.stream(tf_stream):
+                    eng.train_forward_step(t)
                 for c, (lo, hi) in enumerate(bounds):
                     ev_act[c].synchronize()                                   # host has this slice's actions: its envs step
                     with torch.cuda.stream(io_stream):
@@ -397,6 +421,8 @@ def run_b200(args):
                         ev_obs[c].record(io_stream)
             for c in range(S):
                 stream.wait_event(ev_obs[c])
+            ev_tf.record(tf_stream)
+            stream.wait_event(ev_tf)
             eng.update(lr)
             host_loss.copy_(eng.loss, non_blocking=True)
             stream.synchronize()
@@ -405,10 +431,12 @@ def run_b200(args):
             step_host()
         e_steps = max(2, args.steps // 2)
         e_ms = timed(step_host, e_steps)
+        eng.set_train_forward('batched')
         e2e = {'value': world * N * T * e_steps / (e_ms / 1e3), 'unit': UNIT, 'steps': e_steps,
                'ms_per_step': e_ms / e_steps,
                'h2d_bytes_per_step': T * (N * 2 * 84 * 160 + 2 * 4 * N), 'd2h_bytes_per_step': T * N * A * 4 + 4,
                'host_bytes_per_step': T * N * FRAME_PAIR_BYTES, 'env_slices': S, 'cpus_bound_to_gpu_node': numa_cpus,
+               'train_forward': 'stepwise (full training forward, issued per env step on a side stream under the PCIe reads)',
                'api': 'RolloutEngine.act / observe_frames / update over the C ABI; every env step the raw 210x160 frame '
                       'pairs are read by paacb_preprocess_u8 directly from pinned mapped host memory (zero-copy: the 84 '
                       'selected rows of both frames cross PCIe = h2d_bytes_per_step) and the sampled one-hot actions are '
@@ -432,7 +460,7 @@ def run_b200(args):
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': {'fp32': 'f32', 'tf32x3': 'tf32x3', 'tf32': 'tf32', 'bf16x3': 'bf16x3'}[args.math], 'data': 'synthetic',
                 'config': workload_config(args, world), 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
-                'roofline': roofline, 'cpu_baseline': cpu,
+                'roofline': roofline, 'cpu_baseline': cpu, 'variants': variants,
                 'step_fraction_of_tensor_peak': step_frac, 'kernel_time_accounted': accounted / ms_total,
                 'kernels': [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels],
                 'loss': loss_val}

@@ -59,6 +59,11 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device);
 int paacb_destroy(paacb_ctx* ctx);
 int paacb_set_math(paacb_ctx* ctx, int math_mode);
 int paacb_get_math(const paacb_ctx* ctx);
+/* The tensor-core modes keep operand images of the parameters (bf16 hi/lo transposes, int8 digits of conv1) in the
+ * context and reuse them across forwards of the same d_params pointer: PAAC runs t_max + 2 forwards per parameter
+ * update.  paacb_clip_rmsprop refreshes the images itself; a caller that writes the parameter buffer by any other
+ * means (initialisation, checkpoint restore, broadcast) MUST call paacb_params_changed() afterwards. */
+int paacb_params_changed(paacb_ctx* ctx);
 /* nearest-resize index tables, out[y][x] = in[row[y]][col[x]]; defaults are Pillow's for
  * 210x160 -> 84x84 (what scipy.misc.imresize(..., 'nearest') used, atari_emulator.py:73). */
 int paacb_set_resize_tables(paacb_ctx* ctx, const int32_t* row84, const int32_t* col84);
@@ -96,6 +101,16 @@ int paacb_preprocess_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs
 int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
                          float* d_fwd_ws, float* d_pi, float* d_v,
                          const float* d_uniforms, int32_t* d_actions, float* d_onehot, paacb_stream stream);
+
+/* The same forward writing samples [ws_first, ws_first + batch) of a workspace laid out for ws_capacity samples
+ * (paacb_forward_workspace_floats(ws_capacity)).  PAAC's training batch is the concatenation of the t_max acting
+ * batches (paac.py:92,112,151: states[t] is stored, then flattened to [T*N,...]) under UNCHANGED parameters, so the
+ * learner can compute the training forward's activations step by step while the emulators run -- paacb_backward then
+ * takes the assembled workspace with batch = ws_capacity.  Results are bit-identical to one forward over the whole
+ * batch (every sample is computed by the same instruction sequence whatever its position in a launch). */
+int paacb_policy_forward_at(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                            float* d_fwd_ws, int64_t ws_capacity, int64_t ws_first, float* d_pi, float* d_v,
+                            const float* d_uniforms, int32_t* d_actions, float* d_onehot, paacb_stream stream);
 
 /* ---- K7+K8: n-step returns (paac.py:119,140-149; reward clip actor_learner.py:95-101) fused with the
  * A2C loss and its gradient w.r.t. logits and value (policy_v_network.py:29-57 + TF autodiff).

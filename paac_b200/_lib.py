@@ -32,6 +32,8 @@ PROTOTYPES = {
     'paacb_optimizer_workspace_floats': (_i64, [_vp]),
     'paacb_preprocess_u8': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp]),
     'paacb_policy_forward': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'paacb_params_changed': (_i, [_vp]),
+    'paacb_policy_forward_at': (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_returns_loss_grad': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _f,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_backward': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -70,6 +70,7 @@ class ActorLearner(Process):
     def _set_network_state(self, state):
         for n, t in self.network.variables().items():
             t.copy_(state[n])
+        self.network.params_changed()
 
     def _slot_views(self, flat):
         return {n: flat[off:off + int(np.prod(shape))].view(*shape) for n, off, shape, _ in self.network.tensors}
@@ -118,6 +119,7 @@ class ActorLearner(Process):
 
         if self.world_size > 1:      # replicas start identical; afterwards updates are bit-identical on all ranks
             torch.distributed.broadcast(self.network.params, src=0)
+            self.network.params_changed()
             torch.distributed.broadcast(self.engine.ms, src=0)
             torch.distributed.broadcast(self.engine.mom, src=0)
         return last_saving_step

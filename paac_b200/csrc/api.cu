@@ -106,6 +106,8 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
   {
     const char* knob = getenv("PAACB_DBG");
     c->dbg = (knob != nullptr) ? atoi(knob) : 0;
+    const char* ap = getenv("PAACB_ALWAYS_PACK");
+    c->always_pack = (ap != nullptr) ? atoi(ap) : 0;
   }
   int h = PAACB_OBS, w = PAACB_OBS, ch = PAACB_STACK;
   int64_t poff = 0, aoff = 0;
@@ -236,6 +238,7 @@ int paacb_set_math(paacb_ctx* ctx, int math_mode) {
   PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
   PAACB_CHECK_ARG(math_mode == PAACB_MATH_FP32 || math_mode == PAACB_MATH_TF32X3 || math_mode == PAACB_MATH_TF32 ||
                   math_mode == PAACB_MATH_BF16X3, "unknown math mode");
+  ctx->fwd_img_valid = 0;
   if (math_mode == PAACB_MATH_BF16X3) {
     if (!bf16x3_supported(ctx)) {
       set_error("paacb_set_math: PAACB_MATH_BF16X3 covers the Nature architecture only (use PAACB_MATH_TF32X3)");
@@ -284,6 +287,24 @@ int paacb_set_math(paacb_ctx* ctx, int math_mode) {
 }
 
 int paacb_get_math(const paacb_ctx* ctx) { return ctx ? ctx->math : PAACB_EINVAL; }
+
+int paacb_params_changed(paacb_ctx* ctx) {
+  PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  ctx->fwd_img_valid = 0;
+  ctx->fwd_img_src = nullptr;
+  return PAACB_OK;
+}
+
+// the operand images of the forward (bf16 hi/lo transposes, conv1 int8 digits) for the parameters at d_params
+static int ensure_forward_images(const paacb_ctx* ctx, const float* d_params, cudaStream_t st) {
+  if (ctx->fwd_img_valid && ctx->fwd_img_src == d_params && !ctx->always_pack) return PAACB_OK;
+  const int rc = launch_pack_bf16_weights(ctx, d_params, st);
+  if (rc == PAACB_OK) {
+    ctx->fwd_img_valid = 1;
+    ctx->fwd_img_src = d_params;
+  }
+  return rc;
+}
 
 int paacb_set_resize_tables(paacb_ctx* ctx, const int32_t* row84, const int32_t* col84) {
   PAACB_CHECK_ARG(ctx && row84 && col84, "NULL argument");
@@ -334,10 +355,11 @@ int paacb_preprocess_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs
 }
 
 static int run_layer_fwd(const paacb_ctx* ctx, int l, const float* d_params, const uint8_t* d_states, int64_t batch,
-                         float* ws, cudaStream_t st) {
+                         float* ws, const WsSlice& slice, cudaStream_t st) {
   const LayerGeom& g = ctx->layer[l];
-  const void* x = (l == 0) ? (const void*)d_states : (const void*)(ws + g.in_act_off * batch);
-  float* y = ws + g.out_act_off * batch;
+  const void* x = (l == 0) ? (const void*)d_states
+                           : (const void*)(ws + g.in_act_off * slice.cap + slice.first * (int64_t)g.H * g.W * g.C);
+  float* y = ws + g.out_act_off * slice.cap + slice.first * (int64_t)g.OH * g.OW * g.N;
   if (ctx->math != PAACB_MATH_FP32) {
     const int rc = launch_conv_fwd_tc(ctx, g, x, d_params + g.w_off, d_params + g.b_off, y, batch,
                                       ctx->math == PAACB_MATH_TF32X3, st);
@@ -349,19 +371,30 @@ static int run_layer_fwd(const paacb_ctx* ctx, int l, const float* d_params, con
 int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
                          float* d_fwd_ws, float* d_pi, float* d_v, const float* d_uniforms, int32_t* d_actions,
                          float* d_onehot, paacb_stream stream) {
+  return paacb_policy_forward_at(ctx, d_params, d_states, batch, d_fwd_ws, batch, 0, d_pi, d_v, d_uniforms, d_actions,
+                                 d_onehot, stream);
+}
+
+int paacb_policy_forward_at(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                            float* d_fwd_ws, int64_t ws_capacity, int64_t ws_first, float* d_pi, float* d_v,
+                            const float* d_uniforms, int32_t* d_actions, float* d_onehot, paacb_stream stream) {
   PAACB_CHECK_ARG(ctx && d_params && d_states && d_fwd_ws && d_pi && d_v, "NULL argument");
   PAACB_CHECK_ARG(batch >= 0 && batch * (int64_t)ctx->layer[0].OH * ctx->layer[0].OW < (1LL << 40), "batch out of range");
+  PAACB_CHECK_ARG(ws_first >= 0 && ws_capacity >= 0 && ws_first + batch <= ws_capacity,
+                  "samples [ws_first, ws_first + batch) must lie inside the workspace capacity");
+  // every per-sample tensor is a multiple of 64 elements, so any sample offset keeps the 16-byte alignment of the planes
+  const WsSlice slice = {ws_capacity, ws_first};
   PAACB_CHECK_ARG(((uintptr_t)d_params & 15) == 0 && ((uintptr_t)d_states & 15) == 0 && ((uintptr_t)d_fwd_ws & 15) == 0,
                   "params / states / workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (ctx->math == PAACB_MATH_BF16X3) {
     if (batch == 0) return PAACB_OK;
     const int L = ctx->n_layers;
-    int rc = launch_pack_bf16_weights(ctx, d_params, st);      // the caller may have changed the parameters
-    for (int l = 0; l < L - 1 && rc == PAACB_OK; ++l) rc = launch_conv_fwd_bf16(ctx, l, d_params, d_states, d_fwd_ws, batch, st);
-    if (rc == PAACB_OK) rc = launch_fc_fwd_bf16(ctx, L - 1, d_params, d_fwd_ws, batch, st);
+    int rc = ensure_forward_images(ctx, d_params, st);
+    for (int l = 0; l < L - 1 && rc == PAACB_OK; ++l) rc = launch_conv_fwd_bf16(ctx, l, d_params, d_states, d_fwd_ws, batch, slice, st);
+    if (rc == PAACB_OK) rc = launch_fc_fwd_bf16(ctx, L - 1, d_params, d_fwd_ws, batch, slice, st);
     if (rc != PAACB_OK) return rc;
-    const Planes hp = layer_planes(d_fwd_ws, ctx->layer[L - 1].out_act_off, ctx->feat, batch);
+    const Planes hp = layer_planes(d_fwd_ws, ctx->layer[L - 1].out_act_off, ctx->feat, slice);
     return launch_heads_fwd(ctx, nullptr, reinterpret_cast<const uint16_t*>(hp.hi), reinterpret_cast<const uint16_t*>(hp.lo),
                             d_params + ctx->actor_w_off, d_params + ctx->actor_b_off, d_params + ctx->critic_w_off,
                             d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms, d_actions, d_onehot, st);
@@ -375,10 +408,10 @@ int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint
     }
   }
   for (int l = 0; l < ctx->n_layers; ++l) {
-    const int rc = run_layer_fwd(ctx, l, d_params, d_states, batch, d_fwd_ws, st);
+    const int rc = run_layer_fwd(ctx, l, d_params, d_states, batch, d_fwd_ws, slice, st);
     if (rc != PAACB_OK) return rc;
   }
-  const float* h = d_fwd_ws + ctx->layer[ctx->n_layers - 1].out_act_off * batch;
+  const float* h = d_fwd_ws + ctx->layer[ctx->n_layers - 1].out_act_off * slice.cap + slice.first * (int64_t)ctx->feat;
   return launch_heads_fwd(ctx, h, nullptr, nullptr, d_params + ctx->actor_w_off, d_params + ctx->actor_b_off,
                           d_params + ctx->critic_w_off, d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms,
                           d_actions, d_onehot, st);
@@ -465,8 +498,16 @@ int paacb_clip_rmsprop(const paacb_ctx* ctx, float* d_params, float* d_ms, float
   PAACB_CHECK_ARG(clip_type == PAACB_CLIP_IGNORE || clip_norm > 0.f, "clip_norm must be positive");
   PAACB_CHECK_ARG((((uintptr_t)d_params | (uintptr_t)d_ms | (uintptr_t)d_mom | (uintptr_t)d_grads | (uintptr_t)d_opt_ws) & 15) == 0,
                   "buffers must be 16-byte aligned");
-  return launch_clip_rmsprop(ctx, d_params, d_ms, d_mom, d_grads, grad_scale, lr, rho, eps, momentum, clip_norm,
-                             clip_type, d_norm_out, d_opt_ws, (cudaStream_t)stream);
+  int rc = launch_clip_rmsprop(ctx, d_params, d_ms, d_mom, d_grads, grad_scale, lr, rho, eps, momentum, clip_norm,
+                               clip_type, d_norm_out, d_opt_ws, (cudaStream_t)stream);
+  if (rc == PAACB_OK && ctx->math == PAACB_MATH_BF16X3) {
+    // the library just changed the parameters: refresh the cached forward images in stream order (also inside a captured
+    // graph), so the next forwards -- T acting forwards, the bootstrap and the training forward -- need no pack
+    rc = launch_pack_bf16_weights(ctx, d_params, (cudaStream_t)stream);
+    ctx->fwd_img_valid = (rc == PAACB_OK);
+    ctx->fwd_img_src = d_params;
+  }
+  return rc;
 }
 
 int paacb_host_register(void* host_ptr, size_t bytes, void** d_ptr) {

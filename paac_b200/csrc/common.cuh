@@ -84,6 +84,11 @@ struct paacb_ctx {
   uint16_t* wb_d_lo;
   int8_t* wq_i8;                // conv1 forward: three int8 digit images of the weights [3][Cout][K] + per-channel scale
   float* wq_scale;
+  // forward weight images are cached between calls: valid for the parameter buffer `fwd_img_src` until the parameters change
+  // (paacb_clip_rmsprop refreshes them in-stream; paacb_params_changed() invalidates them)
+  mutable int fwd_img_valid;
+  mutable const float* fwd_img_src;
+  int always_pack;              // PAACB_ALWAYS_PACK=1: re-derive the images on every forward (debug)
   int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };
 

@@ -27,6 +27,18 @@ __host__ __device__ inline Planes layer_planes(void* ws, int64_t off_floats_per_
   p.lo = p.hi + elems_per_sample * batch * 2;
   return p;
 }
+// A forward may fill samples [first, first + batch) of a workspace laid out for `cap` samples (paacb_policy_forward_at):
+// the planes of a layer are sized by the capacity, the sample offset moves both plane pointers.
+struct WsSlice {
+  int64_t cap;      // samples the workspace was laid out for
+  int64_t first;    // first sample this call writes
+};
+__host__ __device__ inline Planes layer_planes(void* ws, int64_t off_floats_per_sample, int64_t elems_per_sample, const WsSlice& s) {
+  Planes p = layer_planes(ws, off_floats_per_sample, elems_per_sample, s.cap);
+  p.hi += s.first * elems_per_sample * 2;
+  p.lo += s.first * elems_per_sample * 2;
+  return p;
+}
 constexpr int64_t kStateElems = (int64_t)PAACB_OBS * PAACB_OBS * PAACB_STACK;   // 28,224
 
 // ---- launchers (tc2_*.cu) ---------------------------------------------------------------------------
@@ -34,11 +46,12 @@ bool bf16x3_supported(const paacb_ctx* ctx);
 int launch_pack_bf16_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st);          // forward images
 int launch_pack_bf16_dgrad_weights(const paacb_ctx* ctx, const float* params, cudaStream_t st);    // data-gradient images
 int launch_conv_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
-                         cudaStream_t st);
+                         const WsSlice& slice, cudaStream_t st);
 int launch_pack_conv1_i8(const paacb_ctx* ctx, const float* params, cudaStream_t st);              // int8 digit image of conv1
 int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
-                        cudaStream_t st);
-int launch_fc_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st);
+                        const WsSlice& slice, cudaStream_t st);
+int launch_fc_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, void* fwd_ws, int64_t batch, const WsSlice& slice,
+                       cudaStream_t st);
 int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,
                            cudaStream_t st);
 int launch_fc_dgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,

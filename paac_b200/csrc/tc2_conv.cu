@@ -662,14 +662,14 @@ static int weight_maps(const paacb_ctx* ctx, const uint16_t* hi, const uint16_t*
 }
 
 int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
-                         cudaStream_t st) {
+                         const WsSlice& slice, cudaStream_t st) {
   const LayerGeom& g = ctx->layer[l];
   ConvKParams p;
   memset(&p, 0, sizeof(p));
   p.batch = (int)batch;
   p.bias = params + g.b_off;
   p.in_scale = g.in_u8 ? 0.003921568859368563f : 1.0f;
-  const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, batch);
+  const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
   p.out_hi = out.hi;
   p.out_lo = out.lo;
   const uint8_t* in_hi;
@@ -677,7 +677,7 @@ int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, const
   if (l == 0) {
     in_hi = in_lo = nullptr;                    // conv1 converts the uint8 states itself
   } else {
-    const Planes in = layer_planes(fwd_ws, g.in_act_off, (int64_t)g.H * g.W * g.C, batch);
+    const Planes in = layer_planes(fwd_ws, g.in_act_off, (int64_t)g.H * g.W * g.C, slice);
     in_hi = in.hi;
     in_lo = in.lo;
   }
@@ -703,7 +703,7 @@ int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, const
     p.num_tiles = (int)((q_total + 127) / 128);                                                                    \
     return launch_convk<GE>(ctx, p, K_FWD0 + l, st);                                                               \
   }
-  if (l == 0) return launch_conv1_fwd_i8(ctx, params, states, fwd_ws, batch, st);
+  if (l == 0) return launch_conv1_fwd_i8(ctx, params, states, fwd_ws, batch, slice, st);
   if (l == 1) PAACB_FWD_CASE(G_FWD2)
   if (l == 2) PAACB_FWD_CASE(G_FWD3)
 #undef PAACB_FWD_CASE

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
 }
 
 int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
-                        cudaStream_t st) {
+                        const WsSlice& slice, cudaStream_t st) {
   const LayerGeom& g = ctx->layer[0];
   if (g.C != 4 || g.stride != 4 || g.R != 8 || g.S != 8 || g.N != kC1_N || g.H != 84 || g.W != 84 || g.OH != kC1_OH)
     return PAACB_EUNSUPPORTED;
@@ -275,7 +275,7 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
   p.batch = (int)batch;
   p.bias = params + g.b_off;
   p.wscale = ctx->wq_scale;
-  const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, batch);
+  const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
   p.out_hi = out.hi;
   p.out_lo = out.lo;
   const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);

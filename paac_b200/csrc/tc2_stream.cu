@@ -321,13 +321,14 @@ static int map2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ro
 
 constexpr int kFcBN = 128;
 
-int launch_fc_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void* fwd_ws, int64_t batch, cudaStream_t st) {
+int launch_fc_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void* fwd_ws, int64_t batch, const WsSlice& slice,
+                       cudaStream_t st) {
   const LayerGeom& g = ctx->layer[l];
   if (g.K % 64 != 0 || g.N % kFcBN != 0) return PAACB_EUNSUPPORTED;
   StreamParams p;
   memset(&p, 0, sizeof(p));
-  const Planes x = layer_planes(fwd_ws, g.in_act_off, g.K, batch);
-  const Planes y = layer_planes(fwd_ws, g.out_act_off, g.N, batch);
+  const Planes x = layer_planes(fwd_ws, g.in_act_off, g.K, slice);
+  const Planes y = layer_planes(fwd_ws, g.out_act_off, g.N, slice);
   int rc = map2d(&p.tmA[0], x.hi, (uint64_t)g.K, (uint64_t)batch, 64, 128);
   if (rc == PAACB_OK) rc = map2d(&p.tmA[1], x.lo, (uint64_t)g.K, (uint64_t)batch, 64, 128);
   if (rc == PAACB_OK) rc = map2d(&p.tmB[0], ctx->wb_f_hi + g.w_off, (uint64_t)g.K, (uint64_t)g.N, 64, kFcBN);
@@ -392,7 +393,20 @@ int launch_fc_wgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, const 
   p.m_tiles = (g.K + 127) / 128;
   p.n_tiles = g.N / kFcBN;
   p.kblocks_total = (int)((batch + 63) / 64);
-  int splits = (2 * ctx->num_sms + p.m_tiles * p.n_tiles - 1) / (p.m_tiles * p.n_tiles);
+  // reduction splits: the (k-tile, n-tile, split) units are spread over one persistent CTA per SM; pick the split count
+  // (2..3 units per SM: every unit ends with 16 K fp32 atomics, about a fifth of a 2,000-sample mainloop) whose last wave
+  // is fullest (3 splits left 32 % of the SMs idle in the last wave of the fc layer)
+  const int tiles = p.m_tiles * p.n_tiles;
+  int splits = 1;
+  double best = 0.0;
+  for (int s = 1; s <= 64; ++s) {
+    const int units = tiles * s;
+    if (units < 2 * ctx->num_sms && s < 64) continue;
+    if (units > 3 * ctx->num_sms && splits > 1) break;
+    const int waves = (units + ctx->num_sms - 1) / ctx->num_sms;
+    const double eff = (double)units / ((double)waves * ctx->num_sms);
+    if (eff > best + 1e-9) { best = eff; splits = s; }
+  }
   if (splits > p.kblocks_total) splits = p.kblocks_total;
   if (splits < 1) splits = 1;
   p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;

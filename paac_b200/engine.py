@@ -12,6 +12,15 @@ calls in the order the reference's loop implies:
 All launches go to the current torch stream without host synchronisation, so ``update`` (and ``act`` +
 ``observe`` when frames are device-resident) can be captured in a CUDA graph (``capture_update``).
 PyTorch is used for memory, streams and torch.distributed only.
+
+Scheduling of the training forward (``train_forward=``).  PAAC's training batch is the concatenation of the t_max
+acting batches under unchanged parameters (paac.py:92,112,151), so its forward can be scheduled three ways with
+bit-identical results (tests/test_gpu_learner.py):
+    'batched'   the reference's schedule: one forward over T*N samples inside update()               (default)
+    'stepwise'  the SAME work issued per step with ``train_forward_step(t)`` (paacb_policy_forward_at), e.g. while the
+                emulators run and the frames cross PCIe; update() issues whatever steps are still missing
+    'reuse'     act(t) writes its activations straight into the training workspace and update() runs no training
+                forward at all (the acting forward already IS that computation); values[t] aliases v
 """
 import ctypes as C
 
@@ -27,7 +36,8 @@ FRAME_SLOT_SHAPE = (4, 2, 210, 160)
 class RolloutEngine(object):
 
     def __init__(self, network, n_envs, t_max, gamma=0.99, rho=0.99, eps=0.1, momentum=0.0,
-                 clip_norm=3.0, clip_norm_type='global', seed=3, process_group=None, world_size=1):
+                 clip_norm=3.0, clip_norm_type='global', seed=3, process_group=None, world_size=1,
+                 train_forward='batched'):
         self.net = network
         self.lib = network._lib
         self.ctx = network.ctx
@@ -79,8 +89,20 @@ class RolloutEngine(object):
         self.gen = torch.Generator(device=d)
         self.gen.manual_seed(int(seed))
         self._slice_ws = {}        # forward workspaces of environment slices (act(t, lo, hi))
+        self._stepped = set()      # (t, lo, hi) slices of the training forward already issued ('stepwise')
+        self._values_own = self.values
+        self.set_train_forward(train_forward)
 
     # ---- helpers ----------------------------------------------------------------------------------
+    def set_train_forward(self, mode):
+        """Choose the schedule of the training forward (see the module docstring); call between updates only."""
+        if mode not in ('batched', 'stepwise', 'reuse'):
+            raise ValueError("train_forward must be 'batched', 'stepwise' or 'reuse'")
+        self.train_forward = mode
+        self._stepped.clear()
+        # 'reuse': the acting value IS the training value
+        self.values = self.v.view(self.T, self.N) if mode == 'reuse' else self._values_own
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
@@ -98,6 +120,12 @@ class RolloutEngine(object):
         forward overlaps this slice's frame ingestion."""
         if hi is None:
             hi = self.N
+        if self.train_forward == 'reuse':
+            first = t * self.N + lo
+            self.net.forward(self.states[t, lo:hi], self.pi[first:first + hi - lo], self.v[first:first + hi - lo], self.fwd_ws,
+                             uniforms=self.uniforms[t, lo:hi], actions=self.actions[t, lo:hi], onehot=self.onehot[lo:hi],
+                             ws_capacity=self.B, ws_first=first)
+            return
         if lo == 0 and hi == self.N:
             ws = self.act_ws
         else:
@@ -128,6 +156,30 @@ class RolloutEngine(object):
         self.rewards[t].copy_(rewards, non_blocking=True)
         self.over[t].copy_(over, non_blocking=True)
 
+    def train_forward_step(self, t, lo=0, hi=None):
+        """'stepwise': the training forward of the samples (t, lo..hi), written into their place in the batch workspace."""
+        if self.train_forward != 'stepwise':
+            raise RuntimeError("train_forward_step() needs RolloutEngine(train_forward='stepwise')")
+        if hi is None:
+            hi = self.N
+        first = t * self.N + lo
+        self.net.forward(self.states[t, lo:hi], self.pi[first:first + hi - lo], self.v[first:first + hi - lo], self.fwd_ws,
+                         ws_capacity=self.B, ws_first=first)
+        self._stepped.add((t, lo, hi))
+
+    def _finish_stepwise(self):
+        """Issue the steps of the training forward the caller has not issued itself (whole steps only)."""
+        for t in range(self.T):
+            covered = sorted((lo, hi) for (tt, lo, hi) in self._stepped if tt == t)
+            pos = 0
+            for lo, hi in covered:
+                if lo > pos:
+                    self.train_forward_step(t, pos, lo)
+                pos = max(pos, hi)
+            if pos < self.N:
+                self.train_forward_step(t, pos, self.N)
+        self._stepped.clear()
+
     # ---- update -----------------------------------------------------------------------------------
     def forward_backward(self):
         """Bootstrap forward, training forward, returns + loss gradient, backward.  Leaves dL/dparams in grads."""
@@ -136,7 +188,10 @@ class RolloutEngine(object):
         st = self._stream()
         self.net.forward(self.states[T], self.boot_pi, self.boot_v, self.act_ws)                  # paac.py:140-142
         flat_states = self.states[:T].view((B,) + STATE_SHAPE)                                    # paac.py:151
-        self.net.forward(flat_states, self.pi, self.v, self.fwd_ws)
+        if self.train_forward == 'batched':
+            self.net.forward(flat_states, self.pi, self.v, self.fwd_ws)
+        elif self.train_forward == 'stepwise':
+            self._finish_stepwise()
         _lib.check(self.lib.paacb_returns_loss_grad(
             self.ctx, p(self.rewards), p(self.over), p(self.values), p(self.boot_v), p(self.actions), p(self.pi),
             p(self.v), T, N, C.c_double(self.gamma), C.c_float(self.beta), p(self.y), p(self.adv), p(self.dlogits),

@@ -116,6 +116,13 @@ class Network(object):
             n = int(np.prod(shape))
             flat[off:off + n] = rng.uniform(-d, d, size=n).astype(np.float32)
         self.params.copy_(torch.from_numpy(flat))
+        self.params_changed()
+
+    def params_changed(self):
+        """Tell the library that the parameter buffer was written from outside (it caches operand images of the weights
+        between forwards; paacb_clip_rmsprop refreshes them itself).  Call after ANY direct write to ``params`` /
+        ``variable(name)``."""
+        _lib.check(self._lib.paacb_params_changed(self.ctx), 'paacb_params_changed')
 
     def variable(self, name):
         """View of one variable inside the flat buffer (reference layout: HWIO / [in, out])."""
@@ -129,6 +136,7 @@ class Network(object):
 
     def set_params(self, flat):
         self.params.copy_(torch.as_tensor(np.asarray(flat, np.float32)).reshape(-1))
+        self.params_changed()
 
     def get_params(self):
         return self.params.detach().cpu().numpy().copy()
@@ -154,14 +162,16 @@ class Network(object):
     def workspace_floats(self, batch):
         return int(self._lib.paacb_forward_workspace_floats(self.ctx, int(batch)))
 
-    def forward(self, states, pi, v, ws, uniforms=None, actions=None, onehot=None):
-        """Asynchronous forward on the current torch stream; all arguments are CUDA tensors."""
+    def forward(self, states, pi, v, ws, uniforms=None, actions=None, onehot=None, ws_capacity=None, ws_first=0):
+        """Asynchronous forward on the current torch stream; all arguments are CUDA tensors.
+        ws_capacity / ws_first: write samples [ws_first, ws_first + b) of a workspace laid out for ws_capacity samples."""
         b = states.shape[0]
         st = torch.cuda.current_stream(self.torch_device).cuda_stream
         p = _lib.ptr
-        _lib.check(self._lib.paacb_policy_forward(self.ctx, p(self.params), p(states), b, p(ws), p(pi), p(v),
-                                                  p(uniforms), p(actions), p(onehot), C.c_void_p(st)),
-                   'paacb_policy_forward')
+        _lib.check(self._lib.paacb_policy_forward_at(self.ctx, p(self.params), p(states), b, p(ws),
+                                                     b if ws_capacity is None else int(ws_capacity), int(ws_first),
+                                                     p(pi), p(v), p(uniforms), p(actions), p(onehot), C.c_void_p(st)),
+                   'paacb_policy_forward_at')
 
     def launch_count(self):
         return int(self._lib.paacb_launch_count(self.ctx))

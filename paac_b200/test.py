@@ -66,6 +66,7 @@ def evaluate(args):
     def set_state(state):
         for n, t in network.variables().items():
             t.copy_(state[n])
+        network.params_changed()
 
     saver = Saver(lambda: {n: t.detach().cpu() for n, t in network.variables().items()}, set_state,
                   scope=getattr(network, 'name', 'local_learning'))

@@ -133,3 +133,87 @@ def test_sliced_act_observe_equals_whole_batch():
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][2], outs[1][2])
     assert np.array_equal(outs[0][3], outs[1][3])
     assert_close(outs[1][1], outs[0][1], 1e-6, 'values of sliced vs whole-batch forward')
+
+
+@pytest.mark.parametrize('math', ['bf16x3', 'tf32x3', 'fp32'])
+def test_training_forward_schedules_are_bit_identical(math):
+    """The training forward of PAAC is the concatenation of the acting forwards under unchanged parameters (paac.py:92,112,151).
+    'batched' (one forward over T*N samples in update()), 'stepwise' (paacb_policy_forward_at per step / slice) and 'reuse'
+    (the acting forward writes the training workspace) must leave the SAME BITS in the activation workspace, pi and v, and
+    the same update (gradient sums use atomics, so the post-update weights are compared to rounding)."""
+    arch, A, N, T = 'NATURE', 6, 40, 3
+    rng = np.random.RandomState(11)
+    states = rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)
+    rewards = rng.choice([-1.0, 0.0, 1.0], size=(T, N)).astype(np.float32)
+    over = (rng.random_sample((T, N)) < 0.2).astype(np.float32)
+    res = {}
+    for mode in ('batched', 'stepwise', 'reuse'):
+        net = G.make_net(arch, A, seed=5, math=math)
+        eng = RolloutEngine(net, N, T, seed=9, train_forward=mode)
+        eng.states.copy_(G.dev(states))
+        eng.draw_uniforms()
+        for t in range(T):
+            eng.act(t, 0, 16)
+            eng.act(t, 16, N)
+            if mode == 'stepwise' and t != 1:                # step 1 is left to update(); step 2 is issued in two slices
+                if t == 2:
+                    eng.train_forward_step(t, 0, 24)
+                    eng.train_forward_step(t, 24, N)
+                else:
+                    eng.train_forward_step(t)
+        eng.rewards.copy_(G.dev(rewards)); eng.over.copy_(G.dev(over))
+        eng.update(0.0224)
+        torch.cuda.synchronize()
+        res[mode] = dict(ws=eng.fwd_ws.view(torch.int32).cpu().numpy().copy(), pi=eng.pi.cpu().numpy().copy(),
+                         v=eng.v.cpu().numpy().copy(), values=eng.values.cpu().numpy().copy(),
+                         actions=eng.actions.cpu().numpy().copy(), y=eng.y.cpu().numpy().copy(),
+                         loss=eng.loss.item(), params=net.get_params())
+    ref = res['batched']
+    for mode in ('stepwise', 'reuse'):
+        r = res[mode]
+        assert np.array_equal(r['actions'], ref['actions']), mode
+        assert np.array_equal(r['ws'], ref['ws']), mode + ': activation workspace differs'
+        assert np.array_equal(r['pi'].view(np.int32), ref['pi'].view(np.int32)), mode
+        assert np.array_equal(r['v'].view(np.int32), ref['v'].view(np.int32)), mode
+        assert np.array_equal(r['values'].view(np.int32), ref['values'].view(np.int32)), mode
+        assert np.array_equal(r['y'].view(np.int32), ref['y'].view(np.int32)), mode
+        assert abs(r['loss'] - ref['loss']) <= 1e-6 * max(1.0, abs(ref['loss']))
+        assert_close(r['params'], ref['params'], 1e-6, mode + ': post-update weights')
+
+
+def test_cached_weight_images_follow_the_parameters():
+    """The bf16x3 forward reuses the operand images of the weights between calls (paacb_params_changed contract):
+    after set_params() and after paacb_clip_rmsprop the next forward must see the NEW parameters."""
+    arch, A, N, T = 'NATURE', 6, 8, 2
+    rng = np.random.RandomState(3)
+    states = G.dev(rng.randint(0, 256, (N, 84, 84, 4)).astype(np.uint8))
+
+    def fwd(net):
+        pi = torch.empty((N, A), device='cuda'); v = torch.empty((N,), device='cuda')
+        ws = torch.empty((net.workspace_floats(N),), device='cuda')
+        net.forward(states, pi, v, ws)
+        torch.cuda.synchronize()
+        return pi.cpu().numpy(), v.cpu().numpy()
+
+    net = G.make_net(arch, A, seed=5, math='bf16x3')
+    other = G.make_net(arch, A, seed=6, math='bf16x3')
+    pi0, v0 = fwd(net)
+    net.set_params(other.get_params())                      # host write -> params_changed()
+    pi1, v1 = fwd(net)
+    pi_o, v_o = fwd(other)
+    assert np.array_equal(pi1, pi_o) and np.array_equal(v1, v_o)
+    assert not np.array_equal(v0, v1)
+    # an update through the library refreshes the images in-stream
+    eng = RolloutEngine(net, N, T, seed=9)
+    eng.states.copy_(G.dev(rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)))
+    eng.draw_uniforms()
+    for t in range(T):
+        eng.act(t)
+    eng.rewards.fill_(1.0)
+    eng.update(0.0224)
+    pi2, v2 = fwd(net)
+    fresh = G.make_net(arch, A, seed=1, math='bf16x3')
+    fresh.set_params(net.get_params())
+    pi_f, v_f = fwd(fresh)
+    assert np.array_equal(pi2, pi_f) and np.array_equal(v2, v_f)
+    assert not np.array_equal(v1, v2)

@@ -8,3 +8,5 @@ for l in open(sys.argv[1]):
         steps = d['steps']
         for k in d.get('kernels', []):
             print('%-20s ms/step=%7.3f n=%3d frac=%.3f ach=%9.1f %s share=%.3f' % (k['name'], k['ms'] / steps, k['launches'], k['frac'], k['achieved'], k['unit'], k['share_of_step']))
+        print('variants', d.get('variants'))
+        print('cpu_baseline', d.get('cpu_baseline') and d['cpu_baseline'].get('value'))
