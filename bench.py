@@ -95,11 +95,43 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock / throttle reasons / power sampled DURING the timed region by an NVML thread (every ~5 ms; NVML calls drop the
+    GIL).  Falls back to an `nvidia-smi -lms` child when pynvml is missing."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
+        import threading
+        self.rows, self.p, self.f, self.th = [], None, None, None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[index]) if visible and visible.split(',')[index].isdigit() else index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {'hw_slowdown': pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    'hw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    'sw_power_cap': pynvml.nvmlClocksThrottleReasonSwPowerCap}
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        watts = pynvml.nvmlDeviceGetPowerUsage(h) / 1e3
+                        self.rows.append((mhz, watts, [n for n, b in bits.items() if mask & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.th = None
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
@@ -110,6 +142,17 @@ class ClockSampler(object):
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.th is not None:
+            self.stop_flag.set()
+            self.th.join(1.0)
+            if self.rows:
+                reasons = set()
+                for r in self.rows:
+                    reasons.update(r[2])
+                out.update(sm_mhz=statistics.median(r[0] for r in self.rows), sm_max_mhz=self.max_mhz,
+                           reasons=sorted(reasons), samples=len(self.rows), power_w_max=max(r[1] for r in self.rows),
+                           source='nvml thread, 5 ms period, timed region only')
+            return out
         if self.p is None:
             return out
         time.sleep(0.05)
@@ -135,7 +178,7 @@ class ClockSampler(object):
                     reasons.add(nm)
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(pw))
+                       power_w_max=max(pw), source='nvidia-smi -lms 20')
         return out
 
 
@@ -325,7 +368,8 @@ def run_b200(args):
     hbm_row('preprocess_u8', float(K1_ALGO_BYTES) * N * T * args.steps)
     hbm_row('returns_loss_grad', (4.0 * (2 * A + 6) * B + 4.0 * N) * args.steps)
     hbm_row('grad_sumsq', 4.0 * P * args.steps)
-    hbm_row('clip_rmsprop', 24.0 * P * args.steps)
+    # fused cooperative optimizer: one kernel carries the whole K10 + K11 contract (28 B/param); two-launch version: 4 + 24
+    hbm_row('clip_rmsprop', (24.0 if 'grad_sumsq' in prof else 28.0) * P * args.steps)
     F = 512 if args.arch == 'NATURE' else 256
     hbm_row('heads_fwd', 4.0 * F * (T * N + N + B) * args.steps)       # reads the hidden activations once
     hbm_row('heads_bwd', 8.0 * F * B * args.steps)                     # reads h, writes dh

@@ -108,6 +108,8 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     c->dbg = (knob != nullptr) ? atoi(knob) : 0;
     const char* ap = getenv("PAACB_ALWAYS_PACK");
     c->always_pack = (ap != nullptr) ? atoi(ap) : 0;
+    const char* tp = getenv("PAACB_OPT_TWO_PASS");
+    c->opt_two_pass = (tp != nullptr) ? atoi(tp) : 0;
   }
   int h = PAACB_OBS, w = PAACB_OBS, ch = PAACB_STACK;
   int64_t poff = 0, aoff = 0;
@@ -150,6 +152,18 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     c->tabs.row[y] = (uint8_t)(((2 * y + 1) * 5) / 4);   // floor((y + 0.5) * 2.5)
     c->tabs.col[y] = kDefaultCol[y];
   }
+  {  // the grid-barrier counter of the fused optimizer kernel (context-owned, like the weight images)
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    if (cudaMalloc(&c->opt_counter, 256) == cudaSuccess) {
+      cudaMemset(c->opt_counter, 0, 256);
+    } else {
+      cudaGetLastError();
+      c->opt_counter = nullptr;          // falls back to the two-launch optimizer
+    }
+    cudaSetDevice(cur);
+  }
   *out = c;
   return PAACB_OK;
 }
@@ -161,6 +175,7 @@ int paacb_destroy(paacb_ctx* ctx) {
     delete[] ctx->prof_ev;
     delete[] ctx->prof_kid;
   }
+  if (ctx->opt_counter != nullptr) cudaFree(ctx->opt_counter);
   if (ctx->wpack_hi != nullptr) cudaFree(ctx->wpack_hi);
   if (ctx->wpack_lo != nullptr) cudaFree(ctx->wpack_lo);
   if (ctx->wpack_d_hi != nullptr) cudaFree(ctx->wpack_d_hi);

@@ -88,6 +88,11 @@ struct paacb_ctx {
   // (paacb_clip_rmsprop refreshes them in-stream; paacb_params_changed() invalidates them)
   mutable int fwd_img_valid;
   mutable const float* fwd_img_src;
+  // fused optimizer: grid-barrier counter (4 bytes of device memory, zeroed at creation) and the grid size it is used with
+  unsigned int* opt_counter;
+  mutable int opt_grid;
+  mutable int opt_launches;
+  int opt_two_pass;             // PAACB_OPT_TWO_PASS=1: the two-launch optimizer (sumsq + update)
   int always_pack;              // PAACB_ALWAYS_PACK=1: re-derive the images on every forward (debug)
   int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };

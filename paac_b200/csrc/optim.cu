@@ -11,9 +11,15 @@
 // `gscale` (1/world_size) is applied to the raw gradient first so that a multi-GPU allreduce-SUM
 // followed by this kernel equals the single-learner update on the concatenated batch.
 //
-// Pass 1 writes one double partial sum of squares per CTA; pass 2 re-reduces the partials in a fixed
-// order in every CTA (deterministic, no atomics, no host sync) and applies the update.
-// HBM traffic: 4 B/param (pass 1) + 12 B read + 12 B written (pass 2) = 28 B/param.
+// ONE cooperative launch (all CTAs co-resident, one grid barrier).  Every thread loads its slice of the gradient into
+// registers and asks for its slice of params / ms / mom to be brought into L2 (prefetch.global.L2), reduces the gradient
+// slice, writes one double partial per CTA, crosses the grid barrier, re-reduces the partials in a fixed order
+// (deterministic, no atomics on the data path), and applies the update with the gradient still in registers.  The
+// gradient is read ONCE (the two-launch version re-read it) and the DRAM latency of params / ms / mom is hidden behind
+// the norm reduction and the barrier.  HBM traffic: 16 B read + 12 B written per parameter.  Parameters beyond the resident threads' register slices (only for
+// networks far larger than PAAC's) take a strided second pass that re-reads the gradient.
+// The two-launch version (sumsq_partials_kernel + clip_rmsprop_kernel) is kept for devices / contexts where the
+// cooperative grid does not fit and as the reference the fused kernel is tested against (PAACB_OPT_TWO_PASS=1).
 #include "common.cuh"
 
 namespace paacb {
@@ -107,7 +113,132 @@ clip_rmsprop_kernel(float* __restrict__ params, float* __restrict__ ms, float* _
   }
 }
 
-int64_t optimizer_ws_floats(const paacb_ctx*) { return 2 * kMaxPartials; }   // kMaxPartials doubles
+// ---- fused cooperative version ------------------------------------------------------------------------------
+constexpr int kFusedVec = 4;      // float4 slices of the gradient per thread held in registers
+
+// Sense-free grid barrier on a monotonically increasing counter: every launch of this kernel uses the same grid size, so
+// the counter is a multiple of the grid size between launches and needs no reset.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    const unsigned int target = ticket - (ticket % nblocks) + nblocks;
+    while ((int)(*reinterpret_cast<volatile unsigned int*>(counter) - target) < 0) __nanosleep(20);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+clip_rmsprop_fused_kernel(float* __restrict__ params, float* __restrict__ ms, float* __restrict__ mom,
+                          const float* __restrict__ g, int64_t P, float gscale, float lr, float rho, float eps,
+                          float momentum, float clip, int clip_type, double* __restrict__ partials,
+                          unsigned int* __restrict__ counter, float* __restrict__ norm_out) {
+  const int64_t nvec = P >> 2;
+  const int64_t nthreads = (int64_t)gridDim.x * kOptThreads;
+  const int64_t t0 = (int64_t)blockIdx.x * kOptThreads + threadIdx.x;
+  float4* p4 = reinterpret_cast<float4*>(params);
+  float4* ms4 = reinterpret_cast<float4*>(ms);
+  float4* mom4 = reinterpret_cast<float4*>(mom);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+
+  float4 gv[kFusedVec];
+#pragma unroll
+  for (int k = 0; k < kFusedVec; ++k) {
+    const int64_t i = t0 + k * nthreads;
+    gv[k] = (i < nvec) ? __ldcs(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < kFusedVec; ++k) {
+    const int64_t i = t0 + k * nthreads;
+    if (i < nvec && (threadIdx.x & 1) == 0) {        // one prefetch per 32-byte sector
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p4 + i));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ms4 + i));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(mom4 + i));
+    }
+  }
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFusedVec; ++k) {
+    const float tx = gv[k].x * gscale, ty = gv[k].y * gscale, tz = gv[k].z * gscale, tw = gv[k].w * gscale;
+    s0 = fmaf(tx, tx, s0); s1 = fmaf(ty, ty, s1); s2 = fmaf(tz, tz, s2); s3 = fmaf(tw, tw, s3);
+  }
+  for (int64_t i = t0 + kFusedVec * nthreads; i < nvec; i += nthreads) {      // beyond the register slices
+    float4 t = __ldg(g4 + i);
+    t.x *= gscale; t.y *= gscale; t.z *= gscale; t.w *= gscale;
+    s0 = fmaf(t.x, t.x, s0); s1 = fmaf(t.y, t.y, s1); s2 = fmaf(t.z, t.z, s2); s3 = fmaf(t.w, t.w, s3);
+  }
+  double s = (double)s0 + (double)s1 + (double)s2 + (double)s3;
+  if (blockIdx.x == 0) {
+    for (int64_t i = (nvec << 2) + threadIdx.x; i < P; i += kOptThreads) {
+      const float t = g[i] * gscale;
+      s += (double)t * (double)t;
+    }
+  }
+  __shared__ double red[kOptThreads / 32];
+  __shared__ float s_scale;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kOptThreads / 32; ++i) t += red[i];
+    partials[blockIdx.x] = t;
+  }
+  grid_barrier(counter, gridDim.x);
+
+  // deterministic re-reduction of the partials (same order in every CTA)
+  s = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kOptThreads) s += __ldcg(partials + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kOptThreads / 32; ++i) t += red[i];
+    const float norm = sqrtf((float)t);
+    float scale = 1.0f;
+    if (clip_type == PAACB_CLIP_GLOBAL) scale = clip * fminf(1.0f / norm, 1.0f / clip);
+    s_scale = scale;
+    if (blockIdx.x == 0 && norm_out != nullptr) *norm_out = norm;
+  }
+  __syncthreads();
+  const float sg = s_scale * gscale;      // one multiplier, exactly as in the two-pass kernel
+  const float omr = 1.0f - rho;
+#pragma unroll
+  for (int k = 0; k < kFusedVec; ++k) {
+    const int64_t i = t0 + k * nthreads;
+    if (i < nvec) {
+      float4 pv = p4[i], mv = ms4[i], ov = mom4[i];
+      rmsprop_one(pv.x, mv.x, ov.x, gv[k].x * sg, lr, omr, eps, momentum);
+      rmsprop_one(pv.y, mv.y, ov.y, gv[k].y * sg, lr, omr, eps, momentum);
+      rmsprop_one(pv.z, mv.z, ov.z, gv[k].z * sg, lr, omr, eps, momentum);
+      rmsprop_one(pv.w, mv.w, ov.w, gv[k].w * sg, lr, omr, eps, momentum);
+      p4[i] = pv; ms4[i] = mv; mom4[i] = ov;
+    }
+  }
+  for (int64_t i = t0 + kFusedVec * nthreads; i < nvec; i += nthreads) {
+    float4 gg = __ldg(g4 + i);
+    float4 p = p4[i], m = ms4[i], o = mom4[i];
+    rmsprop_one(p.x, m.x, o.x, gg.x * sg, lr, omr, eps, momentum);
+    rmsprop_one(p.y, m.y, o.y, gg.y * sg, lr, omr, eps, momentum);
+    rmsprop_one(p.z, m.z, o.z, gg.z * sg, lr, omr, eps, momentum);
+    rmsprop_one(p.w, m.w, o.w, gg.w * sg, lr, omr, eps, momentum);
+    p4[i] = p; ms4[i] = m; mom4[i] = o;
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = (nvec << 2) + threadIdx.x; i < P; i += kOptThreads) {
+      float p = params[i], m = ms[i], o = mom[i];
+      rmsprop_one(p, m, o, g[i] * sg, lr, omr, eps, momentum);
+      params[i] = p; ms[i] = m; mom[i] = o;
+    }
+  }
+}
+
+int64_t optimizer_ws_floats(const paacb_ctx*) { return 2 * kMaxPartials + 4; }   // kMaxPartials doubles (+ spare)
 
 static int opt_blocks(const paacb_ctx* ctx, int64_t P) {
   int64_t want = (P / 4 + kOptThreads * 4 - 1) / (kOptThreads * 4);   // >= 4 float4 per thread
@@ -117,12 +248,54 @@ static int opt_blocks(const paacb_ctx* ctx, int64_t P) {
   return (int)want;
 }
 
+// cooperative grid of the fused kernel: as many CTAs as can be co-resident (capped by the partials buffer), queried once
+static int fused_blocks(const paacb_ctx* ctx) {
+  static int cached_dev = -1, cached = 0;
+  if (cached_dev == ctx->device) return cached;
+  int per_sm = 0, coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device) != cudaSuccess || !coop ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_rmsprop_fused_kernel, kOptThreads, 0) != cudaSuccess) {
+    cudaGetLastError();
+    per_sm = 0;
+  }
+  int64_t blocks = (int64_t)per_sm * ctx->num_sms;
+  if (blocks > kMaxPartials) blocks = kMaxPartials;
+  cached_dev = ctx->device;
+  cached = (int)blocks;
+  return cached;
+}
+
 int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* mom, const float* grads, float gscale,
                         float lr, float rho, float eps, float momentum, float clip, int clip_type, float* norm_out,
                         float* ws, cudaStream_t st) {
-  const int64_t P = ctx->param_count;
-  const int blocks = opt_blocks(ctx, P);
+  int64_t P = ctx->param_count;
   double* partials = reinterpret_cast<double*>(ws);
+  const int fused = (ctx->opt_counter != nullptr && !ctx->opt_two_pass) ? fused_blocks(ctx) : 0;
+  if (fused > 0) {
+    // no more CTAs than the register slices need: do not spin CTAs that hold no data
+    int64_t need = ((P >> 2) + kOptThreads * kFusedVec - 1) / (kOptThreads * kFusedVec);
+    int blocks = (int)(need < fused ? (need < 1 ? 1 : need) : fused);
+    if (ctx->opt_grid != 0 && ctx->opt_grid != blocks) blocks = ctx->opt_grid;      // the barrier counter assumes ONE grid size
+    ctx->opt_grid = blocks;
+    unsigned int* counter = ctx->opt_counter;
+    if (++ctx->opt_launches >= (1 << 20)) {      // keep the monotonic barrier counter far from wrapping
+      ctx->opt_launches = 0;
+      if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) { set_error("memset failed"); return PAACB_ECUDA; }
+    }
+    void* args[] = {&params, &ms, &mom, &grads, &P, &gscale, &lr, &rho, &eps, &momentum, &clip, &clip_type, &partials,
+                    &counter, &norm_out};
+    PAACB_LAUNCH_BEGIN(ctx, K_RMSPROP, st);
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)clip_rmsprop_fused_kernel, dim3((unsigned)blocks),
+                                                      dim3(kOptThreads), args, 0, st);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("paacb_clip_rmsprop: cooperative launch failed: %s", cudaGetErrorString(e));
+      return PAACB_ECUDA;
+    }
+    PAACB_LAUNCH_END(ctx, K_RMSPROP, st);
+    return PAACB_OK;
+  }
+  const int blocks = opt_blocks(ctx, P);
   PAACB_LAUNCH_BEGIN(ctx, K_SUMSQ, st);
   sumsq_partials_kernel<<<blocks, kOptThreads, 0, st>>>(grads, P, gscale, partials);
   PAACB_LAUNCH_END(ctx, K_SUMSQ, st);

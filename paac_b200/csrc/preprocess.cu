@@ -11,6 +11,7 @@
 // selected columns from shared memory and merges them into the NHWC uint8 stack: a non-reset step is
 // (prev >> 8) | (new << 24) per pixel word (drop the oldest frame, append the newest as channel 3).
 // HBM traffic per env-step: 26,880 B frames + 28,224 B previous stack read, 28,224 B written.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace paacb {
@@ -95,7 +96,12 @@ int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, co
   unsigned grid = (unsigned)n;
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess) {
-    if (attr.type == cudaMemoryTypeHost && n > 96) grid = 96;
+    if (attr.type == cudaMemoryTypeHost) {
+      unsigned narrow = 96;
+      const char* knob = getenv("PAACB_K1_HOST_GRID");      // tuning knob for tools/experiments/pcie_probe.py
+      if (knob != nullptr && atoi(knob) > 0) narrow = (unsigned)atoi(knob);
+      if (n > narrow) grid = narrow;
+    }
   } else {
     cudaGetLastError();
   }

@@ -89,6 +89,35 @@ def test_clip_rmsprop_vs_oracle(clip_type, gscale):
     assert rc == -1
 
 
+@pytest.mark.parametrize('arch', ['NIPS', 'NATURE'])
+def test_fused_optimizer_equals_two_pass_bitwise(arch, monkeypatch):
+    """The cooperative one-launch optimizer (gradient held in registers across a grid barrier) and the two-launch version
+    (sumsq partials, then update) are the same arithmetic in the same order: identical bits, over repeated launches (the
+    barrier counter is monotonic across launches)."""
+    rng = np.random.RandomState(4)
+    outs = {}
+    for two_pass in ('0', '1'):
+        monkeypatch.setenv('PAACB_OPT_TWO_PASS', two_pass)
+        net = G.make_net(arch, 6)
+        P = net.param_count
+        params = (rng.randn(P) * 0.05).astype(np.float32) if two_pass == '0' else outs['in'][0]
+        ms = (1 + 0.1 * rng.rand(P)).astype(np.float32) if two_pass == '0' else outs['in'][1]
+        mom = (0.01 * rng.randn(P)).astype(np.float32) if two_pass == '0' else outs['in'][2]
+        grads = [(rng.randn(P) * s).astype(np.float32) for s in (0.05, 1e-4, 3.0)] if two_pass == '0' else outs['in'][3]
+        outs['in'] = (params, ms, mom, grads)
+        st = (params, ms, mom)
+        res = []
+        for g in grads:
+            p2, ms2, mom2, norm = G.clip_rmsprop(net, st[0], st[1], st[2], g, 0.125, 0.0224, 0.99, 0.1, 0.9, 3.0, _lib.CLIP_GLOBAL)
+            st = (p2, ms2, mom2)
+            res.append((p2, ms2, mom2, norm))
+        outs[two_pass] = res
+    for a, b in zip(outs['0'], outs['1']):
+        for x, y in zip(a[:3], b[:3]):
+            assert np.array_equal(x.view(np.int32), y.view(np.int32))
+        assert a[3] == b[3]
+
+
 def test_two_updates_match_reference_tf_graph(golden_dir):
     """The same two train steps the reference's shipped graph was evaluated on (NIPS, A=4, b=12)."""
     g = np.load(os.path.join(golden_dir, 'tf_graph_nips.npz'))
