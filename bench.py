@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
     ap.add_argument('--no_variants', action='store_true')
+    ap.add_argument('--no_overlap_allreduce', action='store_true', help='N > 1: one all-reduce after the whole backward')
     ap.add_argument('--e2e_slices', type=int, default=2, help='environment slices pipelined in the end-to-end arm')
     ap.add_argument('--ref_envs', type=int, default=64, help='--impl reference: envs per step (bounded sample)')
     return ap.parse_args()
@@ -62,7 +63,8 @@ def workload_config(args, n_gpus):
                             'Nature' if args.arch == 'NATURE' else 'NIPS', args.envs, T_MAX, NUM_ACTIONS),
             'arch': args.arch, 'envs_per_gpu': args.envs, 't_max': T_MAX, 'num_actions': NUM_ACTIONS,
             'env_steps_per_step': args.envs * T_MAX * n_gpus,
-            'parallelism': 'envs sharded over %d GPU(s); one flat fp32 gradient allreduce per update' % n_gpus,
+            'parallelism': 'envs sharded over %d GPU(s); flat fp32 gradient all-reduced per update (NCCL; the fc + heads tail '
+                           'under the conv weight-gradient kernels, the conv head after them)' % n_gpus,
             'l2': 'inputs larger than L2: each env step reads a different %d-deep rotating frame buffer of %.0f MB and '
                   'the update streams %.2f GB of activations (L2 = 126 MB)' % (
                       args.frame_pool, args.envs * FRAME_PAIR_BYTES / 1e6, args.envs * T_MAX * 21632 * 4 * 2 / 1e9)}
@@ -272,7 +274,7 @@ def run_b200(args):
     conf = dict(name='local_learning', num_actions=A, clip_norm=3.0, clip_norm_type='global', device='/gpu:%d' % local,
                 entropy_regularisation_strength=0.02, seed=3, math=args.math)
     net = (NaturePolicyVNetwork if args.arch == 'NATURE' else NIPSPolicyVNetwork)(conf)
-    eng = RolloutEngine(net, N, T, seed=3 * (rank + 1), world_size=world)
+    eng = RolloutEngine(net, N, T, seed=3 * (rank + 1), world_size=world, overlap_allreduce=not args.no_overlap_allreduce)
     P = net.param_count
 
     gen = torch.Generator(device=dev)

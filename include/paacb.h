@@ -133,6 +133,18 @@ int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d
                    const float* d_fwd_ws, const float* d_dlogits, const float* d_dv,
                    float* d_bwd_ws, float* d_grads, paacb_stream stream);
 
+/* The same backward in two parts, for overlapping the gradient all-reduce with the rest of the backward (multi-GPU):
+ *   PAACB_BWD_TAIL  zeroes d_grads, then computes every data gradient and the gradients of the hidden fc layer and of
+ *                   both heads: d_grads[paacb_grad_tail_offset(ctx) .. P) is final (95 % of the parameters of either
+ *                   architecture) and can be all-reduced while
+ *   PAACB_BWD_HEAD  computes what is left of d_grads[0 .. tail offset) (the conv layers' weight gradients).
+ * PAACB_BWD_ALL = both, what paacb_backward does. */
+enum { PAACB_BWD_ALL = 0, PAACB_BWD_TAIL = 1, PAACB_BWD_HEAD = 2 };
+int paacb_backward_part(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                        const float* d_fwd_ws, const float* d_dlogits, const float* d_dv,
+                        float* d_bwd_ws, float* d_grads, int part, paacb_stream stream);
+int64_t paacb_grad_tail_offset(const paacb_ctx* ctx);
+
 /* ---- K10+K11: tf.clip_by_global_norm + ApplyRMSProp x10 (actor_learner.py:33-34,54-59,70).
  *   g = d_grads * grad_scale (1/world after an allreduce-sum); norm = ||g||_2;
  *   scale = clip * min(1/norm, 1/clip) (PAACB_CLIP_GLOBAL) or 1;  g *= scale;

@@ -10,6 +10,7 @@ PAACB_OK = 0
 ARCH_NIPS, ARCH_NATURE = 0, 1
 MATH_FP32, MATH_TF32X3, MATH_TF32, MATH_BF16X3 = 0, 1, 2, 3
 CLIP_IGNORE, CLIP_GLOBAL = 0, 1
+BWD_ALL, BWD_TAIL, BWD_HEAD = 0, 1, 2
 MAX_ACTIONS = 18
 
 _vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
@@ -33,6 +34,8 @@ PROTOTYPES = {
     'paacb_preprocess_u8': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp]),
     'paacb_policy_forward': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_params_changed': (_i, [_vp]),
+    'paacb_backward_part': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'paacb_grad_tail_offset': (_i64, [_vp]),
     'paacb_policy_forward_at': (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_returns_loss_grad': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _f,
                                      _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -445,19 +445,11 @@ int paacb_returns_loss_grad(const paacb_ctx* ctx, const float* d_rewards, const 
                                   (cudaStream_t)stream);
 }
 
-int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
-                   const float* d_fwd_ws, const float* d_dlogits, const float* d_dv, float* d_bwd_ws, float* d_grads,
-                   paacb_stream stream) {
-  PAACB_CHECK_ARG(ctx && d_params && d_states && d_fwd_ws && d_dlogits && d_dv && d_bwd_ws && d_grads, "NULL argument");
-  PAACB_CHECK_ARG(((uintptr_t)d_bwd_ws & 15) == 0 && ((uintptr_t)d_grads & 15) == 0, "workspace / grads must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(d_grads, 0, (size_t)ctx->param_count * sizeof(float), st) != cudaSuccess) {
-    set_error("paacb_backward: memset failed");
-    return PAACB_ECUDA;
-  }
+// bf16x3: head gradients, every data gradient (they also produce the conv / fc BIAS gradients) and the fc weight gradient
+static int backward_bf16_tail(const paacb_ctx* ctx, const float* d_params, const float* d_fwd_ws, const float* d_dlogits,
+                              const float* d_dv, float* d_bwd_ws, float* d_grads, int64_t batch, cudaStream_t st) {
   const int L = ctx->n_layers;
-  if (ctx->math == PAACB_MATH_BF16X3) {
-    if (batch == 0) return PAACB_OK;
+  {
     const Planes hp = layer_planes(const_cast<float*>(d_fwd_ws), ctx->layer[L - 1].out_act_off, ctx->feat, batch);
     const Planes dhp = layer_planes(d_bwd_ws, ctx->layer[L - 1].out_act_off, ctx->feat, batch);
     int rc = launch_heads_bwd(ctx, nullptr, reinterpret_cast<const uint16_t*>(hp.hi), reinterpret_cast<const uint16_t*>(hp.lo),
@@ -470,24 +462,35 @@ int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d
     if (rc == PAACB_OK) rc = launch_fc_dgrad_bf16(ctx, L - 1, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
     for (int l = L - 2; l >= 1 && rc == PAACB_OK; --l) rc = launch_conv_dgrad_bf16(ctx, l, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
     if (rc == PAACB_OK) rc = launch_fc_wgrad_bf16(ctx, L - 1, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
-    for (int l = L - 2; l >= 0 && rc == PAACB_OK; --l) rc = launch_conv_wgrad_bf16(ctx, l, d_states, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
     return rc;
   }
+}
+
+// fp32 / tf32 modes, layer by layer from the top: `do_tail` = heads + the hidden fc layer (its weight gradient and the data
+// gradient below it), `do_head` = the conv layers
+static int backward_generic(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                            const float* d_fwd_ws, const float* d_dlogits, const float* d_dv, float* d_bwd_ws, float* d_grads,
+                            bool do_tail, bool do_head, cudaStream_t st) {
+  const int L = ctx->n_layers;
+  int rc = PAACB_OK;
   const float* h = d_fwd_ws + ctx->layer[L - 1].out_act_off * batch;
   float* dh = d_bwd_ws + ctx->layer[L - 1].out_act_off * batch;
-  int rc = launch_heads_bwd(ctx, h, nullptr, nullptr, nullptr, nullptr, nullptr, d_params + ctx->actor_w_off, d_params + ctx->critic_w_off, d_dlogits, d_dv, batch,
-                            dh, d_grads + ctx->actor_w_off, d_grads + ctx->actor_b_off, d_grads + ctx->critic_w_off,
-                            d_grads + ctx->critic_b_off, st);
-  if (rc != PAACB_OK) return rc;
+  if (do_tail) {
+    rc = launch_heads_bwd(ctx, h, nullptr, nullptr, nullptr, nullptr, nullptr, d_params + ctx->actor_w_off, d_params + ctx->critic_w_off, d_dlogits, d_dv, batch,
+                          dh, d_grads + ctx->actor_w_off, d_grads + ctx->actor_b_off, d_grads + ctx->critic_w_off,
+                          d_grads + ctx->critic_b_off, st);
+    if (rc != PAACB_OK) return rc;
+  }
   const bool tc = (ctx->math != PAACB_MATH_FP32) && batch > 0;
   const int split3 = ctx->math == PAACB_MATH_TF32X3;
-  if (tc) {
+  if (tc && do_tail) {
     for (int l = 1; l < L; ++l) {
       rc = launch_pack_dgrad_weights(ctx, ctx->layer[l], d_params + ctx->layer[l].w_off, st);
       if (rc != PAACB_OK) return rc;
     }
   }
   for (int l = L - 1; l >= 0; --l) {
+    if ((l == L - 1) ? !do_tail : !do_head) continue;
     const LayerGeom& g = ctx->layer[l];
     const void* x = (l == 0) ? (const void*)d_states : (const void*)(d_fwd_ws + g.in_act_off * batch);
     const float* dz = d_bwd_ws + g.out_act_off * batch;
@@ -502,6 +505,45 @@ int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d
     }
   }
   return PAACB_OK;
+}
+
+int paacb_backward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                   const float* d_fwd_ws, const float* d_dlogits, const float* d_dv, float* d_bwd_ws, float* d_grads,
+                   paacb_stream stream) {
+  return paacb_backward_part(ctx, d_params, d_states, batch, d_fwd_ws, d_dlogits, d_dv, d_bwd_ws, d_grads, PAACB_BWD_ALL,
+                             stream);
+}
+
+int64_t paacb_grad_tail_offset(const paacb_ctx* ctx) {
+  return ctx ? ctx->layer[ctx->n_layers - 1].w_off : PAACB_EINVAL;
+}
+
+int paacb_backward_part(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                        const float* d_fwd_ws, const float* d_dlogits, const float* d_dv, float* d_bwd_ws, float* d_grads,
+                        int part, paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_params && d_states && d_fwd_ws && d_dlogits && d_dv && d_bwd_ws && d_grads, "NULL argument");
+  PAACB_CHECK_ARG(((uintptr_t)d_bwd_ws & 15) == 0 && ((uintptr_t)d_grads & 15) == 0, "workspace / grads must be 16-byte aligned");
+  PAACB_CHECK_ARG(part == PAACB_BWD_ALL || part == PAACB_BWD_TAIL || part == PAACB_BWD_HEAD, "unknown part");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool do_tail = part != PAACB_BWD_HEAD, do_head = part != PAACB_BWD_TAIL;
+  if (do_tail && cudaMemsetAsync(d_grads, 0, (size_t)ctx->param_count * sizeof(float), st) != cudaSuccess) {
+    set_error("paacb_backward: memset failed");
+    return PAACB_ECUDA;
+  }
+  const int L = ctx->n_layers;
+  if (ctx->math == PAACB_MATH_BF16X3) {
+    if (batch == 0) return PAACB_OK;
+    int rc = PAACB_OK;
+    if (do_tail) {
+      rc = backward_bf16_tail(ctx, d_params, d_fwd_ws, d_dlogits, d_dv, d_bwd_ws, d_grads, batch, st);
+      if (rc != PAACB_OK) return rc;
+    }
+    // weight gradients of the conv layers: nothing downstream depends on them, so they come last and a caller can
+    // all-reduce the tail of the gradient buffer while they run
+    for (int l = L - 2; l >= 0 && rc == PAACB_OK && do_head; --l) rc = launch_conv_wgrad_bf16(ctx, l, d_states, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
+    return rc;
+  }
+  return backward_generic(ctx, d_params, d_states, batch, d_fwd_ws, d_dlogits, d_dv, d_bwd_ws, d_grads, do_tail, do_head, st);
 }
 
 int paacb_clip_rmsprop(const paacb_ctx* ctx, float* d_params, float* d_ms, float* d_mom, const float* d_grads,

@@ -37,7 +37,7 @@ class RolloutEngine(object):
 
     def __init__(self, network, n_envs, t_max, gamma=0.99, rho=0.99, eps=0.1, momentum=0.0,
                  clip_norm=3.0, clip_norm_type='global', seed=3, process_group=None, world_size=1,
-                 train_forward='batched'):
+                 train_forward='batched', overlap_allreduce=True):
         self.net = network
         self.lib = network._lib
         self.ctx = network.ctx
@@ -57,6 +57,9 @@ class RolloutEngine(object):
             raise Exception('Norm type not recognized')          # actor_learner.py:67
         self.beta = float(network.entropy_regularisation_strength)
         self.group, self.world = process_group, int(world_size)
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self.tail_off = int(self.lib.paacb_grad_tail_offset(self.ctx))
+        self._pending = []
 
         d, N, T, A, B = self.dev, self.N, self.T, self.A, self.B
         f32 = dict(dtype=torch.float32, device=d)
@@ -196,13 +199,31 @@ class RolloutEngine(object):
             self.ctx, p(self.rewards), p(self.over), p(self.values), p(self.boot_v), p(self.actions), p(self.pi),
             p(self.v), T, N, C.c_double(self.gamma), C.c_float(self.beta), p(self.y), p(self.adv), p(self.dlogits),
             p(self.dv), p(self.loss), st), 'paacb_returns_loss_grad')
+        if self.world > 1 and self.overlap_allreduce:
+            # multi-GPU: the tail of the flat gradient (hidden fc layer + heads, 95 % of the parameters) is final after the
+            # first part of the backward; its all-reduce runs on NCCL's stream under the conv layers' weight gradients
+            for part in (_lib.BWD_TAIL, _lib.BWD_HEAD):
+                _lib.check(self.lib.paacb_backward_part(self.ctx, p(self.net.params), p(flat_states), B, p(self.fwd_ws),
+                                                        p(self.dlogits), p(self.dv), p(self.bwd_ws), p(self.grads), part, st),
+                           'paacb_backward_part')
+                if part == _lib.BWD_TAIL:
+                    self._pending = [torch.distributed.all_reduce(self.grads[self.tail_off:], op=torch.distributed.ReduceOp.SUM,
+                                                                  group=self.group, async_op=True)]
+            return
         _lib.check(self.lib.paacb_backward(self.ctx, p(self.net.params), p(flat_states), B, p(self.fwd_ws),
                                            p(self.dlogits), p(self.dv), p(self.bwd_ws), p(self.grads), st),
                    'paacb_backward')
 
     def allreduce(self):
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.group)
+            if self._pending:
+                self._pending.append(torch.distributed.all_reduce(self.grads[:self.tail_off], op=torch.distributed.ReduceOp.SUM,
+                                                                  group=self.group, async_op=True))
+                for w in self._pending:
+                    w.wait()             # stream-level wait: the optimizer kernel is ordered after both reductions
+                self._pending = []
+            else:
+                torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
     def apply(self, lr):
         p = _lib.ptr

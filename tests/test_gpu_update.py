@@ -64,6 +64,35 @@ def test_backward_vs_autograd(arch, A, b):
         off += d.size
 
 
+@pytest.mark.parametrize('arch,math', [('NATURE', 'bf16x3'), ('NATURE', 'tf32x3'), ('NIPS', 'fp32')])
+def test_backward_parts_equal_whole(arch, math):
+    """paacb_backward_part(TAIL) leaves d_grads[tail_offset:] final (it can be all-reduced while the rest runs);
+    TAIL followed by HEAD equals paacb_backward (gradient sums use atomics: compared to rounding)."""
+    A, b = 6, 50
+    net = G.make_net(arch, A, seed=11, math=math)
+    rng = np.random.RandomState(5)
+    states = rng.randint(0, 256, (b, 84, 84, 4)).astype(np.uint8)
+    fwd = G.forward(net, states)
+    dl = G.dev((rng.randn(b, A) * 0.01).astype(np.float32)); dv = G.dev((rng.randn(b) * 0.01).astype(np.float32))
+    whole, _ = G.backward(net, fwd, dl.cpu().numpy(), dv.cpu().numpy())
+    bws = torch.zeros((int(net._lib.paacb_backward_workspace_floats(net.ctx, b)),), dtype=torch.float32, device='cuda')
+    grads = torch.full((net.param_count,), 7.0, dtype=torch.float32, device='cuda')
+    p = _lib.ptr
+    tail = int(net._lib.paacb_grad_tail_offset(net.ctx))
+    assert 0 < tail < net.param_count and net.param_count - tail > 0.9 * net.param_count
+    _lib.check(net._lib.paacb_backward_part(net.ctx, p(net.params), p(fwd['states']), b, p(fwd['ws']), p(dl), p(dv), p(bws),
+                                            p(grads), _lib.BWD_TAIL, G.stream()), 'tail')
+    torch.cuda.synchronize()
+    after_tail = grads.cpu().numpy()
+    assert_close(after_tail[tail:], whole[tail:], 1e-6, 'tail of the gradient after PAACB_BWD_TAIL')
+    _lib.check(net._lib.paacb_backward_part(net.ctx, p(net.params), p(fwd['states']), b, p(fwd['ws']), p(dl), p(dv), p(bws),
+                                            p(grads), _lib.BWD_HEAD, G.stream()), 'head')
+    torch.cuda.synchronize()
+    both = grads.cpu().numpy()
+    assert np.array_equal(both[tail:], after_tail[tail:])          # HEAD does not touch the tail
+    assert_close(both, whole, 1e-6, 'TAIL + HEAD vs paacb_backward')
+
+
 @pytest.mark.parametrize('clip_type,gscale', [(_lib.CLIP_GLOBAL, 1.0), (_lib.CLIP_GLOBAL, 0.125), (_lib.CLIP_IGNORE, 1.0)])
 def test_clip_rmsprop_vs_oracle(clip_type, gscale):
     net = G.make_net('NIPS', 6)                  # P = 677,943: not a multiple of 4 -> exercises the scalar tail
