@@ -22,23 +22,37 @@ namespace paacb {
 
 constexpr int kC1_N = 32;            // output channels
 constexpr int kC1_ND = 3 * kC1_N;    // MMA N: three digit images
-constexpr int kC1_WU = 21, kC1_HQ = 21, kC1_ROWS = 9, kC1_OH = 20, kC1_OW = 20;
-constexpr int kC1_PLANE = 16 * kC1_WU * kC1_ROWS;      // 3,024 bytes per parity plane patch
-constexpr int kC1_BOX = 4 * kC1_PLANE;                 // one TMA box per tile: [4 parities][9 plane rows][336 bytes]
-constexpr int kC1_SLOT = 12288;
+constexpr int kC1_WU = 21, kC1_HQ = 21, kC1_OH = 20, kC1_OW = 20;
+// A tile is SIX plane rows (6 x 21 = 126 of the 128 MMA rows): every tile then holds whole output rows, i.e. runs of 20
+// output positions (1,280 contiguous bytes per plane) that leave through the TMA engine from a staging tile.  The first
+// version (tiles of 128 consecutive units, 16-byte stores from registers at a 64-byte lane stride) was bound by the LSU:
+// 16 L1 wavefronts per store instruction, l1tex at 72 % with DRAM at 47 % and the tensor pipe at 26 %.
+constexpr int kC1_TROWS = 6;
+constexpr int kC1_ROWS = kC1_TROWS + 1;                // + 1 plane row for the filter rows kh >= 4
+constexpr int kC1_PLANE = 16 * kC1_WU * kC1_ROWS;      // 2,352 bytes per parity plane patch
+constexpr int kC1_BOX = 4 * kC1_PLANE;                 // one TMA box per tile: [4 parities][7 plane rows][336 bytes]
+constexpr int kC1_SLOT = 10240;                        // >= 3 planes + (127 + 21 + 2) units: the two spare MMA rows read stale bytes
 constexpr int kC1_NSLOTS = 6;                            // six tiles of patches in flight
 constexpr int kC1_WBYTES = 2 * kC1_ND * 128;             // K = 256 bytes per row: two 128-byte K-blocks of 96 rows
-constexpr int kC1_SMEM = kC1_NSLOTS * kC1_SLOT + kC1_WBYTES + 1024 + (2 * kC1_NSLOTS + 5) * 8 + 16;
-constexpr int kC1_THREADS = 64 + 256;
+constexpr int kC1_RUN = 1536;                            // staging bytes per run of 20 positions x 64 B (512-byte aligned for the 64-byte swizzle)
+constexpr int kC1_STG_PLANE = kC1_TROWS * kC1_RUN;       // one plane (hi or lo) of one epilogue group's tile
+constexpr int kC1_STG = 2 * 2 * 2 * kC1_STG_PLANE;       // two groups x two tiles in flight x (hi, lo)
+constexpr int kC1_SMEM = kC1_NSLOTS * kC1_SLOT + kC1_WBYTES + kC1_STG + 256 + 1024 + (2 * kC1_NSLOTS + 5) * 8 + 16;
+constexpr int kC1_EPI_WARPS = 16;                       // 2 accumulator buffers x 2 channel halves x 4 TMEM lane quarters
+constexpr int kC1_THREADS = 64 + 32 * kC1_EPI_WARPS;
 constexpr int kC1_TMEM = 256;                            // two accumulator buffers of 96 columns at 0 and 128
+static_assert((kC1_NSLOTS * kC1_SLOT) % 1024 == 0 && kC1_WBYTES % 1024 == 0 && kC1_STG % 1024 == 0, "1024-byte aligned regions");
+static_assert(3 * kC1_PLANE + (127 + kC1_WU + 2) * 16 <= kC1_SLOT, "slot holds every byte an MMA row can address");
 
 struct Conv1Params {
   CUtensorMap tmA;         // uint8 states as (84 words = one 336-byte image row, b * 21 plane rows, 4 row parities)
   CUtensorMap tmW;         // int8 digit image [96 rows = (digit, co)][256 k]
+  CUtensorMap tmOut[2];    // hi / lo plane of the output as (32 channels, b * 400 positions), box = one run of 20 positions
   int num_tiles;
   int batch;
   const float* bias;
   const float* wscale;     // [32]: s_c / (63 * 255)
+  int dbg;                 // PAACB_DBG ablations (timing experiments only): 1 no TMA stores, 2 no epilogue arithmetic, 4 no MMAs, 8 no A loads
   uint8_t* out_hi;
   uint8_t* out_lo;
 };
@@ -97,7 +111,9 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
   uint8_t* wsm = smem + kC1_NSLOTS * kC1_SLOT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + kC1_WBYTES);
+  uint8_t* stg = wsm + kC1_WBYTES;
+  float2* s_sb = reinterpret_cast<float2*>(stg + kC1_STG);          // per channel: (scale, bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + kC1_STG + 256);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kC1_NSLOTS;
   uint64_t* w_bar = bars + 2 * kC1_NSLOTS;
@@ -116,12 +132,15 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
     mbar_init(w_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 256);
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmW);
+    tma_prefetch_desc(&p.tmOut[0]);
+    tma_prefetch_desc(&p.tmOut[1]);
   }
+  if (tid >= 64 && tid < 64 + kC1_N) s_sb[tid - 64] = make_float2(__ldg(p.wscale + tid - 64), __ldg(p.bias + tid - 64));
   if (warp == 1) tmem_alloc(tmem_slot, kC1_TMEM);
   tc_fence_before();
   __syncthreads();
@@ -137,10 +156,10 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int row0 = (int)(((int64_t)tile * 128) / kC1_WU);
         mbar_wait(&empty_bar[slot], phase ^ 1u);
+        if (p.dbg & 8) { mbar_arrive(&full_bar[slot]); if (++slot == kC1_NSLOTS) { slot = 0; phase ^= 1u; } continue; }
         mbar_arrive_expect_tx(&full_bar[slot], kC1_BOX);
-        tma_load_3d(ring + slot * kC1_SLOT, &p.tmA, 0, row0, 0, &full_bar[slot]);
+        tma_load_3d(ring + slot * kC1_SLOT, &p.tmA, 0, tile * kC1_TROWS, 0, &full_bar[slot]);
         if (++slot == kC1_NSLOTS) { slot = 0; phase ^= 1u; }
       }
     }
@@ -160,14 +179,13 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
       const uint32_t aph = (uint32_t)((tl >> 1) & 1);
       mbar_wait(&tempty_bar[ab], aph ^ 1u);
       tc_fence_after();
-      const uint32_t rel = (uint32_t)(((int64_t)tile * 128) % kC1_WU) * 16u;
       const uint32_t d0 = tmem_base + (uint32_t)(ab * 128);
       mbar_wait(&full_bar[slot], phase);
       tc_fence_after();
       if (leader) {
 #pragma unroll
-        for (int kh = 0; kh < 8; ++kh) {           // filter row kh: parity plane kh & 3, one plane row further down for kh >= 4
-          const uint32_t a = ring_a + (uint32_t)(slot * kC1_SLOT + (kh & 3) * kC1_PLANE + (kh >> 2) * kC1_WU * 16) + rel;
+        for (int kh = 0; kh < ((p.dbg & 4) ? 1 : 8); ++kh) {           // filter row kh: parity plane kh & 3, one plane row further down for kh >= 4
+          const uint32_t a = ring_a + (uint32_t)(slot * kC1_SLOT + (kh & 3) * kC1_PLANE + (kh >> 2) * kC1_WU * 16);
           const uint64_t bd = desc_with_addr(bdesc0, w_a + (uint32_t)((kh / 4) * (kC1_ND * 128) + (kh % 4) * 32));
           umma_i8(d0, desc_with_addr(adesc0, a), bd, idesc, kh ? 1u : 0u);
         }
@@ -181,56 +199,85 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
   } else {
     // =========================== epilogue ===========================
     const int ew = warp & 3;
-    const int r = ew * 32 + lane;
-    const int grp = (warp - 2) >> 2;
-    float breg[kC1_N], sreg[kC1_N];
-#pragma unroll
-    for (int j = 0; j < kC1_N; ++j) {
-      breg[j] = __ldg(p.bias + j);
-      sreg[j] = __ldg(p.wscale + j);
-    }
+    const int r = ew * 32 + lane;                   // MMA row = unit r of the tile's 6 x 21 units
+    const int grp = ((warp - 2) >> 2) & 1;          // epilogue group = accumulator buffer it drains
+    const int half = (warp - 2) >> 3;               // channels [16 half, 16 half + 16): two warps share a tile row, which doubles
+                                                    // the warps that hide the TMEM / shared-memory / barrier latencies
+    const int pr = r / kC1_WU, ju = r - pr * kC1_WU;
+    const bool rowok = (r < kC1_TROWS * kC1_WU) && (ju < kC1_OW);
+    // this group's two staging tiles (hi plane, then lo plane, each): the TMA engine drains tile i while tile i + 1 is computed
+    // and staged (with ONE tile the group sat in the barrier behind cp.async.bulk.wait_group.read for a third of the time)
+    uint8_t* stg_g = stg + grp * 4 * kC1_STG_PLANE;
+    const uint32_t srow0 = smem_u32(stg_g) + (uint32_t)(pr * kC1_RUN + ju * 64);
+    const uint32_t swz = (srow0 >> 7) & 3u;         // 64-byte swizzle: 16-byte chunk index ^ address bits [7, 9)
+    int sbuf = 0;
+    const bool io = (tid == 64 + 128 * grp);        // issues the TMA stores of this group's tiles (a thread of half 0)
+    const float4* sb4 = reinterpret_cast<const float4*>(s_sb) + half * 8;
     for (int tl = grp, tile = blockIdx.x + grp * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x, tl += 2) {
       const uint32_t aph = (uint32_t)((tl >> 1) & 1);
-      const uint32_t q = (uint32_t)tile * 128u + (uint32_t)r;
-      const uint32_t prow = q / (uint32_t)kC1_WU;
-      const int ju = (int)(q - prow * (uint32_t)kC1_WU);
-      const uint32_t n = prow / (uint32_t)kC1_HQ;
-      const int oh = (int)(prow - n * (uint32_t)kC1_HQ);
-      const bool ok = (ju < kC1_OW) && (oh < kC1_OH) && ((int)n < p.batch);
-      const int64_t obase = (((int64_t)n * kC1_OH + oh) * kC1_OW + ju) * kC1_N;
+      const uint32_t g = (uint32_t)tile * kC1_TROWS + (uint32_t)pr;           // global plane row
+      const uint32_t n = g / (uint32_t)kC1_HQ;
+      const bool ok = rowok && ((int)(g - n * (uint32_t)kC1_HQ) < kC1_OH) && ((int)n < p.batch);
       mbar_wait(&tfull_bar[grp], aph);
       tc_fence_after();
-      uint32_t v0[32], v1[32], v2[32];
-      const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(grp * 128);
-      tmem_ld32(tcol, v0);
-      tmem_ld32(tcol + 32u, v1);
-      tmem_ld32(tcol + 64u, v2);
+      uint32_t v0[16], v1[16], v2[16];
+      const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(grp * 128 + half * 16);
+      tmem_ld16(tcol, v0);
+      tmem_ld16(tcol + 32u, v1);
+      tmem_ld16(tcol + 64u, v2);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&tempty_bar[grp]);           // the accumulator is in registers: release the buffer before the arithmetic
-      if (ok) {
-        float o[32];
+      uint32_t hw[8], lw[8];
+      if (p.dbg & 2) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 8; ++j) { hw[j] = v0[2 * j] ^ v1[2 * j + 1]; lw[j] = v2[2 * j] ^ v0[2 * j + 1]; }
+      } else
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 sb = sb4[j];              // (scale, bias) of channels 2j, 2j + 1: one broadcast 16-byte load
+        float o[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
           // |acc| < 2^22: int -> float exactly on the integer + FMA pipes (the conversion pipe issues at a quarter rate)
-          const float f0 = __uint_as_float(v0[j] + 0x4B400000u) - 12582912.0f;
-          const float f1 = __uint_as_float(v1[j] + 0x4B400000u) - 12582912.0f;
-          const float f2 = __uint_as_float(v2[j] + 0x4B400000u) - 12582912.0f;
+          const float f0 = __uint_as_float(v0[2 * j + e] + 0x4B400000u) - 12582912.0f;
+          const float f1 = __uint_as_float(v1[2 * j + e] + 0x4B400000u) - 12582912.0f;
+          const float f2 = __uint_as_float(v2[2 * j + e] + 0x4B400000u) - 12582912.0f;
           const float t = fmaf(f2, 1.0f / 4096.0f, fmaf(f1, 1.0f / 64.0f, f0));
-          o[j] = fmaxf(fmaf(t, sreg[j], breg[j]), 0.f);
+          o[e] = fmaxf(fmaf(t, e ? sb.z : sb.x, e ? sb.w : sb.y), 0.f);
         }
-        uint32_t hw[16], lw[16];
+        split_bf16x2(o[0], o[1], hw[j], lw[j]);
+      }
+      if (io) tma_store_wait_read1();          // the runs of the tile before the previous one have left this staging tile
+      named_bar_sync(1 + grp, 256);
+      const uint32_t srow = srow0 + (uint32_t)(sbuf * 2 * kC1_STG_PLANE);
+      if (ok) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) split_bf16x2(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
-        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase * 2);
-        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase * 2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dh[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-          dl[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t a = srow + ((((uint32_t)(2 * half + c)) ^ swz) << 4);
+          sts128(a, make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]));
+          sts128(a + (uint32_t)kC1_STG_PLANE, make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]));
         }
       }
+      fence_proxy_async();                     // staging writes -> visible to the TMA engine
+      named_bar_sync(1 + grp, 256);
+      if (io) {
+#pragma unroll 1
+        for (int q = 0; q < kC1_TROWS; ++q) {
+          const uint32_t gq = (uint32_t)tile * kC1_TROWS + (uint32_t)q;
+          const uint32_t nq = gq / (uint32_t)kC1_HQ;
+          const int ohq = (int)(gq - nq * (uint32_t)kC1_HQ);
+          if (ohq < kC1_OH && (int)nq < p.batch && !(p.dbg & 1)) {
+            const int orow = ((int)nq * kC1_OH + ohq) * kC1_OW;
+            tma_store_2d(&p.tmOut[0], stg_g + sbuf * 2 * kC1_STG_PLANE + q * kC1_RUN, 0, orow);
+            tma_store_2d(&p.tmOut[1], stg_g + (sbuf * 2 + 1) * kC1_STG_PLANE + q * kC1_RUN, 0, orow);
+          }
+        }
+        tma_store_commit();                    // always one bulk group per tile (possibly empty): wait_group.read 1 counts them
+      }
+      sbuf ^= 1;
     }
+    if (io) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -246,8 +293,8 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
   const LayerGeom& g = ctx->layer[0];
   if (g.C != 4 || g.stride != 4 || g.R != 8 || g.S != 8 || g.N != kC1_N || g.H != 84 || g.W != 84 || g.OH != kC1_OH)
     return PAACB_EUNSUPPORTED;
-  const int64_t q_total = batch * kC1_HQ * kC1_WU;
-  if (q_total >= (1LL << 31) - 256) return PAACB_EUNSUPPORTED;
+  const int64_t plane_rows = batch * kC1_HQ;
+  if (plane_rows * kC1_WU >= (1LL << 31) - 256) return PAACB_EUNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv1_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1_SMEM) != cudaSuccess) {
@@ -271,13 +318,22 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
   const uint32_t wbox[2] = {128u, (uint32_t)kC1_ND};
   if (rc == PAACB_OK) rc = encode_tmap(&p.tmW, ctx->wq_i8, 1, 2, wdims, wstr, wbox, 128);
   if (rc != PAACB_OK) return rc;
-  p.num_tiles = (int)((q_total + 127) / 128);
+  p.num_tiles = (int)((plane_rows + kC1_TROWS - 1) / kC1_TROWS);
   p.batch = (int)batch;
   p.bias = params + g.b_off;
   p.wscale = ctx->wq_scale;
+  p.dbg = ctx->dbg;
   const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
   p.out_hi = out.hi;
   p.out_lo = out.lo;
+  {
+    const uint64_t odims[2] = {(uint64_t)kC1_N, (uint64_t)batch * kC1_OH * kC1_OW};
+    const uint64_t ostr[1] = {(uint64_t)kC1_N * 2};
+    const uint32_t obox[2] = {(uint32_t)kC1_N, (uint32_t)kC1_OW};
+    rc = encode_tmap_bf16(&p.tmOut[0], out.hi, 2, odims, ostr, obox, 64);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmOut[1], out.lo, 2, odims, ostr, obox, 64);
+    if (rc != PAACB_OK) return rc;
+  }
   const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, K_FWD0, st);
   conv1_i8_kernel<<<grid, kC1_THREADS, kC1_SMEM, st>>>(p);
