@@ -481,8 +481,11 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
           tma_store_4d(&p.tmOut[0], tile_p, 0, 0, ph, tile * Ge::OH);
           tma_store_commit();
         }
-        // bias gradient: channel = lane for both classes (the shuffles overlap the TMA engine reading the tile)
-        bsum += warp_transpose_sum(o[0], lane) + warp_transpose_sum(o[1], lane);
+        // bias gradient: channel = lane for both classes: add the classes first, ONE transposed warp reduction per tile
+        // (this kernel has no registers left for per-thread column sums; the shuffles overlap the TMA engine reading the tile)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[0][j] += o[1][j];
+        bsum += warp_transpose_sum(o[0], lane);
         if (io) tma_store_wait_read();
         named_bar_sync(1 + ph, 128);
         if (ok) {
@@ -507,6 +510,8 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
     const int ew = warp & 3;                     // TMEM lane quarter this warp may access
     const int r = ew * 32 + lane;                // tile row of this thread
     const int grp = (warp - 2) >> 2;             // epilogue group = accumulator buffer it drains (tiles tl with tl & 1 == grp)
+    // (per-thread column sums reduced once at the end -- what tc2_stream.cu's dgrad does -- cost this kernel 42 registers
+    // it does not have: conv3's data gradient got 7 % slower with them)
     float bsum[NACC == 1 ? BN / 32 : 1];
 #pragma unroll
     for (int i = 0; i < (NACC == 1 ? BN / 32 : 1); ++i) bsum[i] = 0.f;

@@ -191,7 +191,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
     const int r = ew * 32 + lane;
     // dgrad bias sums kept in registers across tiles when the column -> channel map is tile-invariant
     // (channel = column % 64 and tiles start at multiples of 64): bsum[j] belongs to channel 32 * j + lane
-    float bsum[2] = {0.f, 0.f};
+    // (per-thread sums over this thread's rows; the transposed warp reduction runs once at the end of the kernel)
+    float bs[MODE == ST_DGRAD ? 2 : 1][32];
+#pragma unroll
+    for (int i = 0; i < (MODE == ST_DGRAD ? 2 : 1); ++i)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bs[i][j] = 0.f;
     const bool reg_sums = (MODE == ST_DGRAD) && p.dbias != nullptr && p.dbias_mod == 64;
     int tl = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++tl) {
@@ -267,9 +272,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
           }
           if constexpr (MODE == ST_DGRAD) {
             if (p.dbias != nullptr) {
-              const float s = warp_transpose_sum32(o, lane);
-              if (reg_sums) bsum[(c0 >> 5) & 1] += s;
-              else atomicAdd(p.dbias + ((n0 + lane) % p.dbias_mod), s);
+              if (reg_sums) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) bs[(c0 >> 5) & 1][j] += o[j];
+              } else {
+                const float s = warp_transpose_sum32(o, lane);
+                atomicAdd(p.dbias + ((n0 + lane) % p.dbias_mod), s);
+              }
             }
           }
         }
@@ -277,9 +286,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
       tc_fence_before();
       mbar_arrive(&tempty_bar[ab]);
     }
-    if (reg_sums) {
-      atomicAdd(p.dbias + lane, bsum[0]);
-      atomicAdd(p.dbias + 32 + lane, bsum[1]);
+    if constexpr (MODE == ST_DGRAD) {
+      if (reg_sums) {
+        atomicAdd(p.dbias + lane, warp_transpose_sum32(bs[0], lane));
+        atomicAdd(p.dbias + 32 + lane, warp_transpose_sum32(bs[1], lane));
+      }
     }
   }
 
