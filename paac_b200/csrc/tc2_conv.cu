@@ -408,21 +408,17 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
       const int ph = (warp - 2) >> 2;                                       // this warp's output-row parity: classes (ph, 0), (ph, 1)
       const bool io = (tid == 64 + 128 * ph);                               // issues the TMA stores of this group's tile
       float bsum = 0.f;
-      // the ReLU-mask words of this thread's two output pixels, software-pipelined ONE TILE AHEAD: a load issued in the
-      // tile it is used in exposed a DRAM round trip per tile (it was the top stall of the staged epilogue's first version)
-      uint4 mk[2][4], mkn[2][4];
-      auto load_mask = [&](int tile, uint4 (&m)[2][4]) {
-#pragma unroll
-        for (int pw = 0; pw < 2; ++pw) {
-          const int64_t ob = (((int64_t)tile * Ge::XH + Ge::S * qh + ph) * Ge::XW + Ge::S * qw + pw) * BN;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            m[pw][j] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok && tile < p.num_tiles) m[pw][j] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + ob * 2) + j);
-          }
-        }
+      // The ReLU-mask words of this thread's two output pixels (2 x 64 B = one 128-byte line) are loaded at the top of the
+      // tile, before the wait for the MMAs; the line of the NEXT tile is requested into L2 at the same time, so the load
+      // is an L2 hit.  (Version 1 loaded them cold: a DRAM round trip per tile.  Version 2 carried them one tile ahead in
+      // registers: 32 registers this kernel does not have -- the spill put a local-memory load on the critical path right
+      // after the MMA barrier, 18 % of all stall samples.)
+      uint4 mk[2][4];
+      auto mask_ptr = [&](int tile, int pw) {
+        const int64_t ob = (((int64_t)tile * Ge::XH + Ge::S * qh + ph) * Ge::XW + Ge::S * qw + pw) * BN;
+        return reinterpret_cast<const uint4*>(p.mask_hi + ob * 2);
       };
-      load_mask((int)blockIdx.x, mkn);
+      if (ok && (int)blockIdx.x < p.num_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_ptr((int)blockIdx.x, 0)));
       int tl = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
         const int ab = tl & 1;
@@ -430,8 +426,11 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mk[pw][j] = mkn[pw][j];
-        load_mask(tile + (int)gridDim.x, mkn);
+          for (int j = 0; j < 4; ++j) {
+            mk[pw][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) mk[pw][j] = __ldg(mask_ptr(tile, pw) + j);
+          }
+        if (ok && tile + (int)gridDim.x < p.num_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_ptr(tile + (int)gridDim.x, 0)));
         mbar_wait(&tfull_bar[ab], aph);
         tc_fence_after();
         float o[2][32];
