@@ -319,18 +319,22 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    _lib.check(net._lib.paacb_profile_enable(net.ctx, 1))
-    _lib.check(net._lib.paacb_profile_reset(net.ctx))
+    # pass 1 -- the headline: K steps, nothing but the hot path on the stream
     launches0 = net.launch_count()
     clocks = ClockSampler(local)
-    ms_total = timed(step_device, args.steps)
+    ms_plain = timed(step_device, args.steps)
     clk = clocks.stop()
     launches = net.launch_count() - launches0
+    ms_per_step = ms_plain / args.steps
+    value = world * N * T * args.steps / (ms_plain / 1e3)
+    # pass 2 -- the same K steps with every kernel bracketed by a CUDA event pair on the launching stream (the per-kernel
+    # roofline table); the event records cost ~1 % of the step, which is why the headline is not taken from this pass
+    _lib.check(net._lib.paacb_profile_enable(net.ctx, 1))
+    _lib.check(net._lib.paacb_profile_reset(net.ctx))
+    ms_total = timed(step_device, args.steps)
     prof = read_profile(net)
     _lib.check(net._lib.paacb_profile_enable(net.ctx, 0))
     loss_val = float(eng.loss.item())
-    ms_per_step = ms_total / args.steps
-    value = world * N * T * args.steps / (ms_total / 1e3)
 
     # ---- per-kernel roofline table (device time from CUDA events on the launching stream) ---------------
     hbm_peak, tc_burst, tc_sust, peak_kind = load_peaks()
@@ -508,6 +512,7 @@ def run_b200(args):
                 'config': workload_config(args, world), 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'cpu_baseline': cpu, 'variants': variants,
                 'step_fraction_of_tensor_peak': step_frac, 'kernel_time_accounted': accounted / ms_total,
+                'profiled_ms_per_step': ms_total / args.steps,
                 'kernels': [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kk.items()} for kk in kernels],
                 'loss': loss_val}
         print(json.dumps(line), flush=True)

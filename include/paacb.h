@@ -8,7 +8,8 @@
  * Conventions
  *   - extern "C", plain pointers and sizes, no C++/torch types.
  *   - every pointer named d_* is DEVICE memory (or pinned+mapped host memory for d_frames);
- *     the caller owns every buffer; the library never allocates device memory.
+ *     the caller owns every buffer; the library allocates no device memory on the path (a context owns
+ *     only its operand images of the weights, made by paacb_set_math, and a 256-byte barrier counter).
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), does no
  *     host synchronisation and no allocation, so a sequence of calls can be captured in a
  *     CUDA graph by the caller.

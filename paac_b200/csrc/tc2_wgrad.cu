@@ -67,6 +67,7 @@ struct Wg2Params {
   const uint8_t* a_u8;    // conv1: the uint8 states [b, 84, 84, 4], converted to bf16 in shared memory, instead of tmA
   float* dw;              // [K, BN] fp32
   float w_scale;          // 1/255 for the uint8 layer (the operand holds the raw pixel values), else 1
+  int dbg;                // PAACB_DBG ablations (timing experiments only): 16 hi*hi MMAs only, 32 no TMA loads
 };
 
 template <int L>
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
       uint32_t phase = 0;
       for (int s = s_begin; s < s_end; ++s) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (p.dbg & 32) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1u; } continue; }
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
         uint8_t* a = a_sm + stage * Cfg::A_STAGE;
         uint8_t* b = b_sm + stage * Cfg::B_STAGE;
@@ -206,10 +208,10 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
               umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc_full, t > 0 ? 1u : first);
             } else {
               umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, t > 0 ? 1u : first);
-              umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_lo + bo), idesc, 1u);
+              if (!(p.dbg & 16)) umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_lo + bo), idesc, 1u);
             }
             if constexpr (W::A_PIECES == 2)
-              umma_bf16(d, desc_with_addr(adesc0, a_lo + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, 1u);
+              if (!(p.dbg & 16)) umma_bf16(d, desc_with_addr(adesc0, a_lo + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, 1u);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -352,6 +354,7 @@ int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int l, const uint8_t* states, c
   p.batch = (int)batch;
   p.dw = grads + g.w_off;
   p.w_scale = g.in_u8 ? 0.003921568859368563f : 1.0f;
+  p.dbg = ctx->dbg;
   const uint8_t* x_hi;
   const uint8_t* x_lo;
   if (l == 0) {

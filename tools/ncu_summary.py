@@ -36,7 +36,7 @@ def main():
             continue
         seen, rows = set(), []
         for s in src[2:]:
-            if s[sx['Address']] in seen:
+            if len(s) < len(sh) or s[sx['Address']] in seen:
                 continue
             seen.add(s[sx['Address']])
             try:
