@@ -9,7 +9,7 @@
 // dZ is fetched with a box one row/column larger than the tensor so the positions that are not real outputs read
 // zeros (TMA out-of-bounds fill), and the rows of a slot the box never writes are zeroed once at kernel start.
 // All k-tile accumulators of the layer stay in TMEM for the whole kernel (conv2: 4 x 64 columns, conv3: 5 x 64,
-// conv1: 4 x 32); every CTA reduces a contiguous range of samples and adds its partial sums to dW with fp32 atomics
+// conv1: 2 x 64); every CTA reduces a contiguous range of samples and adds its partial sums to dW with fp32 atomics
 // once, at the end.  Bias gradients are produced by the kernels that write dZ (tc2_conv.cu, tc2_stream.cu, heads.cu).
 #include "tc2.cuh"
 
@@ -19,19 +19,22 @@ template <int L>
 struct Wg;
 
 // conv1: X = bf16 states [b,84,84,4] (exact, one piece), dZ1 [b,20,20,32].  Stage = half a sample (224 positions).
-// Units are 32 B (4 pixels x 4 channels): MN groups of 16 k.  A k-tile (kh / 4, kw / 4) takes its 4 groups from the
-// 4 row-parity planes (LBO = plane slot stride); groups 4-7 of the 128-row MMA are unused (rows discarded).
+// Units are 32 B (4 pixels x 4 channels): MN groups of 16 k.  The 8 groups of a 128-row MMA are the 4 row-parity planes
+// (kh & 3; LBO = plane slot stride) for kw / 4 = 0 followed by the SAME 4 planes one unit (4 pixels) further for
+// kw / 4 = 1: the converter warps write every unit twice, into slot p and, shifted by 32 bytes, into slot p + 4, so one
+// MMA covers what were two half-empty k-tiles (the kernel is bound by its MMA count -- PAACB_DBG=128 halves it and the
+// time -- while conversion and loads are free: PAACB_DBG=64 / 32).  k-tile kt = kh / 4.
 template <>
 struct Wg<0> {
-  static constexpr int A_PARTS = 4, A_PIECES = 1, A_SLOT = 9216, A_BOX = 16 * 2 * 21 * 13, B_SLOT = 16384, B_BOX = 64 * 21 * 12;
-  static constexpr int STAGES = 3, KT = 4, BN = 32, KSTEPS = 14, A_KSTEP = 512, B_KSTEP = 1024;
+  static constexpr int A_PARTS = 8, A_PIECES = 1, A_SLOT = 9216, A_BOX = 16 * 2 * 21 * 13, B_SLOT = 16384, B_BOX = 64 * 21 * 12;
+  static constexpr int STAGES = 2, KT = 2, BN = 32, KSTEPS = 14, A_KSTEP = 512, B_KSTEP = 1024;
   static constexpr int A_SWZ = SWZ_32B, A_SBO = 256, B_SWZ = SWZ_64B, B_SBO = 512;
   static constexpr int STAGES_PER_SAMPLE = 2, SAMPLES_PER_STAGE = 1;
   static constexpr int K = 256;
-  __device__ static int a_off(int kt) { return ((kt >> 1) * 21 + (kt & 1)) * 32; }          // within plane 0's slot
+  __device__ static int a_off(int kt) { return kt * 21 * 32; }                               // within plane 0's slot
   __device__ static int a_lbo(int) { return A_SLOT; }
-  // row m of k-tile kt -> weight row k (or -1)
-  __device__ static int k_of(int kt, int m) { return (m < 64) ? (4 * (kt >> 1) + (m >> 4)) * 32 + (kt & 1) * 16 + (m & 15) : -1; }
+  // row m of k-tile kt -> weight row k = kh * 32 + kw * 4 + c: group g = m >> 4 is (kw / 4 = g >> 2, kh & 3 = g & 3)
+  __device__ static int k_of(int kt, int m) { return (4 * kt + ((m >> 4) & 3)) * 32 + (m >> 6) * 16 + (m & 15); }
 };
 // conv2: X1 [b,20,20,32] (hi, lo), dZ2 [b,9,9,64].  Stage = one sample, 100 positions (10 x 10 over the parity plane).
 template <>
@@ -67,7 +70,7 @@ struct Wg2Params {
   const uint8_t* a_u8;    // conv1: the uint8 states [b, 84, 84, 4], converted to bf16 in shared memory, instead of tmA
   float* dw;              // [K, BN] fp32
   float w_scale;          // 1/255 for the uint8 layer (the operand holds the raw pixel values), else 1
-  int dbg;                // PAACB_DBG ablations (timing experiments only): 16 hi*hi MMAs only, 32 no TMA loads
+  int dbg;                // PAACB_DBG ablations (timing experiments only): 16 hi*hi MMAs only, 32 no TMA loads, 64 no conversion, 128 half the k-tiles
 };
 
 template <int L>
@@ -150,6 +153,11 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
           (void)a;                                    // the X operand is written by the converter warps
 #pragma unroll
           for (int piece = 0; piece < 2; ++piece) tma_load_4d(b + piece * W::B_SLOT, &p.tmB[piece], 0, 0, 10 * h, n, &full_bar[stage]);
+          // two stages only: ask for the dZ boxes of the stage after next to be in L2 when their slot frees
+          if (s + 2 < s_end) {
+#pragma unroll
+            for (int piece = 0; piece < 2; ++piece) tma_prefetch_4d(&p.tmB[piece], 0, 0, 10 * ((s + 2) & 1), (s + 2) >> 1);
+          }
         } else if constexpr (L == 1) {
 #pragma unroll
           for (int part = 0; part < 2; ++part)
@@ -188,6 +196,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
         const uint32_t first = (s == s_begin) ? 0u : 1u;
 #pragma unroll
         for (int kt = 0; kt < W::KT; ++kt) {
+          if ((p.dbg & 128) && kt >= W::KT / 2) continue;
           const uint32_t d = tmem_base + (uint32_t)(kt * Cfg::ACC_COLS);
           const uint64_t adesc0 = make_smem_desc(0, (uint32_t)W::a_lbo(kt), W::A_SBO, W::A_SWZ);
           uint32_t a_hi, a_lo = 0;
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
           const int w = ct + i * 256;
           const int R = row0 + w / 21, u = w % 21;
           const int n = R / 21, q = R - n * 21;
-          const bool ok = (w < UNITS) && (s < s_end) && (n < p.batch);
+          const bool ok = (w < UNITS) && (s < s_end) && (n < p.batch) && !(p.dbg & 64);
 #pragma unroll
           for (int part = 0; part < 4; ++part) {
             b[part][i] = make_uint4(0u, 0u, 0u, 0u);
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             const int w = ct + i * 256;
-            if (w < UNITS) {
+            if (w < UNITS && !(p.dbg & 64)) {
               const uint32_t wd[4] = {b[part][i].x, b[part][i].y, b[part][i].z, b[part][i].w};
               uint32_t o[8];
 #pragma unroll
@@ -266,6 +275,12 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
               const uint32_t sw = ((a0 >> 7) & 1u) << 4;       // SWIZZLE_32B on the absolute address
               asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0 ^ sw), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
               asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"((a0 + 16u) ^ sw), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+              if (w > 0) {                                     // the same unit, one unit earlier in slot part + 4 (kw / 4 = 1)
+                const uint32_t a1 = a0 + (uint32_t)(4 * W::A_SLOT) - 32u;
+                const uint32_t sw1 = ((a1 >> 7) & 1u) << 4;
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1 ^ sw1), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"((a1 + 16u) ^ sw1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+              }
             }
           }
         }
