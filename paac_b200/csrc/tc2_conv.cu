@@ -234,6 +234,7 @@ struct ConvKParams {
   uint8_t* out_hi;         // output planes (bf16)
   uint8_t* out_lo;
   const uint8_t* mask_hi;  // dgrad: hi plane of the activation whose ReLU is differentiated (same shape as the output)
+  int dbg;                 // PAACB_DBG ablations (timing experiments only): 256 no A_lo MMAs, 512 no stores, 1024 no patch loads
   float* dbias;            // dgrad: += column sums of the output (the bias gradient of the layer that produced that activation)
 };
 
@@ -332,11 +333,13 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // (requesting the boxes of the tile after next into L2 with cp.async.bulk.prefetch.tensor was measured: 3 % slower)
 #pragma unroll 1
         for (int part = 0; part < Ge::PARTS; ++part) {
 #pragma unroll 1
           for (int piece = 0; piece < (Ge::A_LO ? 2 : 1); ++piece) {
             mbar_wait(&empty_bar[slot], phase ^ 1u);
+            if (p.dbg & 1024) { mbar_arrive(&full_bar[slot]); if (++slot == NSLOTS) { slot = 0; phase ^= 1u; } continue; }
             mbar_arrive_expect_tx(&full_bar[slot], Cfg::BOX_BYTES);
             uint8_t* dst = ring + slot * Ge::SLOT;
             if constexpr (Ge::DGRAD) {
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
               const int jw = Ge::jw(part, t);
               const uint64_t bd = desc_with_addr(bdesc0, w_a + (uint32_t)((jw / 4) * Cfg::KB_BYTES + (jw % 4) * 32));
               if (piece == 0) umma_bf16(d0, ad, bd, idesc_full, (part | t) ? 1u : 0u);    // A_hi * [W_hi | W_lo]
-              else umma_bf16(d0, ad, bd, idesc_half, 1u);                                  // A_lo * W_hi
+              else if (!(p.dbg & 256)) umma_bf16(d0, ad, bd, idesc_half, 1u);              // A_lo * W_hi
             }
             umma_commit(&empty_bar[slot]);
           }
@@ -596,7 +599,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = fmaxf(fmaf(__uint_as_float(v[j]), p.in_scale, breg[c0 + j]), 0.f);
           }
-          if (ok) {
+          if (ok && !(p.dbg & 512)) {
             uint32_t hw[16], lw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) split_bf16x2(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
@@ -671,6 +674,7 @@ int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, const
   ConvKParams p;
   memset(&p, 0, sizeof(p));
   p.batch = (int)batch;
+  p.dbg = ctx->dbg;
   p.bias = params + g.b_off;
   p.in_scale = g.in_u8 ? 0.003921568859368563f : 1.0f;
   const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
@@ -722,6 +726,7 @@ int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, void
   ConvKParams p;
   memset(&p, 0, sizeof(p));
   p.batch = (int)batch;
+  p.dbg = ctx->dbg;
   p.num_tiles = (int)batch;
   const Planes dz = layer_planes(bwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, batch);
   const Planes dx = layer_planes(bwd_ws, gp.out_act_off, (int64_t)g.H * g.W * g.C, batch);
