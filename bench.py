@@ -469,8 +469,9 @@ def run_b200(args):
                         eng.observe_frames(t, host_frames[t & 1].data_ptr() + lo * FRAME_PAIR_BYTES, 1, None, host_rew[t],
                                            host_over[t], lo, hi)
                         ev_obs[c].record(io_stream)
-            for c in range(S):
+            for c, (lo, hi) in enumerate(bounds):
                 stream.wait_event(ev_obs[c])
+                eng.bootstrap(lo, hi)                                         # V(s_T) of this slice under the next slice's frames
             ev_tf.record(tf_stream)
             stream.wait_event(ev_tf)
             eng.update(lr)

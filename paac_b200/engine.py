@@ -93,6 +93,7 @@ class RolloutEngine(object):
         self.gen.manual_seed(int(seed))
         self._slice_ws = {}        # forward workspaces of environment slices (act(t, lo, hi))
         self._stepped = set()      # (t, lo, hi) slices of the training forward already issued ('stepwise')
+        self._booted = []          # [lo, hi) slices whose bootstrap value V(s_T) was already issued (bootstrap())
         self._values_own = self.values
         self.set_train_forward(train_forward)
 
@@ -159,6 +160,24 @@ class RolloutEngine(object):
         self.rewards[t].copy_(rewards, non_blocking=True)
         self.over[t].copy_(over, non_blocking=True)
 
+    def _ws_for(self, lo, hi):
+        if lo == 0 and hi == self.N:
+            return self.act_ws
+        ws = self._slice_ws.get((lo, hi))
+        if ws is None:
+            ws = self._slice_ws[(lo, hi)] = torch.empty((self.net.workspace_floats(hi - lo),), dtype=torch.float32,
+                                                        device=self.dev)
+        return ws
+
+    def bootstrap(self, lo=0, hi=None):
+        """V(s_T) of a slice of the environments (paac.py:140-142), as soon as ITS last frames are in: the end-to-end loop
+        issues it per slice so that it overlaps the frame ingestion of the other slices.  update() computes the bootstrap
+        of whatever slices were not issued."""
+        if hi is None:
+            hi = self.N
+        self.net.forward(self.states[self.T, lo:hi], self.boot_pi[lo:hi], self.boot_v[lo:hi], self._ws_for(lo, hi))
+        self._booted.append((lo, hi))
+
     def train_forward_step(self, t, lo=0, hi=None):
         """'stepwise': the training forward of the samples (t, lo..hi), written into their place in the batch workspace."""
         if self.train_forward != 'stepwise':
@@ -189,7 +208,14 @@ class RolloutEngine(object):
         T, N, B = self.T, self.N, self.B
         p = _lib.ptr
         st = self._stream()
-        self.net.forward(self.states[T], self.boot_pi, self.boot_v, self.act_ws)                  # paac.py:140-142
+        pos = 0                                                                                   # paac.py:140-142
+        for lo, hi in sorted(self._booted):
+            if lo > pos:
+                self.bootstrap(pos, lo)
+            pos = max(pos, hi)
+        if pos < N:
+            self.bootstrap(pos, N)
+        self._booted = []
         flat_states = self.states[:T].view((B,) + STATE_SHAPE)                                    # paac.py:151
         if self.train_forward == 'batched':
             self.net.forward(flat_states, self.pi, self.v, self.fwd_ws)

@@ -217,3 +217,30 @@ def test_cached_weight_images_follow_the_parameters():
     pi_f, v_f = fwd(fresh)
     assert np.array_equal(pi2, pi_f) and np.array_equal(v2, v_f)
     assert not np.array_equal(v1, v2)
+
+
+def test_sliced_bootstrap_equals_whole_batch():
+    """RolloutEngine.bootstrap(lo, hi) per environment slice (what the end-to-end loop issues as each slice's last frames
+    arrive) leaves the same V(s_T), loss and update as the whole-batch bootstrap inside update()."""
+    arch, A, N, T = 'NATURE', 6, 24, 2
+    rng = np.random.RandomState(13)
+    states = rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)
+    rewards = rng.choice([-1.0, 0.0, 1.0], size=(T, N)).astype(np.float32)
+    outs = []
+    for sliced in (False, True):
+        net = G.make_net(arch, A, seed=5, math='bf16x3')
+        eng = RolloutEngine(net, N, T, seed=9)
+        eng.states.copy_(G.dev(states))
+        eng.draw_uniforms()
+        for t in range(T):
+            eng.act(t)
+        eng.rewards.copy_(G.dev(rewards))
+        if sliced:
+            eng.bootstrap(8, 24)          # slice 0 is left to update()
+        eng.update(0.0224)
+        torch.cuda.synchronize()
+        outs.append((eng.boot_v.cpu().numpy(), eng.y.cpu().numpy(), eng.loss.item(), net.get_params()))
+    assert np.array_equal(outs[0][0].view(np.int32), outs[1][0].view(np.int32))
+    assert np.array_equal(outs[0][1].view(np.int32), outs[1][1].view(np.int32))
+    assert abs(outs[0][2] - outs[1][2]) <= 1e-6 * max(1.0, abs(outs[0][2]))
+    assert_close(outs[1][3], outs[0][3], 1e-6, 'post-update weights')

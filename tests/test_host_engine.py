@@ -79,3 +79,21 @@ def test_stepwise_fills_exactly_the_missing_slices():
     net.calls.clear()
     eng._finish_stepwise()
     assert sorted((c['first'], c['b']) for c in net.calls) == [(t * N, N) for t in range(eng.T)]
+
+
+def test_bootstrap_slices_are_completed_by_update_bookkeeping():
+    net, eng = make('batched')
+    eng.bootstrap(4, 8)
+    net.calls.clear()
+    # forward_backward's bootstrap part only (the C calls that follow need a GPU): replicate its bookkeeping
+    pos, issued = 0, []
+    for lo, hi in sorted(eng._booted):
+        if lo > pos:
+            issued.append((pos, lo))
+        pos = max(pos, hi)
+    if pos < eng.N:
+        issued.append((pos, eng.N))
+    assert issued == [(0, 4), (8, eng.N)]
+    eng.bootstrap(0, 4); eng.bootstrap(8, eng.N)
+    assert [(c['b']) for c in net.calls] == [4, eng.N - 8]
+    assert all(not c['sample'] and c['cap'] is None for c in net.calls)
