@@ -262,12 +262,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
             uint32_t hw[16], lw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) split_bf16x2(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
-            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase * 2);
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase * 2);
+            uint8_t* dh = p.out_hi + obase * 2;
+            uint8_t* dl = p.out_lo + obase * 2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dh[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-              dl[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+            for (int j = 0; j < 2; ++j) {
+              stg256(dh + 32 * j, hw + 8 * j);
+              stg256(dl + 32 * j, lw + 8 * j);
             }
           }
           if constexpr (MODE == ST_DGRAD) {

@@ -254,6 +254,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 256-bit global store (sm_100: STG.E.256): a full 32-byte sector per lane.  The epilogues write rows that are 128 bytes
+// or more apart per lane, so every store instruction touches 32 cache lines whatever its width: half the instructions
+// = half the L1 wavefronts.  `ptr` must be 32-byte aligned.
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
