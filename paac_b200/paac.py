@@ -90,6 +90,13 @@ class PAACLearner(ActorLearner):
         total_episode_rewards = np.zeros(N, dtype=np.float64)
         start_time = time.time()
 
+        # The training batch is the concatenation of the acting batches under unchanged parameters (paac.py:92,112,151): its
+        # forward is issued step by step on a side stream WHILE THE EMULATORS RUN (the GPU is idle then), instead of in one
+        # piece inside the update.  Same work, same bits (tests/test_gpu_tc.py::test_training_forward_schedules_are_bit_identical).
+        eng.set_train_forward('stepwise')
+        main_stream = torch.cuda.current_stream(dev)
+        side_stream = torch.cuda.Stream(dev)
+
         while self.global_step < self.max_global_steps:
             loop_start_time = time.time()
             eng.draw_uniforms()
@@ -99,6 +106,9 @@ class PAACLearner(ActorLearner):
 
                 # Start updating all environments with next_actions
                 self.runners.update_environments()
+                side_stream.wait_stream(main_stream)                    # states[t] are complete
+                with torch.cuda.stream(side_stream):
+                    eng.train_forward_step(t)                           # paac.py:151-161's forward, step t's share
                 self.runners.wait_updated()
                 # Done updating all environments, have new states, rewards and is_over
 
@@ -117,6 +127,7 @@ class PAACLearner(ActorLearner):
                     total_episode_rewards[e] = 0
                     emulator_steps[e] = 0
 
+            main_stream.wait_stream(side_stream)
             eng.update(self.get_lr())                                   # paac.py:140-165
             self.last_loss, self.last_norm = eng.loss, eng.norm
 
