@@ -234,7 +234,7 @@ struct ConvKParams {
   uint8_t* out_hi;         // output planes (bf16)
   uint8_t* out_lo;
   const uint8_t* mask_hi;  // dgrad: hi plane of the activation whose ReLU is differentiated (same shape as the output)
-  int dbg;                 // PAACB_DBG ablations (timing experiments only): 256 no A_lo MMAs, 512 no stores, 1024 no patch loads
+  int dbg;                 // PAACB_DBG ablations (timing experiments only): 256 no A_lo MMAs, 512 no stores, 1024 no patch loads, 4096 conv2 dgrad: lo plane through the staging tile, 8192 conv2 dgrad: both planes by direct stores
   float* dbias;            // dgrad: += column sums of the output (the bias gradient of the layer that produced that activation)
 };
 
@@ -464,44 +464,67 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
         uint8_t* tile_p = stg + ph * Cfg::STG_TILE;
         const uint32_t t_row = stg_a + (uint32_t)(ph * Cfg::STG_TILE) + srow * 128u;
         uint32_t lw[2][16];
-        if (io) tma_store_wait_read();                                      // previous tile's lo plane has been read out
-        named_bar_sync(1 + ph, 128);
+        const bool direct_hi = (p.dbg & 8192) != 0;                         // experiment: no staging at all
+        if (!direct_hi) {
+          if (io) tma_store_wait_read();                                    // previous tile's hi plane has been read out
+          named_bar_sync(1 + ph, 128);
+        }
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw) {
           uint32_t hw[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) split_bf16x2(o[pw][2 * j], o[pw][2 * j + 1], hw[j], lw[pw][j]);
           if (ok) {
+            if (direct_hi) {
+              uint8_t* dh = p.out_hi + ((((int64_t)tile * Ge::XH + Ge::S * qh + ph) * Ge::XW + Ge::S * qw) * BN) * 2;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)                                     // 16-byte chunk pw * 4 + c of the row, swizzled
-              sts128(t_row + ((((uint32_t)(pw * 4 + c)) ^ (srow & 7u)) << 4), make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]));
+              for (int c = 0; c < 2; ++c) stg256(dh + pw * 64 + c * 32, &hw[8 * c]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)                                   // 16-byte chunk pw * 4 + c of the row, swizzled
+                sts128(t_row + ((((uint32_t)(pw * 4 + c)) ^ (srow & 7u)) << 4), make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]));
+            }
           }
         }
-        fence_proxy_async();                                                // staging writes -> visible to the TMA engine
-        named_bar_sync(1 + ph, 128);
-        if (io) {
-          tma_store_4d(&p.tmOut[0], tile_p, 0, 0, ph, tile * Ge::OH);
-          tma_store_commit();
+        if (!direct_hi) {
+          fence_proxy_async();                                              // staging writes -> visible to the TMA engine
+          named_bar_sync(1 + ph, 128);
+          if (io) {
+            tma_store_4d(&p.tmOut[0], tile_p, 0, 0, ph, tile * Ge::OH);
+            tma_store_commit();
+          }
         }
         // bias gradient: channel = lane for both classes: add the classes first, ONE transposed warp reduction per tile
         // (this kernel has no registers left for per-thread column sums; the shuffles overlap the TMA engine reading the tile)
 #pragma unroll
         for (int j = 0; j < 32; ++j) o[0][j] += o[1][j];
         bsum += warp_transpose_sum(o[0], lane);
-        if (io) tma_store_wait_read();
-        named_bar_sync(1 + ph, 128);
-        if (ok) {
+        if (p.dbg & 4096) {
+          // (first staged version, kept for A/B timing: the lo plane follows the hi plane through the same staging tile --
+          // two more barriers and a second wait for the TMA engine per tile)
+          if (io) tma_store_wait_read();
+          named_bar_sync(1 + ph, 128);
+          if (ok) {
+#pragma unroll
+            for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                sts128(t_row + ((((uint32_t)(pw * 4 + c)) ^ (srow & 7u)) << 4), make_uint4(lw[pw][4 * c], lw[pw][4 * c + 1], lw[pw][4 * c + 2], lw[pw][4 * c + 3]));
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + ph, 128);
+          if (io) {
+            tma_store_4d(&p.tmOut[1], tile_p, 0, 0, ph, tile * Ge::OH);
+            tma_store_commit();
+          }
+        } else if (ok) {
+          // lo plane: this thread's two pixels are one 128-byte row of the plane -- four 256-bit stores straight from
+          // registers while the TMA engine drains the hi tile (there is no shared memory for a second staging tile)
+          uint8_t* dl = p.out_lo + ((((int64_t)tile * Ge::XH + Ge::S * qh + ph) * Ge::XW + Ge::S * qw) * BN) * 2;
 #pragma unroll
           for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              sts128(t_row + ((((uint32_t)(pw * 4 + c)) ^ (srow & 7u)) << 4), make_uint4(lw[pw][4 * c], lw[pw][4 * c + 1], lw[pw][4 * c + 2], lw[pw][4 * c + 3]));
-        }
-        fence_proxy_async();
-        named_bar_sync(1 + ph, 128);
-        if (io) {
-          tma_store_4d(&p.tmOut[1], tile_p, 0, 0, ph, tile * Ge::OH);
-          tma_store_commit();
+            for (int c = 0; c < 2; ++c) stg256(dl + pw * 64 + c * 32, &lw[pw][8 * c]);
         }
       }
       if (io) tma_store_wait_all();
