@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libpaacb.so')
+LIB_PATH = os.environ.get('PAACB_LIB') or os.path.join(HERE, 'libpaacb.so')      # PAACB_LIB: A/B timing of two builds
 
 PAACB_OK = 0
 ARCH_NIPS, ARCH_NATURE = 0, 1

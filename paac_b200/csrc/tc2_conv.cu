@@ -234,7 +234,7 @@ struct ConvKParams {
   uint8_t* out_hi;         // output planes (bf16)
   uint8_t* out_lo;
   const uint8_t* mask_hi;  // dgrad: hi plane of the activation whose ReLU is differentiated (same shape as the output)
-  int dbg;                 // PAACB_DBG ablations (timing experiments only): 256 no A_lo MMAs, 512 no stores, 1024 no patch loads, 4096 conv2 dgrad: lo plane through the staging tile, 8192 conv2 dgrad: both planes by direct stores
+  int dbg;                 // PAACB_DBG ablations (timing experiments only): 256 no A_lo MMAs, 512 no stores, 1024 no patch loads, 4096 conv2 dgrad: lo plane through the staging tile, 8192 conv2 dgrad: both planes by direct stores (measured: no gain once the staging tile is gone)
   float* dbias;            // dgrad: += column sums of the output (the bias gradient of the layer that produced that activation)
 };
 
@@ -672,6 +672,10 @@ static int launch_convk(const paacb_ctx* ctx, const ConvKParams& p, int slot, cu
       set_error("convk<%d>: cannot set %d bytes of dynamic shared memory", G, Cfg::SMEM_BYTES);
       return PAACB_ECUDA;
     }
+    // one persistent CTA per SM: ask for the largest shared-memory carve-out whatever the kernel's own request (measured
+    // on conv1 forward: the same code ran 10 % slower when its request dropped from 160 KB to 86 KB)
+    cudaFuncSetAttribute(convk_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
     attr_set = true;
   }
   const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);

@@ -23,10 +23,12 @@ namespace paacb {
 constexpr int kC1_N = 32;            // output channels
 constexpr int kC1_ND = 3 * kC1_N;    // MMA N: three digit images
 constexpr int kC1_WU = 21, kC1_HQ = 21, kC1_OH = 20, kC1_OW = 20;
-// A tile is SIX plane rows (6 x 21 = 126 of the 128 MMA rows): every tile then holds whole output rows, i.e. runs of 20
-// output positions (1,280 contiguous bytes per plane) that leave through the TMA engine from a staging tile.  The first
-// version (tiles of 128 consecutive units, 16-byte stores from registers at a 64-byte lane stride) was bound by the LSU:
-// 16 L1 wavefronts per store instruction, l1tex at 72 % with DRAM at 47 % and the tensor pipe at 26 %.
+// A tile is SIX plane rows (6 x 21 = 126 of the 128 MMA rows): a thread's position inside its plane row is a kernel constant.
+// Epilogue history, all measured (profiles/r01_*): (1) 16-byte stores from registers at a 64-byte lane stride: 16 L1
+// wavefronts per store instruction, l1tex at 72 % with DRAM at 47 % -- 0.95 ms per step; (2) a swizzled staging tile
+// drained by TMA stores, two tiles in flight: 0.89-0.92 ms, half of it the per-tile skeleton (two 256-thread barriers, a
+// proxy fence and the wait for the TMA engine); (3) 16 epilogue warps, each thread owning 16 channels of one position =
+// exactly ONE 256-bit store (a full 32-byte sector) per plane, no shared memory, no barrier: 0.64 ms.
 constexpr int kC1_TROWS = 6;
 constexpr int kC1_ROWS = kC1_TROWS + 1;                // + 1 plane row for the filter rows kh >= 4
 constexpr int kC1_PLANE = 16 * kC1_WU * kC1_ROWS;      // 2,352 bytes per parity plane patch
@@ -34,25 +36,21 @@ constexpr int kC1_BOX = 4 * kC1_PLANE;                 // one TMA box per tile: 
 constexpr int kC1_SLOT = 10240;                        // >= 3 planes + (127 + 21 + 2) units: the two spare MMA rows read stale bytes
 constexpr int kC1_NSLOTS = 6;                            // six tiles of patches in flight
 constexpr int kC1_WBYTES = 2 * kC1_ND * 128;             // K = 256 bytes per row: two 128-byte K-blocks of 96 rows
-constexpr int kC1_RUN = 1536;                            // staging bytes per run of 20 positions x 64 B (512-byte aligned for the 64-byte swizzle)
-constexpr int kC1_STG_PLANE = kC1_TROWS * kC1_RUN;       // one plane (hi or lo) of one epilogue group's tile
-constexpr int kC1_STG = 2 * 2 * 2 * kC1_STG_PLANE;       // two groups x two tiles in flight x (hi, lo)
-constexpr int kC1_SMEM = kC1_NSLOTS * kC1_SLOT + kC1_WBYTES + kC1_STG + 256 + 1024 + (2 * kC1_NSLOTS + 5) * 8 + 16;
+constexpr int kC1_SMEM = kC1_NSLOTS * kC1_SLOT + kC1_WBYTES + 256 + 1024 + (2 * kC1_NSLOTS + 5) * 8 + 16;
 constexpr int kC1_EPI_WARPS = 16;                       // 2 accumulator buffers x 2 channel halves x 4 TMEM lane quarters
 constexpr int kC1_THREADS = 64 + 32 * kC1_EPI_WARPS;
 constexpr int kC1_TMEM = 256;                            // two accumulator buffers of 96 columns at 0 and 128
-static_assert((kC1_NSLOTS * kC1_SLOT) % 1024 == 0 && kC1_WBYTES % 1024 == 0 && kC1_STG % 1024 == 0, "1024-byte aligned regions");
+static_assert((kC1_NSLOTS * kC1_SLOT) % 1024 == 0 && kC1_WBYTES % 1024 == 0, "1024-byte aligned regions");
 static_assert(3 * kC1_PLANE + (127 + kC1_WU + 2) * 16 <= kC1_SLOT, "slot holds every byte an MMA row can address");
 
 struct Conv1Params {
   CUtensorMap tmA;         // uint8 states as (84 words = one 336-byte image row, b * 21 plane rows, 4 row parities)
   CUtensorMap tmW;         // int8 digit image [96 rows = (digit, co)][256 k]
-  CUtensorMap tmOut[2];    // hi / lo plane of the output as (32 channels, b * 400 positions), box = one run of 20 positions
   int num_tiles;
   int batch;
   const float* bias;
   const float* wscale;     // [32]: s_c / (63 * 255)
-  int dbg;                 // PAACB_DBG ablations (timing experiments only): 1 no TMA stores, 2 no epilogue arithmetic, 4 no MMAs, 8 no A loads
+  int dbg;                 // PAACB_DBG ablations (timing experiments only): 1 no stores, 2 no epilogue arithmetic, 4 no MMAs, 8 no A loads
   uint8_t* out_hi;
   uint8_t* out_lo;
 };
@@ -111,9 +109,8 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
   uint8_t* wsm = smem + kC1_NSLOTS * kC1_SLOT;
-  uint8_t* stg = wsm + kC1_WBYTES;
-  float2* s_sb = reinterpret_cast<float2*>(stg + kC1_STG);          // per channel: (scale, bias)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + kC1_STG + 256);
+  float2* s_sb = reinterpret_cast<float2*>(wsm + kC1_WBYTES);       // per channel: (scale, bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + kC1_WBYTES + 256);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kC1_NSLOTS;
   uint64_t* w_bar = bars + 2 * kC1_NSLOTS;
@@ -137,8 +134,6 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmW);
-    tma_prefetch_desc(&p.tmOut[0]);
-    tma_prefetch_desc(&p.tmOut[1]);
   }
   if (tid >= 64 && tid < 64 + kC1_N) s_sb[tid - 64] = make_float2(__ldg(p.wscale + tid - 64), __ldg(p.bias + tid - 64));
   if (warp == 1) tmem_alloc(tmem_slot, kC1_TMEM);
@@ -205,13 +200,6 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
                                                     // the warps that hide the TMEM / shared-memory / barrier latencies
     const int pr = r / kC1_WU, ju = r - pr * kC1_WU;
     const bool rowok = (r < kC1_TROWS * kC1_WU) && (ju < kC1_OW);
-    // this group's two staging tiles (hi plane, then lo plane, each): the TMA engine drains tile i while tile i + 1 is computed
-    // and staged (with ONE tile the group sat in the barrier behind cp.async.bulk.wait_group.read for a third of the time)
-    uint8_t* stg_g = stg + grp * 4 * kC1_STG_PLANE;
-    const uint32_t srow0 = smem_u32(stg_g) + (uint32_t)(pr * kC1_RUN + ju * 64);
-    const uint32_t swz = (srow0 >> 7) & 3u;         // 64-byte swizzle: 16-byte chunk index ^ address bits [7, 9)
-    int sbuf = 0;
-    const bool io = (tid == 64 + 128 * grp);        // issues the TMA stores of this group's tiles (a thread of half 0)
     const float4* sb4 = reinterpret_cast<const float4*>(s_sb) + half * 8;
     for (int tl = grp, tile = blockIdx.x + grp * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x, tl += 2) {
       const uint32_t aph = (uint32_t)((tl >> 1) & 1);
@@ -248,36 +236,13 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
         }
         split_bf16x2(o[0], o[1], hw[j], lw[j]);
       }
-      if (io) tma_store_wait_read1();          // the runs of the tile before the previous one have left this staging tile
-      named_bar_sync(1 + grp, 256);
-      const uint32_t srow = srow0 + (uint32_t)(sbuf * 2 * kC1_STG_PLANE);
-      if (ok) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t a = srow + ((((uint32_t)(2 * half + c)) ^ swz) << 4);
-          sts128(a, make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]));
-          sts128(a + (uint32_t)kC1_STG_PLANE, make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]));
-        }
+      if (ok && !(p.dbg & 1)) {                 // 16 channels = one full 32-byte sector per plane
+        const uint32_t oh = g - n * (uint32_t)kC1_HQ;
+        const int64_t ob = ((((int64_t)n * kC1_OH + oh) * kC1_OW + ju) * kC1_N + half * 16) * 2;
+        stg256(p.out_hi + ob, hw);
+        stg256(p.out_lo + ob, lw);
       }
-      fence_proxy_async();                     // staging writes -> visible to the TMA engine
-      named_bar_sync(1 + grp, 256);
-      if (io) {
-#pragma unroll 1
-        for (int q = 0; q < kC1_TROWS; ++q) {
-          const uint32_t gq = (uint32_t)tile * kC1_TROWS + (uint32_t)q;
-          const uint32_t nq = gq / (uint32_t)kC1_HQ;
-          const int ohq = (int)(gq - nq * (uint32_t)kC1_HQ);
-          if (ohq < kC1_OH && (int)nq < p.batch && !(p.dbg & 1)) {
-            const int orow = ((int)nq * kC1_OH + ohq) * kC1_OW;
-            tma_store_2d(&p.tmOut[0], stg_g + sbuf * 2 * kC1_STG_PLANE + q * kC1_RUN, 0, orow);
-            tma_store_2d(&p.tmOut[1], stg_g + (sbuf * 2 + 1) * kC1_STG_PLANE + q * kC1_RUN, 0, orow);
-          }
-        }
-        tma_store_commit();                    // always one bulk group per tile (possibly empty): wait_group.read 1 counts them
-      }
-      sbuf ^= 1;
     }
-    if (io) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -302,6 +267,10 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
       set_error("conv1_i8: cannot set %d bytes of dynamic shared memory", kC1_SMEM);
       return PAACB_ECUDA;
     }
+    // one persistent CTA per SM: ask for the largest shared-memory carve-out whatever the kernel's own request (measured
+    // on conv1 forward: the same code ran 10 % slower when its request dropped from 160 KB to 86 KB)
+    cudaFuncSetAttribute(conv1_i8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
     attr_set = true;
   }
   Conv1Params p;
@@ -326,14 +295,6 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
   const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
   p.out_hi = out.hi;
   p.out_lo = out.lo;
-  {
-    const uint64_t odims[2] = {(uint64_t)kC1_N, (uint64_t)batch * kC1_OH * kC1_OW};
-    const uint64_t ostr[1] = {(uint64_t)kC1_N * 2};
-    const uint32_t obox[2] = {(uint32_t)kC1_N, (uint32_t)kC1_OW};
-    rc = encode_tmap_bf16(&p.tmOut[0], out.hi, 2, odims, ostr, obox, 64);
-    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmOut[1], out.lo, 2, odims, ostr, obox, 64);
-    if (rc != PAACB_OK) return rc;
-  }
   const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, K_FWD0, st);
   conv1_i8_kernel<<<grid, kC1_THREADS, kC1_SMEM, st>>>(p);
