@@ -429,10 +429,14 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            mk[pw][j] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok) mk[pw][j] = __ldg(mask_ptr(tile, pw) + j);
+          for (int j = 0; j < 4; ++j) mk[pw][j] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) {
+#pragma unroll
+          for (int pw = 0; pw < 2; ++pw) {
+            ldg256(mask_ptr(tile, pw), mk[pw][0], mk[pw][1]);
+            ldg256(mask_ptr(tile, pw) + 2, mk[pw][2], mk[pw][3]);
           }
+        }
         if (ok && tile + (int)gridDim.x < p.num_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_ptr(tile + (int)gridDim.x, 0)));
         mbar_wait(&tfull_bar[ab], aph);
         tc_fence_after();
@@ -576,9 +580,10 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              mk[acc][c][j] = make_uint4(0u, 0u, 0u, 0u);
-              if (ok) mk[acc][c][j] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + (ob + c * 32) * 2) + j);
+            for (int j = 0; j < 4; ++j) mk[acc][c][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) {
+              ldg256(p.mask_hi + (ob + c * 32) * 2, mk[acc][c][0], mk[acc][c][1]);
+              ldg256(p.mask_hi + (ob + c * 32) * 2 + 32, mk[acc][c][2], mk[acc][c][3]);
             }
           }
         }

@@ -213,9 +213,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
         for (int c = 0; c < BN / 32; ++c) {
           const int n0 = nt * BN + c * 32;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            mk[c][j] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok && n0 < p.N) mk[c][j] = __ldg(reinterpret_cast<const uint4*>(p.mask_hi + ((int64_t)m * p.ldo + n0) * 2) + j);
+          for (int j = 0; j < 4; ++j) mk[c][j] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok && n0 < p.N) {
+            const uint8_t* mp = p.mask_hi + ((int64_t)m * p.ldo + n0) * 2;
+            ldg256(mp, mk[c][0], mk[c][1]);
+            ldg256(mp + 32, mk[c][2], mk[c][3]);
           }
         }
       }

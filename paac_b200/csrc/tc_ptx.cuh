@@ -262,6 +262,13 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* w) {
                "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                : "memory");
 }
+// 256-bit read-only global load (LDG.E.256.CONSTANT): the counterpart of stg256 for the per-lane mask rows of the data-gradient
+// epilogues.  `ptr` must be 32-byte aligned; fills two uint4.
+__device__ __forceinline__ void ldg256(const void* ptr, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(ptr));
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
