@@ -257,8 +257,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
               o[2 * j + 1] = (ok && a1 != 0u && a1 < 0x8000u) ? __uint_as_float(v[2 * j + 1]) : 0.f;
             }
           } else {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);        // n0 is a multiple of 32: 16-byte aligned if bias is
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = fmaxf(__uint_as_float(v[j]) + __ldg(p.bias + n0 + j), 0.f);
+            for (int j = 0; j < 8; ++j) {                                            // warp-uniform address: one broadcast 16-byte load per 4 columns
+              const float4 bb = __ldg(b4 + j);
+              o[4 * j] = fmaxf(__uint_as_float(v[4 * j]) + bb.x, 0.f);
+              o[4 * j + 1] = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
+              o[4 * j + 2] = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f);
+              o[4 * j + 3] = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
+            }
           }
           if (ok) {
             uint32_t hw[16], lw[16];
