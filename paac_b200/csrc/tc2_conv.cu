@@ -252,7 +252,7 @@ struct ConvKCfg {
   static constexpr int STG_TILE = 13 * 1024;                                // 100 rows x 128 B, 1024-byte aligned
   static constexpr int STG_BYTES = Ge::STAGED ? 2 * STG_TILE : 0;            // one tile per output-row parity: hi plane, then lo plane
   static constexpr int NBARS = 2 * Ge::NSLOTS + 1 + 4 + 1;
-  static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + STG_BYTES + 1024 /* alignment slack */ + NBARS * 8 + 16;
+  static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + STG_BYTES + 1024 /* alignment slack */ + NBARS * 8 + 16 + 256 /* forward: bias row */;
   static constexpr int TMEM_COLS = 4 * NT;                                  // two accumulator buffers of 2 * NT columns
   static_assert(BOX_BYTES <= Ge::SLOT && Ge::SLOT % 1024 == 0, "slot too small");
   // TMA warp, MMA warp, two epilogue groups of four warps (one per accumulator buffer; the staged epilogue splits every
@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] epilogue -> MMA
   uint64_t* mask_bar = tempty_bar + 2;            // staged epilogue: the staging tiles have been read out by the TMA stores
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(bars + Cfg::NBARS + 2);      // forward: the layer's bias row (16-byte aligned)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -317,6 +318,9 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
     tma_prefetch_desc(&p.tmW[0]);
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if constexpr (!Ge::DGRAD) {
+    if (tid >= 64 && tid < 64 + BN) s_bias[tid - 64] = __ldg(p.bias + tid - 64);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -544,11 +548,6 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
     float bsum[NACC == 1 ? BN / 32 : 1];
 #pragma unroll
     for (int i = 0; i < (NACC == 1 ? BN / 32 : 1); ++i) bsum[i] = 0.f;
-    float breg[Ge::DGRAD ? 1 : BN];              // forward: the bias row lives in registers
-    if constexpr (!Ge::DGRAD) {
-#pragma unroll
-      for (int j = 0; j < BN; ++j) breg[j] = __ldg(p.bias + j);
-    }
     for (int tl = grp, tile = blockIdx.x + grp * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x, tl += 2) {
       const int ab = grp;
       const uint32_t aph = (uint32_t)((tl >> 1) & 1);
@@ -590,6 +589,48 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
       }
       mbar_wait(&tfull_bar[ab], aph);
       tc_fence_after();
+      if constexpr (!Ge::DGRAD) {
+        // forward: the whole accumulator row goes to registers first and the buffer is handed back to the MMA warp BEFORE
+        // the arithmetic and the stores (the data-gradient variants have no registers for that: they release it at the end)
+        uint32_t av[BN / 32][32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v2[32];
+          const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * 2 * Cfg::NT + c * 32);
+          tmem_ld32(tcol, av[c]);                               // A_hi * W_hi + A_lo * W_hi
+          tmem_ld32(tcol + (uint32_t)Cfg::NT, v2);              // A_hi * W_lo
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) av[c][j] = __float_as_uint(__uint_as_float(av[c][j]) + __uint_as_float(v2[j]));
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[ab]);
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias);
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t hw[16], lw[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[c * 8 + j];                    // broadcast 16-byte shared-memory load: 4 channels
+            const float o0 = fmaxf(fmaf(__uint_as_float(av[c][4 * j]), p.in_scale, bb.x), 0.f);
+            const float o1 = fmaxf(fmaf(__uint_as_float(av[c][4 * j + 1]), p.in_scale, bb.y), 0.f);
+            const float o2 = fmaxf(fmaf(__uint_as_float(av[c][4 * j + 2]), p.in_scale, bb.z), 0.f);
+            const float o3 = fmaxf(fmaf(__uint_as_float(av[c][4 * j + 3]), p.in_scale, bb.w), 0.f);
+            split_bf16x2(o0, o1, hw[2 * j], lw[2 * j]);
+            split_bf16x2(o2, o3, hw[2 * j + 1], lw[2 * j + 1]);
+          }
+          if (ok && !(p.dbg & 512)) {
+            uint8_t* dh = p.out_hi + (pix * BN + c * 32) * 2;
+            uint8_t* dl = p.out_lo + (pix * BN + c * 32) * 2;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              stg256(dh + 32 * j, hw + 8 * j);
+              stg256(dl + 32 * j, lw + 8 * j);
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int acc = 0; acc < NACC; ++acc) {
         int64_t obase;          // element index of this row's first output channel
@@ -623,9 +664,6 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
               o[2 * j] = (ok && a0 != 0u && a0 < 0x8000u) ? __uint_as_float(v[2 * j]) : 0.f;
               o[2 * j + 1] = (ok && a1 != 0u && a1 < 0x8000u) ? __uint_as_float(v[2 * j + 1]) : 0.f;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = fmaxf(fmaf(__uint_as_float(v[j]), p.in_scale, breg[c0 + j]), 0.f);
           }
           if (ok && !(p.dbg & 512)) {
             uint32_t hw[16], lw[16];
