@@ -397,7 +397,7 @@ int paacb_policy_forward_at(const paacb_ctx* ctx, const float* d_params, const u
   PAACB_CHECK_ARG(batch >= 0 && batch * (int64_t)ctx->layer[0].OH * ctx->layer[0].OW < (1LL << 40), "batch out of range");
   PAACB_CHECK_ARG(ws_first >= 0 && ws_capacity >= 0 && ws_first + batch <= ws_capacity,
                   "samples [ws_first, ws_first + batch) must lie inside the workspace capacity");
-  // every per-sample tensor is a multiple of 64 elements, so any sample offset keeps the 16-byte alignment of the planes
+  // every per-sample tensor is a multiple of 32 elements (Nature: of 64), so any sample offset keeps the planes 16-byte aligned
   const WsSlice slice = {ws_capacity, ws_first};
   PAACB_CHECK_ARG(((uintptr_t)d_params & 15) == 0 && ((uintptr_t)d_states & 15) == 0 && ((uintptr_t)d_fwd_ws & 15) == 0,
                   "params / states / workspace must be 16-byte aligned");
