@@ -465,17 +465,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      constexpr int CW = BN < 32 ? BN : 32;     // columns per TMEM load (16 for the NIPS layers with 16 channels)
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += CW) {
         uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
+        if constexpr (CW == 16) {
+          uint32_t v16[16];
+          tmem_ld16(taddr, v16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[j + 16] = 0u; }
+        } else {
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+        }
         if (ok && !(p.dbg & 16)) {
           float* dst = p.y + out_base + c0;
           if constexpr (MODE == TC_DGRAD) {
             const float* xa = (p.xact != nullptr) ? p.xact + out_base + c0 : nullptr;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < CW; j += 4) {
               float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                      __uint_as_float(v[j + 3]));
               if (xa != nullptr) {
@@ -488,7 +497,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
           } else {
             const float* bp = p.bias + nt * BN + c0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < CW; j += 4) {
               float4 o;
               o.x = fmaf(__uint_as_float(v[j + 0]), p.in_scale, __ldg(bp + j + 0));
               o.y = fmaf(__uint_as_float(v[j + 1]), p.in_scale, __ldg(bp + j + 1));
@@ -548,7 +557,7 @@ static int launch_tc_inst(const paacb_ctx* ctx, const TcParams& p, int slot, int
   return split3 ? launch_tc_inst2<BN, MODE, true, 1>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, 1>(ctx, p, slot, st);
 }
 
-static int pick_bn(int n) { return (n % 128 == 0) ? 128 : ((n % 64 == 0) ? 64 : ((n % 32 == 0) ? 32 : 0)); }
+static int pick_bn(int n) { return (n % 128 == 0) ? 128 : ((n % 64 == 0) ? 64 : ((n % 32 == 0) ? 32 : ((n % 16 == 0) ? 16 : 0))); }
 
 int launch_pack_weights(const paacb_ctx* ctx, const LayerGeom& g, const float* w, cudaStream_t st) {
   if (ctx->wpack_hi == nullptr) return PAACB_EUNSUPPORTED;
@@ -604,10 +613,12 @@ int launch_conv_fwd_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, 
   p.dbg = ctx->dbg;
   const int slot = K_FWD0 + g.index;
   if (g.in_u8) {
+    if (bn == 16) return launch_tc_inst<16, TC_FWD_U8>(ctx, p, slot, split3, st);
     if (bn == 32) return launch_tc_inst<32, TC_FWD_U8>(ctx, p, slot, split3, st);
     if (bn == 64) return launch_tc_inst<64, TC_FWD_U8>(ctx, p, slot, split3, st);
     return PAACB_EUNSUPPORTED;
   }
+  if (bn == 16) return launch_tc_inst<16, TC_FWD_F32>(ctx, p, slot, split3, st);
   if (bn == 32) return launch_tc_inst<32, TC_FWD_F32>(ctx, p, slot, split3, st);
   if (bn == 64) return launch_tc_inst<64, TC_FWD_F32>(ctx, p, slot, split3, st);
   return launch_tc_inst<128, TC_FWD_F32>(ctx, p, slot, split3, st);
@@ -643,6 +654,7 @@ int launch_conv_dgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const float* 
   p.in_scale = 1.0f;
   p.dbg = ctx->dbg;
   const int slot = K_DGRAD0 + g.index;
+  if (bn == 16) return launch_tc_inst<16, TC_DGRAD>(ctx, p, slot, split3, st);
   if (bn == 32) return launch_tc_inst<32, TC_DGRAD>(ctx, p, slot, split3, st);
   if (bn == 64) return launch_tc_inst<64, TC_DGRAD>(ctx, p, slot, split3, st);
   return launch_tc_inst<128, TC_DGRAD>(ctx, p, slot, split3, st);

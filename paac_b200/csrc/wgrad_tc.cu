@@ -355,6 +355,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (BN == 16) {                // the NIPS first layer: 16 output channels
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        if (k < g.K && c.kbs > 0) {
+          float* dst = p.dw + (int64_t)k * g.N + c.nt * BN;
+#pragma unroll
+          for (int jx = 0; jx < 16; ++jx) atomicAdd(dst + jx, __uint_as_float(v[jx]) * p.w_scale);
+        }
+      } else {
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -365,6 +375,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
 #pragma unroll
           for (int jx = 0; jx < 32; ++jx) atomicAdd(dst + jx, __uint_as_float(v[jx]) * p.w_scale);
         }
+      }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -401,7 +412,7 @@ static int launch_wg_inst(const paacb_ctx* ctx, const WgParams& p, cudaStream_t 
 
 int launch_conv_wgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* dz, float* dw, float* db,
                          int64_t batch, int split3, cudaStream_t st) {
-  const int bn = (g.N % 128 == 0) ? 128 : ((g.N % 64 == 0) ? 64 : ((g.N % 32 == 0) ? 32 : 0));
+  const int bn = (g.N % 128 == 0) ? 128 : ((g.N % 64 == 0) ? 64 : ((g.N % 32 == 0) ? 32 : ((g.N % 16 == 0) ? 16 : 0)));
   if (bn == 0 || (g.S * g.C) % 32 != 0 || g.K % 32 != 0) return PAACB_EUNSUPPORTED;
   WgParams p;
   memset(&p, 0, sizeof(p));
@@ -421,10 +432,12 @@ int launch_conv_wgrad_tc(const paacb_ctx* ctx, const LayerGeom& g, const void* x
 #define WG(BN_, U8_) \
   (split3 ? launch_wg_inst<BN_, U8_, true>(ctx, p, st) : launch_wg_inst<BN_, U8_, false>(ctx, p, st))
   if (g.in_u8) {
+    if (bn == 16) return WG(16, true);
     if (bn == 32) return WG(32, true);
     if (bn == 64) return WG(64, true);
     return PAACB_EUNSUPPORTED;
   }
+  if (bn == 16) return WG(16, false);
   if (bn == 32) return WG(32, false);
   if (bn == 64) return WG(64, false);
   return WG(128, false);
