@@ -82,7 +82,8 @@ struct Wg2Cfg {
   static constexpr int DATA_BYTES = A_BYTES + W::STAGES * B_STAGE;
   static constexpr bool U8_A = (L == 0);                 // conv1: eight converter warps produce the X operand from the uint8 states
   static constexpr int TX_BYTES = (U8_A ? 0 : W::A_PARTS * W::A_PIECES * W::A_BOX) + 2 * W::B_BOX;
-  static constexpr int THREADS = 192 + (U8_A ? 256 : 0);
+  static constexpr int CONV_THREADS = 288;               // conv1: nine converter warps, one 32-byte unit of each plane per thread (273 units)
+  static constexpr int THREADS = 192 + (U8_A ? CONV_THREADS : 0);
   static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + (2 * W::STAGES + 1) * 8 + 16;
   // dZ_hi and dZ_lo slots lie back to back: one MMA of N = 2 * BN evaluates X_hi^T * [dZ_hi | dZ_lo] (X is read from shared
   // memory once), a second of N = BN adds X_lo^T * dZ_hi.  conv3 has 5 k-tiles: 5 * 128 columns do not fit in TMEM, it
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
   for (int i = tid * 16; i < Cfg::DATA_BYTES; i += Cfg::THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], Cfg::U8_A ? 257 : 1);      // TMA producer (+ 256 converter threads)
+      mbar_init(&full_bar[s], Cfg::U8_A ? 1 + Cfg::CONV_THREADS : 1);      // TMA producer (+ the converter threads)
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(done_bar, 1);
@@ -233,15 +234,17 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
   } else if (Cfg::U8_A && warp >= 6) {
     // =========================== uint8 -> bf16 converters (conv1) ===========================
     // A stage needs 13 plane rows of each of the 4 row-parity planes: 273 units (4 pixels x 4 channels) per plane.
-    // 256 threads: thread c converts units c and c + 256 of every plane, loaded one stage ahead into registers.
+    // 288 threads: thread c converts unit c of every plane (with 256 threads the first warp carried a second unit and was the
+    // critical path of every stage), loaded one stage ahead into registers.
     if constexpr (Cfg::U8_A) {
       constexpr int UNITS = 13 * 21;
+      constexpr int UPT = (UNITS + Cfg::CONV_THREADS - 1) / Cfg::CONV_THREADS;      // units per thread and plane
       const int ct = tid - 192;
-      auto load_stage = [&](int s, uint4 (&b)[4][2]) {
+      auto load_stage = [&](int s, uint4 (&b)[4][UPT]) {
         const int row0 = (s >> 1) * 21 + 10 * (s & 1);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int w = ct + i * 256;
+        for (int i = 0; i < UPT; ++i) {
+          const int w = ct + i * Cfg::CONV_THREADS;
           const int R = row0 + w / 21, u = w % 21;
           const int n = R / 21, q = R - n * 21;
           const bool ok = (w < UNITS) && (s < s_end) && (n < p.batch) && !(p.dbg & 64);
@@ -254,14 +257,14 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
       };
       int stage = 0;
       uint32_t phase = 0;
-      auto store_stage = [&](const uint4 (&b)[4][2]) {
+      auto store_stage = [&](const uint4 (&b)[4][UPT]) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         const uint32_t base = smem_u32(a_sm + stage * Cfg::A_STAGE);
 #pragma unroll
         for (int part = 0; part < 4; ++part) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int w = ct + i * 256;
+          for (int i = 0; i < UPT; ++i) {
+            const int w = ct + i * Cfg::CONV_THREADS;
             if (w < UNITS && !(p.dbg & 64)) {
               const uint32_t wd[4] = {b[part][i].x, b[part][i].y, b[part][i].z, b[part][i].w};
               uint32_t o[8];
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
         mbar_arrive(&full_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       };
-      uint4 bufa[4][2], bufb[4][2];
+      uint4 bufa[4][UPT], bufb[4][UPT];
       int s = s_begin;
       load_stage(s, bufa);
       load_stage(s + 1, bufb);
