@@ -80,7 +80,7 @@ struct Wg2Cfg {
   static constexpr int B_STAGE = 2 * W::B_SLOT;
   static constexpr int A_BYTES = W::STAGES * A_STAGE;
   static constexpr int DATA_BYTES = A_BYTES + W::STAGES * B_STAGE;
-  static constexpr bool U8_A = (L == 0);                 // conv1: eight converter warps produce the X operand from the uint8 states
+  static constexpr bool U8_A = (L == 0);                 // conv1: nine converter warps produce the X operand from the uint8 states
   static constexpr int TX_BYTES = (U8_A ? 0 : W::A_PARTS * W::A_PIECES * W::A_BOX) + 2 * W::B_BOX;
   static constexpr int CONV_THREADS = 288;               // conv1: nine converter warps, one 32-byte unit of each plane per thread (273 units)
   static constexpr int THREADS = 192 + (U8_A ? CONV_THREADS : 0);
