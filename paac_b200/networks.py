@@ -125,7 +125,8 @@ class Network(object):
         _lib.check(self._lib.paacb_params_changed(self.ctx), 'paacb_params_changed')
 
     def variable(self, name):
-        """View of one variable inside the flat buffer (reference layout: HWIO / [in, out])."""
+        """View of one variable inside the flat buffer (reference layout: HWIO / [in, out]).
+        After WRITING through such a view call ``params_changed()``: the library caches operand images of the weights."""
         for n, off, shape, _ in self.tensors:
             if n == name:
                 return self.params[off:off + int(np.prod(shape))].view(*shape)
