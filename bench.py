@@ -47,7 +47,8 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='environments per GPU')
     ap.add_argument('--arch', default='NATURE', choices=['NATURE', 'NIPS'])
-    ap.add_argument('--math', default=os.environ.get('PAACB_BENCH_MATH', 'bf16x3'), choices=['fp32', 'tf32x3', 'tf32', 'bf16x3'])
+    ap.add_argument('--math', default=os.environ.get('PAACB_BENCH_MATH', 'auto'), choices=['auto', 'fp32', 'tf32x3', 'tf32', 'bf16x3'],
+                    help="'auto': bf16x3 for Nature (the benchmark configuration), tf32x3 for NIPS")
     ap.add_argument('--frame_pool', type=int, default=8, help='device frame buffers rotated between env steps')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
@@ -55,7 +56,10 @@ def parse():
     ap.add_argument('--no_overlap_allreduce', action='store_true', help='N > 1: one all-reduce after the whole backward')
     ap.add_argument('--e2e_slices', type=int, default=2, help='environment slices pipelined in the end-to-end arm')
     ap.add_argument('--ref_envs', type=int, default=64, help='--impl reference: envs per step (bounded sample)')
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.math == 'auto':
+        args.math = 'bf16x3' if args.arch == 'NATURE' else 'tf32x3'
+    return args
 
 
 def workload_config(args, n_gpus):
