@@ -290,6 +290,13 @@ int paacb_set_math(paacb_ctx* ctx, int math_mode) {
     const cudaError_t e2 = cudaMalloc(&ctx->wpack_lo, bytes);
     const cudaError_t e3 = cudaMalloc(&ctx->wpack_d_hi, bytes);
     const cudaError_t e4 = cudaMalloc(&ctx->wpack_d_lo, bytes);
+    if (ctx->wq_i8 == nullptr && ctx->layer[0].N == 16) {      // NIPS: the first layer runs on the int8 pipe (tc2_conv1.cu)
+      if (cudaMalloc(&ctx->wq_i8, (size_t)3 * ctx->layer[0].N * ctx->layer[0].K) != cudaSuccess ||
+          cudaMalloc(&ctx->wq_scale, (size_t)ctx->layer[0].N * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->wq_i8 = nullptr;                                    // falls back to the tf32 kernel
+      }
+    }
     cudaSetDevice(cur);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
       cudaGetLastError();
@@ -375,6 +382,11 @@ static int run_layer_fwd(const paacb_ctx* ctx, int l, const float* d_params, con
   const void* x = (l == 0) ? (const void*)d_states
                            : (const void*)(ws + g.in_act_off * slice.cap + slice.first * (int64_t)g.H * g.W * g.C);
   float* y = ws + g.out_act_off * slice.cap + slice.first * (int64_t)g.OH * g.OW * g.N;
+  if (ctx->math != PAACB_MATH_FP32 && l == 0 && g.N == 16 && ctx->wq_i8 != nullptr && !(ctx->dbg & (1 << 17))) {
+    int rc = launch_pack_conv1_i8(ctx, d_params, st);           // NIPS conv1: uint8 pixels x int8 weight digits (tc2_conv1.cu)
+    if (rc == PAACB_OK) rc = launch_conv1_fwd_i8_f32(ctx, d_params, d_states, y, batch, st);
+    if (rc != PAACB_EUNSUPPORTED) return rc;
+  }
   if (ctx->math != PAACB_MATH_FP32) {
     const int rc = launch_conv_fwd_tc(ctx, g, x, d_params + g.w_off, d_params + g.b_off, y, batch,
                                       ctx->math == PAACB_MATH_TF32X3, st);

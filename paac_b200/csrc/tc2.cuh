@@ -50,6 +50,8 @@ int launch_conv_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, c
 int launch_pack_conv1_i8(const paacb_ctx* ctx, const float* params, cudaStream_t st);              // int8 digit image of conv1
 int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
                         const WsSlice& slice, cudaStream_t st);
+int launch_conv1_fwd_i8_f32(const paacb_ctx* ctx, const float* params, const uint8_t* states, float* y, int64_t batch,
+                            cudaStream_t st);                                                  // NIPS conv1 in the tf32 pipeline
 int launch_fc_fwd_bf16(const paacb_ctx* ctx, int layer, const float* params, void* fwd_ws, int64_t batch, const WsSlice& slice,
                        cudaStream_t st);
 int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int layer, const void* fwd_ws, void* bwd_ws, float* grads, int64_t batch,

@@ -20,8 +20,16 @@
 
 namespace paacb {
 
-constexpr int kC1_N = 32;            // output channels
-constexpr int kC1_ND = 3 * kC1_N;    // MMA N: three digit images
+// NC = output channels: 32 (Nature; bf16-split planes out) or 16 (NIPS; fp32 out, the tf32 pipeline's activation format)
+template <int NC>
+struct C1 {
+  static constexpr int ND = 3 * NC;                          // MMA N: three digit images
+  static constexpr int WBYTES = 2 * ND * 128;                // K = 256 bytes per row: two 128-byte K-blocks of ND rows
+  static constexpr int EPI_WARPS = 8 * (NC / 16);            // 2 accumulator buffers x (NC / 16) channel groups x 4 TMEM lane quarters
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static_assert(NC == 16 || NC == 32, "conv1 has 16 or 32 output channels");
+  static_assert(WBYTES % 1024 == 0, "1024-byte aligned regions");
+};
 constexpr int kC1_WU = 21, kC1_HQ = 21, kC1_OH = 20, kC1_OW = 20;
 // A tile is SIX plane rows (6 x 21 = 126 of the 128 MMA rows): a thread's position inside its plane row is a kernel constant.
 // Epilogue history, all measured (profiles/r01_*): (1) 16-byte stores from registers at a 64-byte lane stride: 16 L1
@@ -35,12 +43,9 @@ constexpr int kC1_PLANE = 16 * kC1_WU * kC1_ROWS;      // 2,352 bytes per parity
 constexpr int kC1_BOX = 4 * kC1_PLANE;                 // one TMA box per tile: [4 parities][7 plane rows][336 bytes]
 constexpr int kC1_SLOT = 10240;                        // >= 3 planes + (127 + 21 + 2) units: the two spare MMA rows read stale bytes
 constexpr int kC1_NSLOTS = 6;                            // six tiles of patches in flight
-constexpr int kC1_WBYTES = 2 * kC1_ND * 128;             // K = 256 bytes per row: two 128-byte K-blocks of 96 rows
-constexpr int kC1_SMEM = kC1_NSLOTS * kC1_SLOT + kC1_WBYTES + 256 + 1024 + (2 * kC1_NSLOTS + 5) * 8 + 16;
-constexpr int kC1_EPI_WARPS = 16;                       // 2 accumulator buffers x 2 channel halves x 4 TMEM lane quarters
-constexpr int kC1_THREADS = 64 + 32 * kC1_EPI_WARPS;
-constexpr int kC1_TMEM = 256;                            // two accumulator buffers of 96 columns at 0 and 128
-static_assert((kC1_NSLOTS * kC1_SLOT) % 1024 == 0 && kC1_WBYTES % 1024 == 0, "1024-byte aligned regions");
+constexpr int kC1_SMEM_FIXED = kC1_NSLOTS * kC1_SLOT + 256 + 1024 + (2 * kC1_NSLOTS + 5) * 8 + 16;   // + C1<NC>::WBYTES
+constexpr int kC1_TMEM = 256;                            // two accumulator buffers of <= 96 columns at 0 and 128
+static_assert((kC1_NSLOTS * kC1_SLOT) % 1024 == 0, "1024-byte aligned regions");
 static_assert(3 * kC1_PLANE + (127 + kC1_WU + 2) * 16 <= kC1_SLOT, "slot holds every byte an MMA row can address");
 
 struct Conv1Params {
@@ -49,18 +54,19 @@ struct Conv1Params {
   int num_tiles;
   int batch;
   const float* bias;
-  const float* wscale;     // [32]: s_c / (63 * 255)
+  const float* wscale;     // [NC]: s_c / (63 * 255)
+  float* out_f32;          // fp32 output [b, 20, 20, NC] (F32OUT variants) instead of the planes
   int dbg;                 // PAACB_DBG ablations (timing experiments only): 1 no stores, 2 no epilogue arithmetic, 4 no MMAs, 8 no A loads
   uint8_t* out_hi;
   uint8_t* out_lo;
 };
 
 // weights -> three int8 digit images + per-channel scale.  One block per output channel, one thread per k.
-__global__ void __launch_bounds__(256) pack_conv1_i8_kernel(const float* __restrict__ w, int8_t* __restrict__ wq,
+__global__ void __launch_bounds__(256) pack_conv1_i8_kernel(const float* __restrict__ w, int nc, int8_t* __restrict__ wq,
                                                             float* __restrict__ wscale) {
   __shared__ float red[8];
   const int c = blockIdx.x, k = threadIdx.x;
-  const float v = __ldg(w + k * kC1_N + c);
+  const float v = __ldg(w + k * nc + c);
   float m = fabsf(v);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -75,17 +81,17 @@ __global__ void __launch_bounds__(256) pack_conv1_i8_kernel(const float* __restr
   const double r1 = (x - d0) * 64.0;
   const double d1 = rint(r1);
   const double d2 = rint((r1 - d1) * 64.0);
-  wq[(0 * kC1_N + c) * 256 + k] = (int8_t)d0;
-  wq[(1 * kC1_N + c) * 256 + k] = (int8_t)d1;
-  wq[(2 * kC1_N + c) * 256 + k] = (int8_t)d2;
+  wq[(0 * nc + c) * 256 + k] = (int8_t)d0;
+  wq[(1 * nc + c) * 256 + k] = (int8_t)d1;
+  wq[(2 * nc + c) * 256 + k] = (int8_t)d2;
   if (k == 0) wscale[c] = s / (63.0f * 255.0f);
 }
 
 int launch_pack_conv1_i8(const paacb_ctx* ctx, const float* params, cudaStream_t st) {
   const LayerGeom& g = ctx->layer[0];
-  if (g.K != 256 || g.N != kC1_N) return PAACB_EUNSUPPORTED;
+  if (g.K != 256 || (g.N != 16 && g.N != 32) || ctx->wq_i8 == nullptr) return PAACB_EUNSUPPORTED;
   PAACB_LAUNCH_BEGIN(ctx, K_PACK, st);
-  pack_conv1_i8_kernel<<<kC1_N, 256, 0, st>>>(params + g.w_off, ctx->wq_i8, ctx->wq_scale);
+  pack_conv1_i8_kernel<<<g.N, 256, 0, st>>>(params + g.w_off, g.N, ctx->wq_i8, ctx->wq_scale);
   PAACB_LAUNCH_END(ctx, K_PACK, st);
   return PAACB_OK;
 }
@@ -104,7 +110,9 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int n) {
   return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_constant__ Conv1Params p) {
+template <int NC, bool F32OUT>
+__global__ void __launch_bounds__(C1<NC>::THREADS, 1) conv1_i8_kernel(const __grid_constant__ Conv1Params p) {
+  constexpr int kC1_ND = C1<NC>::ND, kC1_WBYTES = C1<NC>::WBYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
@@ -129,13 +137,13 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
     mbar_init(w_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 256);
+      mbar_init(&tempty_bar[s], 128 * (NC / 16));
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmW);
   }
-  if (tid >= 64 && tid < 64 + kC1_N) s_sb[tid - 64] = make_float2(__ldg(p.wscale + tid - 64), __ldg(p.bias + tid - 64));
+  if (tid >= 64 && tid < 64 + NC) s_sb[tid - 64] = make_float2(__ldg(p.wscale + tid - 64), __ldg(p.bias + tid - 64));
   if (warp == 1) tmem_alloc(tmem_slot, kC1_TMEM);
   tc_fence_before();
   __syncthreads();
@@ -211,12 +219,13 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
       uint32_t v0[16], v1[16], v2[16];
       const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(grp * 128 + half * 16);
       tmem_ld16(tcol, v0);
-      tmem_ld16(tcol + 32u, v1);
-      tmem_ld16(tcol + 64u, v2);
+      tmem_ld16(tcol + (uint32_t)NC, v1);
+      tmem_ld16(tcol + (uint32_t)(2 * NC), v2);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&tempty_bar[grp]);           // the accumulator is in registers: release the buffer before the arithmetic
       uint32_t hw[8], lw[8];
+      float of[F32OUT ? 16 : 1];
       if (p.dbg & 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { hw[j] = v0[2 * j] ^ v1[2 * j + 1]; lw[j] = v2[2 * j] ^ v0[2 * j + 1]; }
@@ -234,13 +243,19 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
           const float t = fmaf(f2, 1.0f / 4096.0f, fmaf(f1, 1.0f / 64.0f, f0));
           o[e] = fmaxf(fmaf(t, e ? sb.z : sb.x, e ? sb.w : sb.y), 0.f);
         }
-        split_bf16x2(o[0], o[1], hw[j], lw[j]);
+        if constexpr (F32OUT) { of[2 * j] = o[0]; of[2 * j + 1] = o[1]; }
+        else split_bf16x2(o[0], o[1], hw[j], lw[j]);
       }
       if (ok && !(p.dbg & 1)) {                 // 16 channels = one full 32-byte sector per plane
         const uint32_t oh = g - n * (uint32_t)kC1_HQ;
-        const int64_t ob = ((((int64_t)n * kC1_OH + oh) * kC1_OW + ju) * kC1_N + half * 16) * 2;
-        stg256(p.out_hi + ob, hw);
-        stg256(p.out_lo + ob, lw);
+        const int64_t oe = (((int64_t)n * kC1_OH + oh) * kC1_OW + ju) * NC + half * 16;      // element index
+        if constexpr (F32OUT) {
+          stg256(p.out_f32 + oe, reinterpret_cast<const uint32_t*>(of));
+          stg256(p.out_f32 + oe + 8, reinterpret_cast<const uint32_t*>(of) + 8);
+        } else {
+          stg256(p.out_hi + oe * 2, hw);
+          stg256(p.out_lo + oe * 2, lw);
+        }
       }
     }
   }
@@ -253,23 +268,25 @@ __global__ void __launch_bounds__(kC1_THREADS, 1) conv1_i8_kernel(const __grid_c
   }
 }
 
-int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
-                        const WsSlice& slice, cudaStream_t st) {
+template <int NC, bool F32OUT>
+static int launch_conv1_inst(const paacb_ctx* ctx, const float* params, const uint8_t* states, uint8_t* out_hi, uint8_t* out_lo,
+                             float* out_f32, int64_t batch, cudaStream_t st) {
   const LayerGeom& g = ctx->layer[0];
-  if (g.C != 4 || g.stride != 4 || g.R != 8 || g.S != 8 || g.N != kC1_N || g.H != 84 || g.W != 84 || g.OH != kC1_OH)
+  if (g.C != 4 || g.stride != 4 || g.R != 8 || g.S != 8 || g.N != NC || g.H != 84 || g.W != 84 || g.OH != kC1_OH)
     return PAACB_EUNSUPPORTED;
   const int64_t plane_rows = batch * kC1_HQ;
   if (plane_rows * kC1_WU >= (1LL << 31) - 256) return PAACB_EUNSUPPORTED;
+  constexpr int SMEM = kC1_SMEM_FIXED + C1<NC>::WBYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv1_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv1_i8_kernel<NC, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       cudaGetLastError();
-      set_error("conv1_i8: cannot set %d bytes of dynamic shared memory", kC1_SMEM);
+      set_error("conv1_i8: cannot set %d bytes of dynamic shared memory", SMEM);
       return PAACB_ECUDA;
     }
     // one persistent CTA per SM: ask for the largest shared-memory carve-out whatever the kernel's own request (measured
     // on conv1 forward: the same code ran 10 % slower when its request dropped from 160 KB to 86 KB)
-    cudaFuncSetAttribute(conv1_i8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(conv1_i8_kernel<NC, F32OUT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
     attr_set = true;
   }
@@ -282,9 +299,9 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
   const uint64_t astr[2] = {4u * 336u, 336u};
   const uint32_t abox[3] = {84u, (uint32_t)kC1_ROWS, 4u};
   int rc = encode_tmap(&p.tmA, states, 4, 3, adims, astr, abox, 0);
-  const uint64_t wdims[2] = {256u, (uint64_t)kC1_ND};
+  const uint64_t wdims[2] = {256u, (uint64_t)C1<NC>::ND};
   const uint64_t wstr[1] = {256u};
-  const uint32_t wbox[2] = {128u, (uint32_t)kC1_ND};
+  const uint32_t wbox[2] = {128u, (uint32_t)C1<NC>::ND};
   if (rc == PAACB_OK) rc = encode_tmap(&p.tmW, ctx->wq_i8, 1, 2, wdims, wstr, wbox, 128);
   if (rc != PAACB_OK) return rc;
   p.num_tiles = (int)((plane_rows + kC1_TROWS - 1) / kC1_TROWS);
@@ -292,14 +309,30 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
   p.bias = params + g.b_off;
   p.wscale = ctx->wq_scale;
   p.dbg = ctx->dbg;
-  const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
-  p.out_hi = out.hi;
-  p.out_lo = out.lo;
+  p.out_hi = out_hi;
+  p.out_lo = out_lo;
+  p.out_f32 = out_f32;
   const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, K_FWD0, st);
-  conv1_i8_kernel<<<grid, kC1_THREADS, kC1_SMEM, st>>>(p);
+  conv1_i8_kernel<NC, F32OUT><<<grid, C1<NC>::THREADS, SMEM, st>>>(p);
   PAACB_LAUNCH_END(ctx, K_FWD0, st);
   return PAACB_OK;
+}
+
+// Nature, bf16-split pipeline: planes out
+int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
+                        const WsSlice& slice, cudaStream_t st) {
+  const LayerGeom& g = ctx->layer[0];
+  const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
+  return launch_conv1_inst<32, false>(ctx, params, states, out.hi, out.lo, nullptr, batch, st);
+}
+
+// NIPS (16 output channels), tf32 pipeline: fp32 activations out.  The int8 digit scheme is exact to 2^-19 of the largest
+// weight of a channel, tighter than the tf32 split of the layers that follow.
+int launch_conv1_fwd_i8_f32(const paacb_ctx* ctx, const float* params, const uint8_t* states, float* y, int64_t batch,
+                            cudaStream_t st) {
+  if (ctx->layer[0].N != 16 || ctx->wq_i8 == nullptr) return PAACB_EUNSUPPORTED;
+  return launch_conv1_inst<16, true>(ctx, params, states, nullptr, nullptr, y, batch, st);
 }
 
 }  // namespace paacb
