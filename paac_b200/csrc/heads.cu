@@ -88,7 +88,7 @@ heads_fwd_kernel(const float* __restrict__ h, const uint16_t* __restrict__ h_hi,
 }
 
 constexpr int kHbThreads = 256;
-constexpr int kHbChunk = 64;     // samples per CTA
+constexpr int kHbChunk = 128;    // samples per CTA
 
 template <int FPT>   // features per thread: F = FPT * 256
 __global__ void __launch_bounds__(kHbThreads)
