@@ -236,9 +236,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
         if (n0 >= p.N) continue;                 // warp-uniform: N is a multiple of 32
         if constexpr (MODE == ST_WGRAD) {
           if (ok) {
-            float* dst = p.dw + (int64_t)m * p.ldo + n0;
+            float4* dst = reinterpret_cast<float4*>(p.dw + (int64_t)m * p.ldo + n0);      // RED.ADD.F32x4
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 8; ++j)
+              atomicAdd(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                             __uint_as_float(v[4 * j + 3])));
           }
         } else {
           const int64_t obase = (int64_t)m * p.ldo + n0;

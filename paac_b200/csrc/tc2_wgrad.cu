@@ -328,9 +328,12 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
           tmem_ld_wait();
         }
         if (k >= 0) {
-          float* dst = p.dw + (int64_t)k * W::BN + c0;
+          // 16-byte vector reductions (RED.ADD.F32x4): a quarter of the requests the 148 CTAs send to the same dW addresses
+          float4* dst = reinterpret_cast<float4*>(p.dw + (int64_t)k * W::BN + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]) * p.w_scale);
+          for (int j = 0; j < 8; ++j)
+            atomicAdd(dst + j, make_float4(__uint_as_float(v[4 * j]) * p.w_scale, __uint_as_float(v[4 * j + 1]) * p.w_scale,
+                                           __uint_as_float(v[4 * j + 2]) * p.w_scale, __uint_as_float(v[4 * j + 3]) * p.w_scale));
         }
       }
     }
