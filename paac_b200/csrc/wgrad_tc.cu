@@ -360,9 +360,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
         tmem_ld16(taddr, v);
         tmem_ld_wait();
         if (k < g.K && c.kbs > 0) {
-          float* dst = p.dw + (int64_t)k * g.N + c.nt * BN;
+          float4* dst = reinterpret_cast<float4*>(p.dw + (int64_t)k * g.N + c.nt * BN);      // RED.ADD.F32x4
 #pragma unroll
-          for (int jx = 0; jx < 16; ++jx) atomicAdd(dst + jx, __uint_as_float(v[jx]) * p.w_scale);
+          for (int jx = 0; jx < 4; ++jx)
+            atomicAdd(dst + jx, make_float4(__uint_as_float(v[4 * jx]) * p.w_scale, __uint_as_float(v[4 * jx + 1]) * p.w_scale,
+                                            __uint_as_float(v[4 * jx + 2]) * p.w_scale, __uint_as_float(v[4 * jx + 3]) * p.w_scale));
         }
       } else {
 #pragma unroll
@@ -371,9 +373,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
         tmem_ld32(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
         if (k < g.K && c.kbs > 0) {
-          float* dst = p.dw + (int64_t)k * g.N + c.nt * BN + c0;
+          float4* dst = reinterpret_cast<float4*>(p.dw + (int64_t)k * g.N + c.nt * BN + c0);  // RED.ADD.F32x4
 #pragma unroll
-          for (int jx = 0; jx < 32; ++jx) atomicAdd(dst + jx, __uint_as_float(v[jx]) * p.w_scale);
+          for (int jx = 0; jx < 8; ++jx)
+            atomicAdd(dst + jx, make_float4(__uint_as_float(v[4 * jx]) * p.w_scale, __uint_as_float(v[4 * jx + 1]) * p.w_scale,
+                                            __uint_as_float(v[4 * jx + 2]) * p.w_scale, __uint_as_float(v[4 * jx + 3]) * p.w_scale));
         }
       }
       }
