@@ -84,14 +84,20 @@ def run_reference(args):
         return
     from oracle import cpu_baseline
     cores = os.cpu_count() or 1
+    warm = max(args.warmup, 1)
     sps, ms, done, cores = cpu_baseline.time_cycles(args.arch, args.ref_envs, T_MAX, NUM_ACTIONS, steps=args.steps,
-                                                    warmup=min(args.warmup, 1), cores=cores, max_seconds=240)
-    sample = ('restated reference CPU path (oracle port, not TF1): %d timed update cycles of %d envs x t_max %d '
-              '(a bounded sample of the %d-env workload), torch-CPU fp32 + NumPy preprocessing, %d threads'
-              % (done, args.ref_envs, T_MAX, args.envs, cores))
+                                                    warmup=warm, cores=cores, max_seconds=240)
+    sample = ('restated reference CPU path (oracle port, not TF1): %d timed update cycles (after %d warm-up cycles) of %d envs x '
+              't_max %d -- a bounded sample of the %d-env workload: the CPU rate per env-step does not depend on the env count '
+              'beyond this size -- torch-CPU fp32 + NumPy preprocessing, %d threads' % (done, warm, args.ref_envs, T_MAX, args.envs, cores))
+    cfg = workload_config(args, 1)
+    # what this arm really ran: the bounded sample, on the host cores of ONE process whatever --gpus says
+    cfg.update(envs_timed=args.ref_envs, env_steps_per_step=args.ref_envs * T_MAX,
+               workload=cfg['workload'] + ' [reference arm: %d-env bounded sample per step on %d host threads]' % (args.ref_envs, cores),
+               parallelism='host CPU only (rank 0); at --gpus N > 1 this is still ONE CPU run, not N')
     line = {'impl': 'reference', 'metric': METRIC, 'value': sps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done,
-            'warmup': min(args.warmup, 1), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, args.gpus),
+            'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
             'cpu_baseline': {'value': sps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': sps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -200,6 +206,14 @@ def load_peaks():
     return 6650.0, 1590.0, 1400.0, 'fallback'
 
 
+def load_umma_peaks():
+    """tools/probe/umma_peak on a B200 (profiles/r02_umma_peaks.json): what ONE CTA per SM issues per tcgen05.mma kind and N."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r02_umma_peaks.json')))['peaks']
+    except Exception:
+        return None
+
+
 def layer_macs(arch):
     """MACs per sample of each conv/fc layer: (name, macs, has_dgrad)."""
     if arch == 'NATURE':
@@ -289,12 +303,11 @@ def run_b200(args):
     u = torch.rand((T, N), device=dev, generator=gen)
     rewards = torch.where(u < 0.05, -1.0, torch.where(u > 0.95, 1.0, 0.0)).float()
     over = (torch.rand((T, N), device=dev, generator=gen) < 0.01).float()
-    eng.states[0].copy_(torch.randint(0, 256, eng.states[0].shape, dtype=torch.uint8, device=dev, generator=gen))
+    eng.state(0).copy_(torch.randint(0, 256, eng.state(0).shape, dtype=torch.uint8, device=dev, generator=gen))
     lr = 0.0224
     counter = [0]
 
     def step_device():
-        eng.draw_uniforms()
         for t in range(T):
             eng.act(t)
             buf = pool[counter[0] % len(pool)]
@@ -343,12 +356,20 @@ def run_b200(args):
 
     # ---- per-kernel roofline table (device time from CUDA events on the launching stream) ---------------
     hbm_peak, tc_burst, tc_sust, peak_kind = load_peaks()
-    # kernels are timed inside a long step -> sustained figure; kind::tf32 issues at half the bf16 rate
+    # conv / FC kernels are held against the TENSOR roofline -- algorithmic flops (2 x MACs of the layer, whatever
+    # the number of MMAs the split arithmetic issues) / device time / peak -- with the HBM fraction of the same kernel beside
+    # it.  Kernels are timed inside a long step -> the sustained figure of MEASURED_PEAKS.json (a cuBLAS bf16 GEMM).  The
+    # other tcgen05 kinds scale it by the ratio tools/probe/umma_peak measured on this pool (kind::tf32 / kind::i8 vs
+    # kind::f16 at N = 256); without that file: tf32 = 1/2, i8 = 2 (the architectural ratios).
     bf16_math = args.math == 'bf16x3'
-    tf32_peak = tc_sust if bf16_math else 0.5 * tc_sust
+    up = load_umma_peaks()
+    r_tf32 = (up['tf32']['N256'] / up['f16_bf16']['N256']) if up else 0.5
+    r_i8 = (up['i8']['N256'] / up['f16_bf16']['N256']) if up else 2.0
+    tf32_peak = tc_sust if bf16_math else r_tf32 * tc_sust
+    i8_peak = r_i8 * tc_sust
     peak_note = ('bf16_tflops_sustained (kind::f16 on bf16-split operands, 3 MMAs per algorithmic product: 1/3 is the ceiling)'
                  if bf16_math else
-                 '0.5 x bf16_tflops_sustained (kind::tf32 / fp32 contraction; tf32 issues at half the bf16 rate)')
+                 '%.2f x bf16_tflops_sustained (kind::tf32; ratio %s)' % (r_tf32, 'measured, profiles/r02_umma_peaks.json' if up else 'architectural'))
     B = N * T
     fwd_samples = (T * N + N + B) * args.steps       # acting + bootstrap + training forward
     kernels = []
@@ -360,15 +381,14 @@ def run_b200(args):
                 ach = 2.0 * macs * samples / (ms / 1e3) / 1e12
                 nbytes = float(layer_bytes(args.arch, kind, li, 2 if bf16_math else 4)) * samples
                 ach_b = nbytes / (ms / 1e3) / 1e9
-                row = {'name': key, 'ms': ms, 'launches': cnt, 'frac_tensor': ach / tf32_peak, 'tflops': ach,
-                       'frac_hbm': ach_b / hbm_peak, 'gbs': ach_b}
-                # the roofline that binds this kernel is the one it is closer to
-                if row['frac_hbm'] >= row['frac_tensor']:
-                    row.update(bound='hbm', achieved=ach_b, peak=hbm_peak, unit='GB/s', frac=row['frac_hbm'],
-                               algo_per_launch=nbytes / cnt)
-                else:
-                    row.update(bound='tensor', achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=row['frac_tensor'],
-                               algo_per_launch=2.0 * macs * samples / cnt)
+                # conv1 forward runs on the int8 pipe in every tensor-core mode (tc2_conv1.cu)
+                i8 = (li == 0 and kind == 'fwd' and args.math != 'fp32')
+                peak = i8_peak if i8 else tf32_peak
+                row = {'name': key, 'ms': ms, 'launches': cnt, 'frac_tensor': ach / peak, 'tflops': ach,
+                       'frac_hbm': ach_b / hbm_peak, 'gbs': ach_b, 'hbm_bytes_per_launch': nbytes / cnt,
+                       'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                       'algo_per_launch': 2.0 * macs * samples / cnt,
+                       'peak_note': ('%.2f x bf16_tflops_sustained (kind::i8)' % r_i8) if i8 else peak_note}
                 kernels.append(row)
     def hbm_row(key, bytes_total):
         if key in prof:
@@ -395,8 +415,13 @@ def run_b200(args):
     # under profiles/: traffic per launch = bytes per sample x the samples an average launch of that kernel processes
     dram_table, dram_src = {}, None
     try:
-        dj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_dram_bytes.json')))
-        dram_table, dram_src = dj['kernels'], dj['source']
+        for name in ('r02_ncu_dram_bytes.json', 'r01_ncu_dram_bytes.json'):
+            path = os.path.join(ROOT, 'profiles', name)
+            if os.path.exists(path):
+                dj = json.load(open(path))
+                if dj.get('arch', 'NATURE') == args.arch:
+                    dram_table, dram_src = dj['kernels'], dj['source']
+                    break
     except Exception:
         pass
     units_total = {'preprocess_u8': N * T * args.steps, 'heads_fwd': fwd_samples, 'heads_bwd': B * args.steps}
@@ -417,7 +442,10 @@ def run_b200(args):
                 'algo_per_launch': dom['algo_per_launch'],
                 'frac_tensor': dom.get('frac_tensor'), 'frac_hbm': dom.get('frac_hbm'),
                 'peak_source': ('%s: MEASURED_PEAKS.json ' % peak_kind) +
-                               (peak_note if dom['bound'] == 'tensor' else 'hbm_gbs (copy bandwidth)')}
+                               (dom.get('peak_note', peak_note) if dom['bound'] == 'tensor' else 'hbm_gbs (copy bandwidth)'),
+                'rule': 'SURVEY 8(d): conv / FC kernels against the tensor roofline in ALGORITHMIC flops (frac_hbm beside it), '
+                        'K1 / heads / returns / optimizer against HBM; dominant kernel = largest share of the profiled step',
+                'tcgen05_peaks_one_cta_per_sm': up}
     # nominal whole-step fraction: contract flops per env-step / tf32 peak
     flops_per_env_step = 71.96e6 if args.arch == 'NATURE' else 21.65e6
     step_frac = (value / world) * flops_per_env_step / 1e12 / tf32_peak
@@ -463,13 +491,13 @@ def run_b200(args):
             # Lock-step PAAC with the environment slices pipelined: slice c's actions go back to the host as soon as its
             # forward is done, its environments step (here: the pre-generated frames), and its frame ingestion (PCIe-bound)
             # overlaps the next slice's forward.  Every slice still sees act -> step -> observe in order: same results.
-            eng.draw_uniforms()
             for t in range(T):
                 for c, (lo, hi) in enumerate(bounds):
                     if t > 0:
                         stream.wait_event(ev_obs[c])                          # states[t] of this slice are complete
-                    eng.act(t, lo, hi)
-                    host_onehot[lo:hi].copy_(eng.onehot[lo:hi], non_blocking=True)      # the environments need the actions
+                    # the heads kernel writes the one-hot actions straight into pinned, mapped host memory (what the
+                    # runners' shared action array is): the environments need the actions, nothing else comes back
+                    eng.act(t, lo, hi, onehot_out=host_onehot[lo:hi])
                     ev_act[c].record(stream)
                 tf_stream.wait_event(ev_act[S - 1])                           # states[t] complete (every slice's act waited for it)
                 with torch.cuda.stream(tf_stream):

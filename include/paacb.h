@@ -9,7 +9,7 @@
  *   - extern "C", plain pointers and sizes, no C++/torch types.
  *   - every pointer named d_* is DEVICE memory (or pinned+mapped host memory for d_frames);
  *     the caller owns every buffer; the library allocates no device memory on the path (a context owns
- *     only its operand images of the weights, made by paacb_set_math, and a 256-byte barrier counter).
+ *     only its operand images of the weights, made by paacb_set_math, and a 256-byte grid-barrier block).
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), does no
  *     host synchronisation and no allocation, so a sequence of calls can be captured in a
  *     CUDA graph by the caller.
@@ -19,7 +19,11 @@
  *     conv weights HWIO, fc weights [in,out]; all parameters live in ONE flat fp32 buffer in
  *     TF variable-creation order (paacb_tensor_info gives name/offset/shape).
  *   - one context per GPU per process; a context is immutable after paacb_set_* calls and may
- *     be used from one host thread at a time.
+ *     be used from one host thread at a time.  Calls on DIFFERENT streams may overlap on the device only while the
+ *     parameters do not change (the acting and training forwards of one rollout): the cached operand images of the
+ *     weights are written by paacb_clip_rmsprop / the first forward after paacb_params_changed and read by every forward.
+ *   - the CURRENT CUDA device of the calling thread must be the context's device (PAACB_EINVAL otherwise): launches,
+ *     kernel attributes and tensor maps all belong to it.
  */
 #ifndef PAACB_H
 #define PAACB_H
@@ -31,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PAACB_VERSION 101
+#define PAACB_VERSION 102
 #define PAACB_MAX_ACTIONS 18          /* ALE full action set */
 #define PAACB_MAX_TENSORS 12
 #define PAACB_FRAME_H 210
@@ -92,6 +96,16 @@ int paacb_preprocess_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs
                         const uint8_t* d_reset, const uint8_t* d_prev, uint8_t* d_next,
                         int64_t n_envs, paacb_stream stream);
 
+/* K1 plus the per-step rollout bookkeeping of paac.py:119-123 in the same launch:
+ *   d_rewards_out[n] = d_rewards_in[n], d_over_out[n] = d_over_in[n]   (row t of the [T, N] rollout buffers; reward
+ *   clipping happens in K7).  The *_in arrays are the runners' shared reward / episode_over arrays (device memory, or
+ *   pinned+mapped host memory: runners.py:12-16 + paacb_host_register).  over_is_reset != 0: d_over_in[n] != 0 is also
+ *   environment n's reset flag (emulator_runner.py:26-27; needs pairs_per_env == 4), OR-ed with d_reset when given. */
+int paacb_observe_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_per_env, const uint8_t* d_reset,
+                     const uint8_t* d_prev, uint8_t* d_next, int64_t n_envs, const float* d_rewards_in,
+                     const float* d_over_in, float* d_rewards_out, float* d_over_out, int over_is_reset,
+                     paacb_stream stream);
+
 /* ---- K2-K6: forward (+ sampling).  Replaces session.run([output_layer_v, output_layer_pi])
  * and __sample_policy_action (paac.py:18-45).
  *   d_params   float [P]               d_states uint8 [b,84,84,4]
@@ -112,6 +126,18 @@ int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint
 int paacb_policy_forward_at(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
                             float* d_fwd_ws, int64_t ws_capacity, int64_t ws_first, float* d_pi, float* d_v,
                             const float* d_uniforms, int32_t* d_actions, float* d_onehot, paacb_stream stream);
+
+/* The same forward with the sampling uniforms drawn INSIDE the heads kernel (K6, replaces np.random.multinomial of
+ * paac.py:42-44 without a separate generator launch): Philox4x32-10, key = d_rng[0] (seed), counter =
+ * (first_sample + i, d_rng[1] + draw_index) for sample i of this call, u = (first output word >> 8) * 2^-24.
+ *   d_rng  uint64 [2] in device memory: {seed, draw base}.  paacb_rng_advance adds n to the base in stream order (once per
+ *          update, n = t_max), so a captured CUDA graph of the rollout replays with fresh uniforms.
+ *   first_sample  global index of this call's sample 0 (environment slices draw what the whole batch would). */
+int paacb_policy_forward_sample(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                                float* d_fwd_ws, int64_t ws_capacity, int64_t ws_first, float* d_pi, float* d_v,
+                                const uint64_t* d_rng, uint64_t draw_index, int64_t first_sample, int32_t* d_actions,
+                                float* d_onehot, paacb_stream stream);
+int paacb_rng_advance(const paacb_ctx* ctx, uint64_t* d_rng, uint64_t n, paacb_stream stream);
 
 /* ---- K7+K8: n-step returns (paac.py:119,140-149; reward clip actor_learner.py:95-101) fused with the
  * A2C loss and its gradient w.r.t. logits and value (policy_v_network.py:29-57 + TF autodiff).
@@ -155,6 +181,19 @@ int paacb_clip_rmsprop(const paacb_ctx* ctx, float* d_params, float* d_ms, float
                        float grad_scale, float lr, float rho, float eps, float momentum,
                        float clip_norm, int clip_type, float* d_norm_out, float* d_opt_ws,
                        paacb_stream stream);
+
+/* The same update with the learning rate read from DEVICE memory when the kernel runs (d_lr float [1]): a captured CUDA
+ * graph of the update is replayed while the host anneals the rate (actor_learner.py:119-123) by writing that word. */
+int paacb_clip_rmsprop_dlr(const paacb_ctx* ctx, float* d_params, float* d_ms, float* d_mom, const float* d_grads,
+                           float grad_scale, const float* d_lr, float rho, float eps, float momentum,
+                           float clip_norm, int clip_type, float* d_norm_out, float* d_opt_ws, paacb_stream stream);
+
+/* ---- opt-in summaries (actor_learner.py:85-87, logger_utils.py:23-33): one pass over g = d_grads * grad_scale.
+ *   d_out4 double [4] = {sum g, sum g^2, max g, min g}; mean / stddev / max / min of the RAW gradient follow on the host,
+ *   those of the CLIPPED gradient are the raw ones times clip * min(1/norm, 1/clip) (the clip is one non-negative scalar),
+ *   norm = sqrt(sum g^2).  d_opt_ws: the optimizer workspace (scratch).  Not on the hot path: call it when a record is due. */
+int paacb_grad_stats(const paacb_ctx* ctx, const float* d_grads, float grad_scale, float* d_opt_ws, double* d_out4,
+                     paacb_stream stream);
 
 /* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
 int64_t paacb_launch_count(const paacb_ctx* ctx);

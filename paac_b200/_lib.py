@@ -41,6 +41,11 @@ PROTOTYPES = {
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_backward': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_clip_rmsprop': (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
+    'paacb_observe_u8': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp]),
+    'paacb_policy_forward_sample': (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, C.c_uint64, _i64, _vp, _vp, _vp]),
+    'paacb_rng_advance': (_i, [_vp, _vp, C.c_uint64, _vp]),
+    'paacb_clip_rmsprop_dlr': (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
+    'paacb_grad_stats': (_i, [_vp, _vp, _f, _vp, _vp, _vp]),
     'paacb_launch_count': (_i64, [_vp]),
     'paacb_profile_enable': (_i, [_vp, _i]),
     'paacb_profile_reset': (_i, [_vp]),
@@ -69,7 +74,7 @@ def load():
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype, fn.argtypes = res, args
-    if lib.paacb_version() < 101:
+    if lib.paacb_version() < 102:
         raise PaacbError('libpaacb.so is stale (version %d); rebuild' % lib.paacb_version())
     _lib = lib
     return lib

@@ -54,23 +54,31 @@ class ActorLearner(Process):
                                     rho=args.alpha, eps=args.e, momentum=0.0, clip_norm=args.clip_norm,
                                     clip_norm_type=args.clip_norm_type,
                                     seed=getattr(args, 'random_seed', 3) * (self.rank + 1),
-                                    world_size=self.world_size)
+                                    world_size=self.world_size, first_env=first)
 
         self.session = Session()
 
         scope = getattr(self.network, 'name', 'local_learning')
-        self.network_saver = Saver(self._get_network_state, self._set_network_state, scope=scope)
+        # tf.train.Saver() of actor_learner.py:79 is created AFTER apply_gradients, so the reference's checkpoints/ bundle holds
+        # the RMSProp slots next to the network variables (the shipped -80000000.index files confirm it): written here too, so
+        # that the reference's train.py can resume from a folder written by this implementation; optional on restore.
+        self.network_saver = Saver(self._get_network_state, self._set_network_state, scope=scope,
+                                   optional=lambda key: 'OptimizerVariables' in key)
         self.optimizer_saver = Saver(self._get_optimizer_state, self._set_optimizer_state, max_to_keep=1,
                                      name='OptimizerSaver', scope=scope)
 
     # ---- checkpoint payloads: TF variable names, reference layouts -----------------
     def _get_network_state(self):
-        return {n: t.detach().cpu().clone() for n, t in self.network.variables().items()}
+        out = {n: t.detach().cpu().clone() for n, t in self.network.variables().items()}
+        out.update(self._get_optimizer_state())
+        return out
 
     def _set_network_state(self, state):
         for n, t in self.network.variables().items():
             t.copy_(state[n])
         self.network.params_changed()
+        if all(k in state for k in self._get_optimizer_state()):
+            self._set_optimizer_state(state)
 
     def _slot_views(self, flat):
         return {n: flat[off:off + int(np.prod(shape))].view(*shape) for n, off, shape, _ in self.network.tensors}

@@ -73,6 +73,28 @@ void prof_drain(const paacb_ctx* ctx) {
   ctx->prof_n = 0;
 }
 
+// Every launch goes to the CURRENT device; kernel attributes, tensor maps and the context's own buffers belong to
+// ctx->device.  A mismatch would silently run on the wrong GPU, so it is an argument error.
+int check_current_device(const paacb_ctx* ctx, const char* who) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cudaGetDevice failed", who);
+    return PAACB_ECUDA;
+  }
+  if (cur != ctx->device) {
+    set_error("%s: the current CUDA device is %d but the context was created for device %d (cudaSetDevice first)", who, cur,
+              ctx->device);
+    return PAACB_EINVAL;
+  }
+  return PAACB_OK;
+}
+#define PAACB_CHECK_DEVICE(ctx)                                              \
+  do {                                                                       \
+    const int rc__ = paacb::check_current_device((ctx), __func__);           \
+    if (rc__ != PAACB_OK) return rc__;                                       \
+  } while (0)
+
 }  // namespace paacb
 
 using namespace paacb;
@@ -103,6 +125,7 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
   memset(c, 0, sizeof(*c));
   c->arch = arch; c->num_actions = num_actions; c->device = device; c->math = PAACB_MATH_FP32;
   c->num_sms = prop.multiProcessorCount;
+  c->opt_fused_blocks = -1;
   {
     const char* knob = getenv("PAACB_DBG");
     c->dbg = (knob != nullptr) ? atoi(knob) : 0;
@@ -110,6 +133,8 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     c->always_pack = (ap != nullptr) ? atoi(ap) : 0;
     const char* tp = getenv("PAACB_OPT_TWO_PASS");
     c->opt_two_pass = (tp != nullptr) ? atoi(tp) : 0;
+    const char* hg = getenv("PAACB_K1_HOST_GRID");      // tuning knob for tools/experiments/pcie_probe.py
+    c->k1_host_grid = (hg != nullptr && atoi(hg) > 0) ? atoi(hg) : 96;
   }
   int h = PAACB_OBS, w = PAACB_OBS, ch = PAACB_STACK;
   int64_t poff = 0, aoff = 0;
@@ -317,10 +342,25 @@ int paacb_params_changed(paacb_ctx* ctx) {
   return PAACB_OK;
 }
 
-// the operand images of the forward (bf16 hi/lo transposes, conv1 int8 digits) for the parameters at d_params
+// the operand images of the forward for the parameters at d_params: bf16 hi/lo transposes + conv1 int8 digits (bf16x3), or
+// the pre-swizzled tf32 images (+ NIPS conv1 int8 digits) of the tf32 modes.  Cached in the context between calls.
+static int pack_forward_images(const paacb_ctx* ctx, const float* d_params, cudaStream_t st) {
+  if (ctx->math == PAACB_MATH_BF16X3) return launch_pack_bf16_weights(ctx, d_params, st);
+  if (ctx->math == PAACB_MATH_FP32) return PAACB_OK;
+  for (int l = 0; l < ctx->n_layers; ++l) {
+    const LayerGeom& g = ctx->layer[l];
+    const int rc = launch_pack_weights(ctx, g, d_params + g.w_off, st);
+    if (rc != PAACB_OK) return rc;
+  }
+  if (ctx->layer[0].N == 16 && ctx->wq_i8 != nullptr) {          // NIPS conv1 runs on the int8 pipe (tc2_conv1.cu)
+    const int rc = launch_pack_conv1_i8(ctx, d_params, st);
+    if (rc != PAACB_OK && rc != PAACB_EUNSUPPORTED) return rc;
+  }
+  return PAACB_OK;
+}
 static int ensure_forward_images(const paacb_ctx* ctx, const float* d_params, cudaStream_t st) {
   if (ctx->fwd_img_valid && ctx->fwd_img_src == d_params && !ctx->always_pack) return PAACB_OK;
-  const int rc = launch_pack_bf16_weights(ctx, d_params, st);
+  const int rc = pack_forward_images(ctx, d_params, st);
   if (rc == PAACB_OK) {
     ctx->fwd_img_valid = 1;
     ctx->fwd_img_src = d_params;
@@ -365,15 +405,31 @@ int64_t paacb_backward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
 int64_t paacb_optimizer_workspace_floats(const paacb_ctx* ctx) { return ctx ? optimizer_ws_floats(ctx) : PAACB_EINVAL; }
 int64_t paacb_launch_count(const paacb_ctx* ctx) { return ctx ? ctx->launches : PAACB_EINVAL; }
 
-int paacb_preprocess_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_per_env, const uint8_t* d_reset,
-                        const uint8_t* d_prev, uint8_t* d_next, int64_t n_envs, paacb_stream stream) {
+static int preprocess_impl(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_per_env, const uint8_t* d_reset,
+                           const uint8_t* d_prev, uint8_t* d_next, int64_t n_envs, const StepScalars& sc, paacb_stream stream) {
   PAACB_CHECK_ARG(ctx && d_frames && d_prev && d_next, "NULL argument");
+  PAACB_CHECK_DEVICE(ctx);
   PAACB_CHECK_ARG(pairs_per_env == 1 || pairs_per_env == PAACB_STACK, "pairs_per_env must be 1 or 4");
-  PAACB_CHECK_ARG(d_reset == nullptr || pairs_per_env == PAACB_STACK, "reset flags need pairs_per_env == 4");
+  PAACB_CHECK_ARG((d_reset == nullptr && !(sc.over_in != nullptr && sc.over_is_reset)) || pairs_per_env == PAACB_STACK,
+                  "reset flags need pairs_per_env == 4");
   PAACB_CHECK_ARG(n_envs >= 0 && n_envs < (1LL << 31), "n_envs out of range");
   PAACB_CHECK_ARG(((uintptr_t)d_frames & 15) == 0 && ((uintptr_t)d_prev & 15) == 0 && ((uintptr_t)d_next & 15) == 0,
                   "buffers must be 16-byte aligned");
-  return launch_preprocess(ctx, d_frames, pairs_per_env, d_reset, d_prev, d_next, n_envs, (cudaStream_t)stream);
+  return launch_preprocess(ctx, d_frames, pairs_per_env, d_reset, d_prev, d_next, n_envs, sc, (cudaStream_t)stream);
+}
+
+int paacb_preprocess_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_per_env, const uint8_t* d_reset,
+                        const uint8_t* d_prev, uint8_t* d_next, int64_t n_envs, paacb_stream stream) {
+  const StepScalars none = {nullptr, nullptr, nullptr, nullptr, 0};
+  return preprocess_impl(ctx, d_frames, pairs_per_env, d_reset, d_prev, d_next, n_envs, none, stream);
+}
+
+int paacb_observe_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_per_env, const uint8_t* d_reset,
+                     const uint8_t* d_prev, uint8_t* d_next, int64_t n_envs, const float* d_rewards_in,
+                     const float* d_over_in, float* d_rewards_out, float* d_over_out, int over_is_reset, paacb_stream stream) {
+  PAACB_CHECK_ARG(d_rewards_in && d_over_in && d_rewards_out && d_over_out, "NULL reward / episode-over buffer");
+  const StepScalars sc = {d_rewards_in, d_over_in, d_rewards_out, d_over_out, over_is_reset ? 1 : 0};
+  return preprocess_impl(ctx, d_frames, pairs_per_env, d_reset, d_prev, d_next, n_envs, sc, stream);
 }
 
 static int run_layer_fwd(const paacb_ctx* ctx, int l, const float* d_params, const uint8_t* d_states, int64_t batch,
@@ -382,9 +438,9 @@ static int run_layer_fwd(const paacb_ctx* ctx, int l, const float* d_params, con
   const void* x = (l == 0) ? (const void*)d_states
                            : (const void*)(ws + g.in_act_off * slice.cap + slice.first * (int64_t)g.H * g.W * g.C);
   float* y = ws + g.out_act_off * slice.cap + slice.first * (int64_t)g.OH * g.OW * g.N;
-  if (ctx->math != PAACB_MATH_FP32 && l == 0 && g.N == 16 && ctx->wq_i8 != nullptr && !(ctx->dbg & (1 << 17))) {
-    int rc = launch_pack_conv1_i8(ctx, d_params, st);           // NIPS conv1: uint8 pixels x int8 weight digits (tc2_conv1.cu)
-    if (rc == PAACB_OK) rc = launch_conv1_fwd_i8_f32(ctx, d_params, d_states, y, batch, st);
+  if (ctx->math != PAACB_MATH_FP32 && l == 0 && g.N == 16 && ctx->wq_i8 != nullptr && !(PAACB_DBGV(ctx->dbg) & (1 << 17))) {
+    // NIPS conv1: uint8 pixels x int8 weight digits (tc2_conv1.cu; the digit image is part of the cached forward images)
+    const int rc = launch_conv1_fwd_i8_f32(ctx, d_params, d_states, y, batch, st);
     if (rc != PAACB_EUNSUPPORTED) return rc;
   }
   if (ctx->math != PAACB_MATH_FP32) {
@@ -395,53 +451,73 @@ static int run_layer_fwd(const paacb_ctx* ctx, int l, const float* d_params, con
   return launch_conv_fwd_simt(ctx, g, x, d_params + g.w_off, d_params + g.b_off, y, batch, st);
 }
 
-int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
-                         float* d_fwd_ws, float* d_pi, float* d_v, const float* d_uniforms, int32_t* d_actions,
-                         float* d_onehot, paacb_stream stream) {
-  return paacb_policy_forward_at(ctx, d_params, d_states, batch, d_fwd_ws, batch, 0, d_pi, d_v, d_uniforms, d_actions,
-                                 d_onehot, stream);
-}
-
-int paacb_policy_forward_at(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
-                            float* d_fwd_ws, int64_t ws_capacity, int64_t ws_first, float* d_pi, float* d_v,
-                            const float* d_uniforms, int32_t* d_actions, float* d_onehot, paacb_stream stream) {
+static int forward_impl(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch, float* d_fwd_ws,
+                        int64_t ws_capacity, int64_t ws_first, float* d_pi, float* d_v, const float* d_uniforms,
+                        const uint64_t* d_rng, uint64_t draw, int64_t first_sample, int32_t* d_actions, float* d_onehot,
+                        paacb_stream stream) {
   PAACB_CHECK_ARG(ctx && d_params && d_states && d_fwd_ws && d_pi && d_v, "NULL argument");
+  PAACB_CHECK_DEVICE(ctx);
   PAACB_CHECK_ARG(batch >= 0 && batch * (int64_t)ctx->layer[0].OH * ctx->layer[0].OW < (1LL << 40), "batch out of range");
   PAACB_CHECK_ARG(ws_first >= 0 && ws_capacity >= 0 && ws_first + batch <= ws_capacity,
                   "samples [ws_first, ws_first + batch) must lie inside the workspace capacity");
+  PAACB_CHECK_ARG(d_uniforms == nullptr || d_rng == nullptr, "give injected uniforms OR a device rng state, not both");
   // every per-sample tensor is a multiple of 32 elements (Nature: of 64), so any sample offset keeps the planes 16-byte aligned
   const WsSlice slice = {ws_capacity, ws_first};
   PAACB_CHECK_ARG(((uintptr_t)d_params & 15) == 0 && ((uintptr_t)d_states & 15) == 0 && ((uintptr_t)d_fwd_ws & 15) == 0,
                   "params / states / workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (batch == 0) return PAACB_OK;
+  int rc = ensure_forward_images(ctx, d_params, st);
+  if (rc != PAACB_OK) return rc;
   if (ctx->math == PAACB_MATH_BF16X3) {
-    if (batch == 0) return PAACB_OK;
     const int L = ctx->n_layers;
-    int rc = ensure_forward_images(ctx, d_params, st);
     for (int l = 0; l < L - 1 && rc == PAACB_OK; ++l) rc = launch_conv_fwd_bf16(ctx, l, d_params, d_states, d_fwd_ws, batch, slice, st);
     if (rc == PAACB_OK) rc = launch_fc_fwd_bf16(ctx, L - 1, d_params, d_fwd_ws, batch, slice, st);
     if (rc != PAACB_OK) return rc;
     const Planes hp = layer_planes(d_fwd_ws, ctx->layer[L - 1].out_act_off, ctx->feat, slice);
     return launch_heads_fwd(ctx, nullptr, reinterpret_cast<const uint16_t*>(hp.hi), reinterpret_cast<const uint16_t*>(hp.lo),
                             d_params + ctx->actor_w_off, d_params + ctx->actor_b_off, d_params + ctx->critic_w_off,
-                            d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms, d_actions, d_onehot, st);
-  }
-  if (ctx->math != PAACB_MATH_FP32 && batch > 0) {
-    // the caller may have changed the parameters since the last call: repack (a few microseconds)
-    for (int l = 0; l < ctx->n_layers; ++l) {
-      const LayerGeom& g = ctx->layer[l];
-      const int rc = launch_pack_weights(ctx, g, d_params + g.w_off, st);
-      if (rc != PAACB_OK) return rc;
-    }
+                            d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms, d_rng, draw, first_sample, d_actions,
+                            d_onehot, st);
   }
   for (int l = 0; l < ctx->n_layers; ++l) {
-    const int rc = run_layer_fwd(ctx, l, d_params, d_states, batch, d_fwd_ws, slice, st);
+    rc = run_layer_fwd(ctx, l, d_params, d_states, batch, d_fwd_ws, slice, st);
     if (rc != PAACB_OK) return rc;
   }
   const float* h = d_fwd_ws + ctx->layer[ctx->n_layers - 1].out_act_off * slice.cap + slice.first * (int64_t)ctx->feat;
   return launch_heads_fwd(ctx, h, nullptr, nullptr, d_params + ctx->actor_w_off, d_params + ctx->actor_b_off,
-                          d_params + ctx->critic_w_off, d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms,
-                          d_actions, d_onehot, st);
+                          d_params + ctx->critic_w_off, d_params + ctx->critic_b_off, batch, d_pi, d_v, d_uniforms, d_rng, draw,
+                          first_sample, d_actions, d_onehot, st);
+}
+
+int paacb_policy_forward(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                         float* d_fwd_ws, float* d_pi, float* d_v, const float* d_uniforms, int32_t* d_actions,
+                         float* d_onehot, paacb_stream stream) {
+  return forward_impl(ctx, d_params, d_states, batch, d_fwd_ws, batch, 0, d_pi, d_v, d_uniforms, nullptr, 0, 0, d_actions,
+                      d_onehot, stream);
+}
+
+int paacb_policy_forward_at(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                            float* d_fwd_ws, int64_t ws_capacity, int64_t ws_first, float* d_pi, float* d_v,
+                            const float* d_uniforms, int32_t* d_actions, float* d_onehot, paacb_stream stream) {
+  return forward_impl(ctx, d_params, d_states, batch, d_fwd_ws, ws_capacity, ws_first, d_pi, d_v, d_uniforms, nullptr, 0, 0,
+                      d_actions, d_onehot, stream);
+}
+
+int paacb_policy_forward_sample(const paacb_ctx* ctx, const float* d_params, const uint8_t* d_states, int64_t batch,
+                                float* d_fwd_ws, int64_t ws_capacity, int64_t ws_first, float* d_pi, float* d_v,
+                                const uint64_t* d_rng, uint64_t draw_index, int64_t first_sample, int32_t* d_actions,
+                                float* d_onehot, paacb_stream stream) {
+  PAACB_CHECK_ARG(d_rng != nullptr && (d_actions != nullptr || d_onehot != nullptr), "NULL rng state / no output for the actions");
+  PAACB_CHECK_ARG(((uintptr_t)d_rng & 7) == 0 && first_sample >= 0, "rng state must be 8-byte aligned, first_sample >= 0");
+  return forward_impl(ctx, d_params, d_states, batch, d_fwd_ws, ws_capacity, ws_first, d_pi, d_v, nullptr, d_rng, draw_index,
+                      first_sample, d_actions, d_onehot, stream);
+}
+
+int paacb_rng_advance(const paacb_ctx* ctx, uint64_t* d_rng, uint64_t n, paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_rng && ((uintptr_t)d_rng & 7) == 0, "NULL / misaligned rng state");
+  PAACB_CHECK_DEVICE(ctx);
+  return launch_rng_advance(ctx, d_rng, n, (cudaStream_t)stream);
 }
 
 int paacb_returns_loss_grad(const paacb_ctx* ctx, const float* d_rewards, const float* d_episode_over,
@@ -452,6 +528,7 @@ int paacb_returns_loss_grad(const paacb_ctx* ctx, const float* d_rewards, const 
   PAACB_CHECK_ARG(ctx && d_rewards && d_episode_over && d_values && d_bootstrap_v && d_actions && d_pi && d_v &&
                   d_y && d_adv && d_dlogits && d_dv && d_loss, "NULL argument");
   PAACB_CHECK_ARG(t_max >= 1 && n_envs >= 0, "t_max / n_envs out of range");
+  PAACB_CHECK_DEVICE(ctx);
   return launch_returns_loss_grad(ctx, d_rewards, d_episode_over, d_values, d_bootstrap_v, d_actions, d_pi, d_v,
                                   t_max, n_envs, gamma, entropy_beta, d_y, d_adv, d_dlogits, d_dv, d_loss,
                                   (cudaStream_t)stream);
@@ -536,6 +613,7 @@ int paacb_backward_part(const paacb_ctx* ctx, const float* d_params, const uint8
   PAACB_CHECK_ARG(ctx && d_params && d_states && d_fwd_ws && d_dlogits && d_dv && d_bwd_ws && d_grads, "NULL argument");
   PAACB_CHECK_ARG(((uintptr_t)d_bwd_ws & 15) == 0 && ((uintptr_t)d_grads & 15) == 0, "workspace / grads must be 16-byte aligned");
   PAACB_CHECK_ARG(part == PAACB_BWD_ALL || part == PAACB_BWD_TAIL || part == PAACB_BWD_HEAD, "unknown part");
+  PAACB_CHECK_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   const bool do_tail = part != PAACB_BWD_HEAD, do_head = part != PAACB_BWD_TAIL;
   if (do_tail && cudaMemsetAsync(d_grads, 0, (size_t)ctx->param_count * sizeof(float), st) != cudaSuccess) {
@@ -558,25 +636,49 @@ int paacb_backward_part(const paacb_ctx* ctx, const float* d_params, const uint8
   return backward_generic(ctx, d_params, d_states, batch, d_fwd_ws, d_dlogits, d_dv, d_bwd_ws, d_grads, do_tail, do_head, st);
 }
 
-int paacb_clip_rmsprop(const paacb_ctx* ctx, float* d_params, float* d_ms, float* d_mom, const float* d_grads,
-                       float grad_scale, float lr, float rho, float eps, float momentum, float clip_norm,
-                       int clip_type, float* d_norm_out, float* d_opt_ws, paacb_stream stream) {
+static int clip_rmsprop_impl(const paacb_ctx* ctx, float* d_params, float* d_ms, float* d_mom, const float* d_grads,
+                             float grad_scale, float lr, const float* d_lr, float rho, float eps, float momentum, float clip_norm,
+                             int clip_type, float* d_norm_out, float* d_opt_ws, paacb_stream stream) {
   PAACB_CHECK_ARG(ctx && d_params && d_ms && d_mom && d_grads && d_opt_ws, "NULL argument");
+  PAACB_CHECK_DEVICE(ctx);
   PAACB_CHECK_ARG(clip_type == PAACB_CLIP_IGNORE || clip_type == PAACB_CLIP_GLOBAL,
                   "clip_type must be ignore or global ('local' is broken in the reference, actor_learner.py:62-63)");
   PAACB_CHECK_ARG(clip_type == PAACB_CLIP_IGNORE || clip_norm > 0.f, "clip_norm must be positive");
   PAACB_CHECK_ARG((((uintptr_t)d_params | (uintptr_t)d_ms | (uintptr_t)d_mom | (uintptr_t)d_grads | (uintptr_t)d_opt_ws) & 15) == 0,
                   "buffers must be 16-byte aligned");
-  int rc = launch_clip_rmsprop(ctx, d_params, d_ms, d_mom, d_grads, grad_scale, lr, rho, eps, momentum, clip_norm,
+  int rc = launch_clip_rmsprop(ctx, d_params, d_ms, d_mom, d_grads, grad_scale, lr, d_lr, rho, eps, momentum, clip_norm,
                                clip_type, d_norm_out, d_opt_ws, (cudaStream_t)stream);
-  if (rc == PAACB_OK && ctx->math == PAACB_MATH_BF16X3) {
+  if (rc == PAACB_OK && ctx->math != PAACB_MATH_FP32) {
     // the library just changed the parameters: refresh the cached forward images in stream order (also inside a captured
     // graph), so the next forwards -- T acting forwards, the bootstrap and the training forward -- need no pack
-    rc = launch_pack_bf16_weights(ctx, d_params, (cudaStream_t)stream);
+    rc = pack_forward_images(ctx, d_params, (cudaStream_t)stream);
     ctx->fwd_img_valid = (rc == PAACB_OK);
     ctx->fwd_img_src = d_params;
   }
   return rc;
+}
+
+int paacb_clip_rmsprop(const paacb_ctx* ctx, float* d_params, float* d_ms, float* d_mom, const float* d_grads,
+                       float grad_scale, float lr, float rho, float eps, float momentum, float clip_norm,
+                       int clip_type, float* d_norm_out, float* d_opt_ws, paacb_stream stream) {
+  return clip_rmsprop_impl(ctx, d_params, d_ms, d_mom, d_grads, grad_scale, lr, nullptr, rho, eps, momentum, clip_norm, clip_type,
+                           d_norm_out, d_opt_ws, stream);
+}
+
+int paacb_clip_rmsprop_dlr(const paacb_ctx* ctx, float* d_params, float* d_ms, float* d_mom, const float* d_grads,
+                           float grad_scale, const float* d_lr, float rho, float eps, float momentum, float clip_norm,
+                           int clip_type, float* d_norm_out, float* d_opt_ws, paacb_stream stream) {
+  PAACB_CHECK_ARG(d_lr != nullptr, "d_lr is NULL");
+  return clip_rmsprop_impl(ctx, d_params, d_ms, d_mom, d_grads, grad_scale, 0.f, d_lr, rho, eps, momentum, clip_norm, clip_type,
+                           d_norm_out, d_opt_ws, stream);
+}
+
+int paacb_grad_stats(const paacb_ctx* ctx, const float* d_grads, float grad_scale, float* d_opt_ws, double* d_out4,
+                     paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_grads && d_opt_ws && d_out4, "NULL argument");
+  PAACB_CHECK_ARG(((uintptr_t)d_opt_ws & 15) == 0 && ((uintptr_t)d_out4 & 7) == 0, "workspace / output misaligned");
+  PAACB_CHECK_DEVICE(ctx);
+  return launch_grad_stats(ctx, d_grads, grad_scale, d_opt_ws, d_out4, (cudaStream_t)stream);
 }
 
 int paacb_host_register(void* host_ptr, size_t bytes, void** d_ptr) {

@@ -10,6 +10,15 @@
 #error "paacb is written for sm_100a (B200) only"
 #endif
 
+// Ablation switches (PAACB_DBG bit mask: stages of a kernel switched off for timing experiments, tools/ablation_sweep.py)
+// exist only in builds made with PAACB_ABLATIONS=1 (python -m paac_b200.build); in the product build they compile to 0 and
+// the branches vanish from the kernels.
+#ifdef PAACB_ABLATIONS
+#define PAACB_DBGV(x) (x)
+#else
+#define PAACB_DBGV(x) 0
+#endif
+
 namespace paacb {
 
 // One conv / fc layer viewed as an implicit GEMM: Y[M, N] = im2col(X)[M, K] * W[K, N].
@@ -27,6 +36,15 @@ struct LayerGeom {
   int64_t out_act_off;    // offset of the output activation, per sample
 };
 
+// per-step scalars that ride along with K1 (paacb_observe_u8); all nullptr for plain paacb_preprocess_u8
+struct StepScalars {
+  const float* rewards_in;   // [n] device or pinned+mapped host memory (the runners' shared arrays)
+  const float* over_in;      // [n] episode-over flags (0/1)
+  float* rewards_out;        // [n] row t of the rollout buffers
+  float* over_out;
+  int over_is_reset;         // over_in[n] != 0 resets environment n's stack (needs 4 frame pairs per environment)
+};
+
 struct ResizeTables {
   uint8_t row[PAACB_OBS];
   uint8_t col[PAACB_OBS];
@@ -38,6 +56,14 @@ enum KernelId {
   K_SUMSQ = 16, K_RMSPROP = 17, K_PACK = 18, K_COUNT = 19
 };
 constexpr int kMaxProfEvents = 8192;
+
+// "done once per device" flag for per-device state such as cudaFuncSetAttribute (function attributes belong to the device
+// that was current when they were set): one bit per device index, set/read atomically (the setup itself is idempotent).
+struct DeviceOnce {
+  unsigned long long mask[2] = {0ull, 0ull};
+  bool done(int device) const { return (__atomic_load_n(&mask[(device >> 6) & 1], __ATOMIC_ACQUIRE) >> (device & 63)) & 1ull; }
+  void mark(int device) { __atomic_fetch_or(&mask[(device >> 6) & 1], 1ull << (device & 63), __ATOMIC_RELEASE); }
+};
 
 struct TensorInfo {
   char name[40];
@@ -88,12 +114,18 @@ struct paacb_ctx {
   // (paacb_clip_rmsprop refreshes them in-stream; paacb_params_changed() invalidates them)
   mutable int fwd_img_valid;
   mutable const float* fwd_img_src;
-  // fused optimizer: grid-barrier counter (4 bytes of device memory, zeroed at creation) and the grid size it is used with
+  // fused optimizer: self-resetting grid barrier (arrival counter + generation word in device memory, zeroed at creation)
+  // and the co-resident grid size of the cooperative kernel on this context's device (-1: not queried yet)
   unsigned int* opt_counter;
-  mutable int opt_grid;
-  mutable int opt_launches;
+  mutable int opt_fused_blocks;
   int opt_two_pass;             // PAACB_OPT_TWO_PASS=1: the two-launch optimizer (sumsq + update)
   int always_pack;              // PAACB_ALWAYS_PACK=1: re-derive the images on every forward (debug)
+  // K1: memory type of the frame buffers seen so far (address >> 21 -> host?) and the narrow grid of the zero-copy launch
+  static constexpr int kK1Cache = 8;
+  mutable int k1_cache_n;
+  mutable uintptr_t k1_cache_key[kK1Cache];
+  mutable int k1_cache_host[kK1Cache];
+  int k1_host_grid;             // PAACB_K1_HOST_GRID (default 96)
   int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };
 
@@ -135,7 +167,7 @@ void prof_drain(const paacb_ctx* ctx);
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`) --------------------------
 int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
-                      const uint8_t* prev, uint8_t* next, int64_t n, cudaStream_t st);
+                      const uint8_t* prev, uint8_t* next, int64_t n, const StepScalars& sc, cudaStream_t st);
 
 // SIMT fp32 implicit GEMMs (gemm_simt.cu)
 int launch_conv_fwd_simt(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* w, const float* bias,
@@ -150,8 +182,9 @@ int launch_conv_wgrad_simt(const paacb_ctx* ctx, const LayerGeom& g, const void*
 // heads (heads.cu)
 // h == nullptr: the hidden activation is given as bf16-split planes (h_hi, h_lo)
 int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi, const uint16_t* h_lo, const float* wa, const float* ba, const float* wc,
-                     const float* bc, int64_t batch, float* pi, float* v, const float* uniforms, int32_t* actions,
-                     float* onehot, cudaStream_t st);
+                     const float* bc, int64_t batch, float* pi, float* v, const float* uniforms, const uint64_t* rng,
+                     uint64_t draw, int64_t first_sample, int32_t* actions, float* onehot, cudaStream_t st);
+int launch_rng_advance(const paacb_ctx* ctx, uint64_t* rng, uint64_t n, cudaStream_t st);
 // dh == nullptr: dh is written as bf16-split planes (dh_hi, dh_lo) and its column sums are added to dbh
 int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi, const uint16_t* h_lo, uint16_t* dh_hi,
                      uint16_t* dh_lo, float* dbh, const float* wa, const float* wc, const float* dlogits,
@@ -166,9 +199,12 @@ int launch_returns_loss_grad(const paacb_ctx* ctx, const float* rewards, const f
 
 // optimizer (optim.cu)
 int64_t optimizer_ws_floats(const paacb_ctx* ctx);
+// d_lr != nullptr: the learning rate is read from device memory at run time instead of `lr`
 int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* mom, const float* grads, float gscale,
-                        float lr, float rho, float eps, float momentum, float clip, int clip_type, float* norm_out,
-                        float* ws, cudaStream_t st);
+                        float lr, const float* d_lr, float rho, float eps, float momentum, float clip, int clip_type,
+                        float* norm_out, float* ws, cudaStream_t st);
+
+int launch_grad_stats(const paacb_ctx* ctx, const float* grads, float gscale, float* ws, double* out4, cudaStream_t st);
 
 // tcgen05 path (gemm_tc.cu); returns PAACB_EUNSUPPORTED when a layer/mode is not covered
 int launch_pack_weights(const paacb_ctx* ctx, const LayerGeom& g, const float* w, cudaStream_t st);

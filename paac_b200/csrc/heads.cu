@@ -22,11 +22,50 @@ __device__ __forceinline__ float split_load(const uint16_t* hi, const uint16_t* 
 constexpr int kMaxA = PAACB_MAX_ACTIONS;
 constexpr int kHeadWarps = 8;
 
+// ---- K6: the uniform of a sampling decision ---------------------------------------------------------------------
+// Either injected by the caller (d_uniforms; tests and reference-style host sampling) or drawn IN the kernel from
+// Philox4x32-10 (Salmon et al., SC'11; the generator behind curand / torch.cuda): counter = (sample index, draw index),
+// key = seed, u = (first output word >> 8) * 2^-24 in [0, 1).  Stateless: every (seed, draw, sample) has one value
+// whatever the launch geometry or the slicing of the environments.  oracle/sampling.py restates it in NumPy.
+struct SampleSrc {
+  const float* uniforms;        // injected uniforms [b] or nullptr
+  const uint64_t* rng;          // device {seed, draw base} or nullptr
+  uint64_t draw;                // added to the draw base
+  int64_t first;                // global index of sample 0 of this call (environment slices)
+};
+__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t& hi) {
+  const uint64_t p = (uint64_t)a * b;
+  hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+__device__ __forceinline__ uint32_t philox4x32_10_x(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    const uint32_t lo0 = mulhilo32(0xD2511F53u, c0, hi0);
+    const uint32_t lo1 = mulhilo32(0xCD9E8D57u, c2, hi1);
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+__device__ __forceinline__ float sample_uniform(const SampleSrc& s, int64_t b) {
+  if (s.uniforms != nullptr) return __ldg(s.uniforms + b);
+  const uint64_t seed = s.rng[0], d = s.rng[1] + s.draw, i = (uint64_t)(s.first + b);
+  const uint32_t x = philox4x32_10_x((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)d, (uint32_t)(d >> 32), (uint32_t)seed,
+                                     (uint32_t)(seed >> 32));
+  return (float)(x >> 8) * 5.9604644775390625e-08f;      // 2^-24
+}
+// paacb_rng_advance: draw base += n, in stream order (one launch per update; the base lives in device memory so that a
+// captured CUDA graph of the rollout replays with fresh uniforms)
+__global__ void rng_advance_kernel(uint64_t* rng, uint64_t n) { rng[1] += n; }
+
 __global__ void __launch_bounds__(kHeadWarps * 32)
 heads_fwd_kernel(const float* __restrict__ h, const uint16_t* __restrict__ h_hi, const uint16_t* __restrict__ h_lo,
                  const float* __restrict__ wa, const float* __restrict__ ba,
                  const float* __restrict__ wc, const float* __restrict__ bc, int64_t batch, int F, int A,
-                 float* __restrict__ pi, float* __restrict__ v, const float* __restrict__ uniforms,
+                 float* __restrict__ pi, float* __restrict__ v, const SampleSrc smp,
                  int32_t* __restrict__ actions, float* __restrict__ onehot) {
   extern __shared__ float sw[];              // [F][A+1]: actor columns then the critic column
   const int A1 = A + 1;
@@ -71,8 +110,8 @@ heads_fwd_kernel(const float* __restrict__ h, const uint16_t* __restrict__ h_hi,
     const float p = e / sum;
     if (lane < A) pi[b * A + lane] = p;
     if (lane == 0) v[b] = val;
-    if (uniforms != nullptr) {
-      const float u = __ldg(uniforms + b);
+    if (smp.uniforms != nullptr || smp.rng != nullptr) {
+      const float u = sample_uniform(smp, b);
       // fp32 running sum in index order: c_j = c_{j-1} + p_j; action = first j < A-1 with u < c_j
       int act = A - 1;
       float c = 0.f;
@@ -181,12 +220,12 @@ __device__ __forceinline__ void unpack4(uint2 hi, uint2 lo, float (&x)[4]) {
   x[3] = __uint_as_float(hi.y & 0xffff0000u) + __uint_as_float(lo.y & 0xffff0000u);
 }
 
-constexpr int kHsF = 512;
-
+// kHsF = hidden width: 512 (Nature) or 256 (NIPS)
+template <int kHsF>
 __global__ void __launch_bounds__(kHeadWarps * 32)
 heads_fwd_split_kernel(const uint16_t* __restrict__ h_hi, const uint16_t* __restrict__ h_lo, const float* __restrict__ wa,
                        const float* __restrict__ ba, const float* __restrict__ wc, const float* __restrict__ bc, int64_t batch,
-                       int A, float* __restrict__ pi, float* __restrict__ v, const float* __restrict__ uniforms,
+                       int A, float* __restrict__ pi, float* __restrict__ v, const SampleSrc smp,
                        int32_t* __restrict__ actions, float* __restrict__ onehot) {
   extern __shared__ __align__(16) float sw[];          // [A+1][F]: actor rows then the critic row
   const int A1 = A + 1;
@@ -197,10 +236,11 @@ heads_fwd_split_kernel(const uint16_t* __restrict__ h_hi, const uint16_t* __rest
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t b = (int64_t)blockIdx.x * kHeadWarps + warp; b < batch; b += (int64_t)gridDim.x * kHeadWarps) {
-    // lane's features: 128 * j + 4 * lane + e  (j, e = 0..3): every warp load covers 256 contiguous bytes of a plane
-    float x[4][4];
+    // lane's features: 128 * j + 4 * lane + e  (j < F / 128, e = 0..3): every warp load covers 256 contiguous bytes of a plane
+    constexpr int NJ = kHsF / 128;
+    float x[NJ][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int64_t o = b * kHsF + 128 * j + 4 * lane;
       unpack4(__ldg(reinterpret_cast<const uint2*>(h_hi + o)), __ldg(reinterpret_cast<const uint2*>(h_lo + o)), x[j]);
     }
@@ -210,7 +250,7 @@ heads_fwd_split_kernel(const uint16_t* __restrict__ h_hi, const uint16_t* __rest
       acc[a] = 0.f;
       if (a < A1) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const float4 w = *reinterpret_cast<const float4*>(sw + a * kHsF + 128 * j + 4 * lane);
           acc[a] = fmaf(x[j][0], w.x, fmaf(x[j][1], w.y, fmaf(x[j][2], w.z, fmaf(x[j][3], w.w, acc[a]))));
         }
@@ -234,8 +274,8 @@ heads_fwd_split_kernel(const uint16_t* __restrict__ h_hi, const uint16_t* __rest
     const float p = e / sum;
     if (lane < A) pi[b * A + lane] = p;
     if (lane == 0) v[b] = val;
-    if (uniforms != nullptr) {
-      const float u = __ldg(uniforms + b);
+    if (smp.uniforms != nullptr || smp.rng != nullptr) {
+      const float u = sample_uniform(smp, b);
       int act = A - 1;
       float c = 0.f;
       bool done = false;
@@ -250,7 +290,8 @@ heads_fwd_split_kernel(const uint16_t* __restrict__ h_hi, const uint16_t* __rest
 }
 
 // thread t owns the adjacent features 2t, 2t + 1 (one 32-bit word of each plane); 4 samples in flight
-__global__ void __launch_bounds__(kHbThreads)
+template <int kHsF>
+__global__ void __launch_bounds__(kHsF / 2)
 heads_bwd_split_kernel(const uint16_t* __restrict__ h_hi, const uint16_t* __restrict__ h_lo, uint16_t* __restrict__ dh_hi,
                        uint16_t* __restrict__ dh_lo, float* __restrict__ dbh, const float* __restrict__ wa,
                        const float* __restrict__ wc, const float* __restrict__ dlogits, const float* __restrict__ dv,
@@ -261,7 +302,7 @@ heads_bwd_split_kernel(const uint16_t* __restrict__ h_hi, const uint16_t* __rest
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * kHbChunk;
   const int nb = (int)((batch - b0 < kHbChunk) ? batch - b0 : kHbChunk);
-  for (int i = tid; i < kHbChunk * A1; i += kHbThreads) {
+  for (int i = tid; i < kHbChunk * A1; i += kHsF / 2) {
     const int r = i / A1, a = i - r * A1;
     sd[r][a] = (r < nb) ? ((a < A) ? __ldg(dlogits + (b0 + r) * A + a) : __ldg(dv + b0 + r)) : 0.f;   // zero rows past the batch
   }
@@ -330,23 +371,28 @@ heads_bwd_split_kernel(const uint16_t* __restrict__ h_hi, const uint16_t* __rest
 }
 
 int launch_heads_fwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi, const uint16_t* h_lo, const float* wa, const float* ba, const float* wc,
-                     const float* bc, int64_t batch, float* pi, float* v, const float* uniforms, int32_t* actions,
-                     float* onehot, cudaStream_t st) {
+                     const float* bc, int64_t batch, float* pi, float* v, const float* uniforms, const uint64_t* rng,
+                     uint64_t draw, int64_t first_sample, int32_t* actions, float* onehot, cudaStream_t st) {
   if (batch == 0) return PAACB_OK;
   const int F = ctx->feat, A = ctx->num_actions;
   int64_t blocks = (batch + kHeadWarps - 1) / kHeadWarps;
   const int64_t cap = (int64_t)ctx->num_sms * 8;
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)F * (A + 1) * sizeof(float);
-  if (h == nullptr && F == kHsF) {
+  const SampleSrc smp = {uniforms, rng, draw, first_sample};
+  if (h == nullptr && (F == 512 || F == 256)) {
     PAACB_LAUNCH_BEGIN(ctx, K_HEADS_FWD, st);
-    heads_fwd_split_kernel<<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h_hi, h_lo, wa, ba, wc, bc, batch, A, pi, v, uniforms,
-                                                                             actions, onehot);
+    if (F == 512)
+      heads_fwd_split_kernel<512><<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h_hi, h_lo, wa, ba, wc, bc, batch, A, pi, v, smp,
+                                                                                    actions, onehot);
+    else
+      heads_fwd_split_kernel<256><<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h_hi, h_lo, wa, ba, wc, bc, batch, A, pi, v, smp,
+                                                                                    actions, onehot);
     PAACB_LAUNCH_END(ctx, K_HEADS_FWD, st);
     return PAACB_OK;
   }
   PAACB_LAUNCH_BEGIN(ctx, K_HEADS_FWD, st);
-  heads_fwd_kernel<<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h, h_hi, h_lo, wa, ba, wc, bc, batch, F, A, pi, v, uniforms,
+  heads_fwd_kernel<<<(unsigned)blocks, kHeadWarps * 32, smem, st>>>(h, h_hi, h_lo, wa, ba, wc, bc, batch, F, A, pi, v, smp,
                                                                      actions, onehot);
   PAACB_LAUNCH_END(ctx, K_HEADS_FWD, st);
   return PAACB_OK;
@@ -360,9 +406,13 @@ int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi,
   const int F = ctx->feat, A = ctx->num_actions;
   const unsigned blocks = (unsigned)((batch + kHbChunk - 1) / kHbChunk);
   if (F > 2 * kHbThreads) { set_error("heads_bwd: hidden width > 512 unsupported"); return PAACB_EUNSUPPORTED; }
-  if (h == nullptr && dh == nullptr && F == kHsF) {
+  if (h == nullptr && dh == nullptr && (F == 512 || F == 256)) {
     PAACB_LAUNCH_BEGIN(ctx, K_HEADS_BWD, st);
-    heads_bwd_split_kernel<<<blocks, kHbThreads, 0, st>>>(h_hi, h_lo, dh_hi, dh_lo, dbh, wa, wc, dlogits, dv, batch, A, dwa, dba,
+    if (F == 512)
+      heads_bwd_split_kernel<512><<<blocks, 256, 0, st>>>(h_hi, h_lo, dh_hi, dh_lo, dbh, wa, wc, dlogits, dv, batch, A, dwa, dba,
+                                                          dwc, dbc);
+    else
+      heads_bwd_split_kernel<256><<<blocks, 128, 0, st>>>(h_hi, h_lo, dh_hi, dh_lo, dbh, wa, wc, dlogits, dv, batch, A, dwa, dba,
                                                           dwc, dbc);
     PAACB_LAUNCH_END(ctx, K_HEADS_BWD, st);
     return PAACB_OK;
@@ -373,6 +423,13 @@ int launch_heads_bwd(const paacb_ctx* ctx, const float* h, const uint16_t* h_hi,
   else
     heads_bwd_kernel<2><<<blocks, kHbThreads, 0, st>>>(h, h_hi, h_lo, dh_hi, dh_lo, dbh, wa, wc, dlogits, dv, batch, F, A, dh, dwa, dba, dwc, dbc);
   PAACB_LAUNCH_END(ctx, K_HEADS_BWD, st);
+  return PAACB_OK;
+}
+
+int launch_rng_advance(const paacb_ctx* ctx, uint64_t* rng, uint64_t n, cudaStream_t st) {
+  PAACB_LAUNCH_BEGIN(ctx, K_HEADS_FWD, st);
+  rng_advance_kernel<<<1, 1, 0, st>>>(rng, n);
+  PAACB_LAUNCH_END(ctx, K_HEADS_FWD, st);
   return PAACB_OK;
 }
 

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
           }
           const uint8_t* src = ok ? xb + (base_j[j] + tab) * ESZ + my_chunk * 16 : xb;   // !ok: 0 bytes read, zero fill
           const int row = j * RPI + my_row0;
-          if (!(p.dbg & 4)) cp_async16(dst0 + (uint32_t)(row * Cfg::ROWB) + (((uint32_t)my_chunk ^ swz_of(row)) << 4), src, ok ? 16u : 0u);
+          if (!(PAACB_DBGV(p.dbg) & 4)) cp_async16(dst0 + (uint32_t)(row * Cfg::ROWB) + (((uint32_t)my_chunk ^ swz_of(row)) << 4), src, ok ? 16u : 0u);
         }
       }
       ld_kb += NG * KSUB;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
           mbar_wait(&empty_bar[pstage], pphase ^ 1u);
           if (wq4 == 0 && elect_one_sync()) {
             uint8_t* b_hi = smem + (size_t)pstage * Cfg::STAGE_BYTES;
-            if (p.dbg & 1) {
+            if (PAACB_DBGV(p.dbg) & 1) {
               mbar_arrive(&full_bar[pstage]);
             } else {
               mbar_arrive_expect_tx(&full_bar[pstage], Cfg::STAGE_BYTES);
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
                 hi[c * 4 + 2] = __float_as_uint(u8_to_f32(wds[c], 2));
                 hi[c * 4 + 3] = __float_as_uint(u8_to_f32(wds[c], 3));
               }
-              if (!(p.dbg & 2)) tmem_st32(taddr, hi);
+              if (!(PAACB_DBGV(p.dbg) & 2)) tmem_st32(taddr, hi);
             } else {
               // TF32X3: hi = a with the 13 low mantissa bits cleared (1 LOP), lo = a - hi exactly (1 FADD); the tensor
               // core reads only the tf32 bits of lo, an error of 2^-21 |a|.  Plain TF32 rounds to nearest (2 integer ops).
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
                 hi[c * 4 + 2] = Cfg::A_LO ? (b[sb][c].z & 0xFFFFE000u) : tf32_rna_bits(b[sb][c].z);
                 hi[c * 4 + 3] = Cfg::A_LO ? (b[sb][c].w & 0xFFFFE000u) : tf32_rna_bits(b[sb][c].w);
               }
-              if (!(p.dbg & 2)) tmem_st32(taddr, hi);
+              if (!(PAACB_DBGV(p.dbg) & 2)) tmem_st32(taddr, hi);
               if constexpr (Cfg::A_LO) {
                 uint32_t lo[32];
 #pragma unroll
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
                   lo[c * 4 + 2] = __float_as_uint(__uint_as_float(b[sb][c].z) - __uint_as_float(hi[c * 4 + 2]));
                   lo[c * 4 + 3] = __float_as_uint(__uint_as_float(b[sb][c].w) - __uint_as_float(hi[c * 4 + 3]));
                 }
-                if (!(p.dbg & 2)) tmem_st32(taddr + 32u, lo);
+                if (!(PAACB_DBGV(p.dbg) & 2)) tmem_st32(taddr + 32u, lo);
               }
             }
           }
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
           tc_fence_after();
           const uint32_t b_st = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
           if (leader) {
-          if (!(p.dbg & 8)) {
+          if (!(PAACB_DBGV(p.dbg) & 8)) {
 #pragma unroll
           for (int sb = 0; sb < KSUB; ++sb) {
             const uint32_t b_hi = b_st + (uint32_t)(sb * Cfg::B_BYTES), b_lo = b_hi + (uint32_t)(KSUB * Cfg::B_BYTES);
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
           tmem_ld32(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
         }
-        if (ok && !(p.dbg & 16)) {
+        if (ok && !(PAACB_DBGV(p.dbg) & 16)) {
           float* dst = p.y + out_base + c0;
           if constexpr (MODE == TC_DGRAD) {
             const float* xa = (p.xact != nullptr) ? p.xact + out_base + c0 : nullptr;
@@ -528,15 +528,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const TcParams 
 template <int BN, int MODE, bool SPLIT, int KSUB>
 static int launch_tc_inst2(const paacb_ctx* ctx, const TcParams& p, int slot, cudaStream_t st) {
   using Cfg = TcCfg<BN, MODE, SPLIT, KSUB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;   // kernel attributes are per device: one bit per device index
+  if (!attr_set.done(ctx->device)) {
     if (cudaFuncSetAttribute(igemm_tc_kernel<BN, MODE, SPLIT, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess) {
       cudaGetLastError();
       set_error("igemm_tc: cannot set %d bytes of dynamic shared memory", Cfg::SMEM_BYTES);
       return PAACB_ECUDA;
     }
-    attr_set = true;
+    attr_set.mark(ctx->device);
   }
   const uint32_t tiles = p.m_tiles * (uint32_t)p.n_tiles * (uint32_t)p.classes;
   const unsigned grid = tiles < (uint32_t)ctx->num_sms ? tiles : (unsigned)ctx->num_sms;
@@ -551,7 +551,7 @@ static int launch_tc_inst(const paacb_ctx* ctx, const TcParams& p, int slot, int
   // K-blocks per pipeline stage: 4 for the uint8 layer (32-byte rows: small stages are all handshake); the fp32
   // layers measured faster with single-K-block stages (deeper TMEM / smem pipelines, fewer live registers)
   constexpr int KS = (MODE == TC_FWD_U8) ? 4 : 1;
-  if (KS > 1 && p.kblocks % KS == 0 && !(ctx->dbg & 32)) {
+  if (KS > 1 && p.kblocks % KS == 0 && !(PAACB_DBGV(ctx->dbg) & 32)) {
     return split3 ? launch_tc_inst2<BN, MODE, true, KS>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, KS>(ctx, p, slot, st);
   }
   return split3 ? launch_tc_inst2<BN, MODE, true, 1>(ctx, p, slot, st) : launch_tc_inst2<BN, MODE, false, 1>(ctx, p, slot, st);

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kOptThreads)
 clip_rmsprop_kernel(float* __restrict__ params, float* __restrict__ ms, float* __restrict__ mom,
                     const float* __restrict__ g, int64_t P, float gscale, float lr, float rho, float eps,
                     float momentum, float clip, int clip_type, const double* __restrict__ partials, int npartials,
-                    float* __restrict__ norm_out) {
+                    float* __restrict__ norm_out, const float* __restrict__ d_lr) {
+  if (d_lr != nullptr) lr = __ldg(d_lr);       // learning rate from device memory (graph replay)
   // ---- deterministic re-reduction of the partial sums (same order in every CTA) ----
   __shared__ double red[kOptThreads / 32];
   __shared__ float s_scale;
@@ -116,15 +117,23 @@ clip_rmsprop_kernel(float* __restrict__ params, float* __restrict__ ms, float* _
 // ---- fused cooperative version ------------------------------------------------------------------------------
 constexpr int kFusedVec = 4;      // float4 slices of the gradient per thread held in registers
 
-// Sense-free grid barrier on a monotonically increasing counter: every launch of this kernel uses the same grid size, so
-// the counter is a multiple of the grid size between launches and needs no reset.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nblocks) {
+// Self-resetting grid barrier on two words (arrival counter, generation): the last CTA to arrive zeroes the counter and
+// bumps the generation, the others spin on the generation they read BEFORE arriving.  No host-side bookkeeping, no
+// wrap-around, any grid size per launch: a captured CUDA graph of the update can be replayed indefinitely.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    volatile unsigned int* gen_p = bar + 1;
+    const unsigned int gen = *gen_p;
     __threadfence();
-    const unsigned int ticket = atomicAdd(counter, 1u);
-    const unsigned int target = ticket - (ticket % nblocks) + nblocks;
-    while ((int)(*reinterpret_cast<volatile unsigned int*>(counter) - target) < 0) __nanosleep(20);
+    const unsigned int ticket = atomicAdd(bar, 1u);
+    if (ticket == nblocks - 1u) {
+      *reinterpret_cast<volatile unsigned int*>(bar) = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen_p == gen) __nanosleep(20);
+    }
     __threadfence();
   }
   __syncthreads();
@@ -134,7 +143,8 @@ __global__ void __launch_bounds__(kOptThreads)
 clip_rmsprop_fused_kernel(float* __restrict__ params, float* __restrict__ ms, float* __restrict__ mom,
                           const float* __restrict__ g, int64_t P, float gscale, float lr, float rho, float eps,
                           float momentum, float clip, int clip_type, double* __restrict__ partials,
-                          unsigned int* __restrict__ counter, float* __restrict__ norm_out) {
+                          unsigned int* __restrict__ counter, float* __restrict__ norm_out, const float* __restrict__ d_lr) {
+  if (d_lr != nullptr) lr = __ldg(d_lr);       // learning rate from device memory (graph replay)
   const int64_t nvec = P >> 2;
   const int64_t nthreads = (int64_t)gridDim.x * kOptThreads;
   const int64_t t0 = (int64_t)blockIdx.x * kOptThreads + threadIdx.x;
@@ -238,6 +248,58 @@ clip_rmsprop_fused_kernel(float* __restrict__ params, float* __restrict__ ms, fl
   }
 }
 
+// ---- opt-in summaries (actor_learner.py:85-87 + logger_utils.py:23-33): sum, sum of squares, max and min of the flat
+// gradient in one pass.  The clipped gradient is the raw one times a non-negative scalar, so its four statistics follow
+// from these without a second pass.  Off the hot path: two small launches, only when the caller asks.
+__global__ void __launch_bounds__(kOptThreads)
+grad_stats_partials_kernel(const float* __restrict__ g, int64_t P, float gscale, double* __restrict__ partials) {
+  double s = 0.0, q = 0.0;
+  float mx = -INFINITY, mn = INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * kOptThreads + threadIdx.x; i < P; i += (int64_t)gridDim.x * kOptThreads) {
+    const float t = __ldg(g + i) * gscale;
+    s += (double)t;
+    q += (double)t * (double)t;
+    mx = fmaxf(mx, t);
+    mn = fminf(mn, t);
+  }
+  __shared__ double rs[kOptThreads / 32], rq[kOptThreads / 32];
+  __shared__ float rmx[kOptThreads / 32], rmn[kOptThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; rmx[threadIdx.x >> 5] = mx; rmn[threadIdx.x >> 5] = mn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < kOptThreads / 32; ++i) { s += rs[i]; q += rq[i]; mx = fmaxf(mx, rmx[i]); mn = fminf(mn, rmn[i]); }
+    partials[4 * blockIdx.x] = s; partials[4 * blockIdx.x + 1] = q; partials[4 * blockIdx.x + 2] = mx; partials[4 * blockIdx.x + 3] = mn;
+  }
+}
+__global__ void grad_stats_final_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0.0, q = 0.0, mx = -INFINITY, mn = INFINITY;
+  for (int i = 0; i < n; ++i) {
+    s += partials[4 * i]; q += partials[4 * i + 1];
+    mx = fmax(mx, partials[4 * i + 2]); mn = fmin(mn, partials[4 * i + 3]);
+  }
+  out[0] = s; out[1] = q; out[2] = mx; out[3] = mn;
+}
+
+int launch_grad_stats(const paacb_ctx* ctx, const float* grads, float gscale, float* ws, double* out4, cudaStream_t st) {
+  const int blocks = kMaxPartials / 4;           // 4 doubles per block inside the optimizer workspace
+  double* partials = reinterpret_cast<double*>(ws);
+  PAACB_LAUNCH_BEGIN(ctx, K_SUMSQ, st);
+  grad_stats_partials_kernel<<<blocks, kOptThreads, 0, st>>>(grads, ctx->param_count, gscale, partials);
+  PAACB_LAUNCH_END(ctx, K_SUMSQ, st);
+  PAACB_LAUNCH_BEGIN(ctx, K_SUMSQ, st);
+  grad_stats_final_kernel<<<1, 32, 0, st>>>(partials, blocks, out4);
+  PAACB_LAUNCH_END(ctx, K_SUMSQ, st);
+  return PAACB_OK;
+}
+
 int64_t optimizer_ws_floats(const paacb_ctx*) { return 2 * kMaxPartials + 4; }   // kMaxPartials doubles (+ spare)
 
 static int opt_blocks(const paacb_ctx* ctx, int64_t P) {
@@ -248,10 +310,10 @@ static int opt_blocks(const paacb_ctx* ctx, int64_t P) {
   return (int)want;
 }
 
-// cooperative grid of the fused kernel: as many CTAs as can be co-resident (capped by the partials buffer), queried once
+// cooperative grid of the fused kernel: as many CTAs as can be co-resident on the context's device (capped by the partials
+// buffer); queried once per context
 static int fused_blocks(const paacb_ctx* ctx) {
-  static int cached_dev = -1, cached = 0;
-  if (cached_dev == ctx->device) return cached;
+  if (ctx->opt_fused_blocks >= 0) return ctx->opt_fused_blocks;
   int per_sm = 0, coop = 0;
   if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device) != cudaSuccess || !coop ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_rmsprop_fused_kernel, kOptThreads, 0) != cudaSuccess) {
@@ -260,14 +322,13 @@ static int fused_blocks(const paacb_ctx* ctx) {
   }
   int64_t blocks = (int64_t)per_sm * ctx->num_sms;
   if (blocks > kMaxPartials) blocks = kMaxPartials;
-  cached_dev = ctx->device;
-  cached = (int)blocks;
-  return cached;
+  ctx->opt_fused_blocks = (int)blocks;
+  return ctx->opt_fused_blocks;
 }
 
 int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* mom, const float* grads, float gscale,
-                        float lr, float rho, float eps, float momentum, float clip, int clip_type, float* norm_out,
-                        float* ws, cudaStream_t st) {
+                        float lr, const float* d_lr, float rho, float eps, float momentum, float clip, int clip_type,
+                        float* norm_out, float* ws, cudaStream_t st) {
   int64_t P = ctx->param_count;
   double* partials = reinterpret_cast<double*>(ws);
   const int fused = (ctx->opt_counter != nullptr && !ctx->opt_two_pass) ? fused_blocks(ctx) : 0;
@@ -275,15 +336,9 @@ int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* m
     // no more CTAs than the register slices need: do not spin CTAs that hold no data
     int64_t need = ((P >> 2) + kOptThreads * kFusedVec - 1) / (kOptThreads * kFusedVec);
     int blocks = (int)(need < fused ? (need < 1 ? 1 : need) : fused);
-    if (ctx->opt_grid != 0 && ctx->opt_grid != blocks) blocks = ctx->opt_grid;      // the barrier counter assumes ONE grid size
-    ctx->opt_grid = blocks;
-    unsigned int* counter = ctx->opt_counter;
-    if (++ctx->opt_launches >= (1 << 20)) {      // keep the monotonic barrier counter far from wrapping
-      ctx->opt_launches = 0;
-      if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) { set_error("memset failed"); return PAACB_ECUDA; }
-    }
+    unsigned int* counter = ctx->opt_counter;      // self-resetting barrier: no host-side state, replay-safe
     void* args[] = {&params, &ms, &mom, &grads, &P, &gscale, &lr, &rho, &eps, &momentum, &clip, &clip_type, &partials,
-                    &counter, &norm_out};
+                    &counter, &norm_out, &d_lr};
     PAACB_LAUNCH_BEGIN(ctx, K_RMSPROP, st);
     const cudaError_t e = cudaLaunchCooperativeKernel((const void*)clip_rmsprop_fused_kernel, dim3((unsigned)blocks),
                                                       dim3(kOptThreads), args, 0, st);
@@ -301,7 +356,7 @@ int launch_clip_rmsprop(const paacb_ctx* ctx, float* params, float* ms, float* m
   PAACB_LAUNCH_END(ctx, K_SUMSQ, st);
   PAACB_LAUNCH_BEGIN(ctx, K_RMSPROP, st);
   clip_rmsprop_kernel<<<blocks, kOptThreads, 0, st>>>(params, ms, mom, grads, P, gscale, lr, rho, eps, momentum, clip,
-                                                      clip_type, partials, blocks, norm_out);
+                                                      clip_type, partials, blocks, norm_out, d_lr);
   PAACB_LAUNCH_END(ctx, K_RMSPROP, st);
   return PAACB_OK;
 }

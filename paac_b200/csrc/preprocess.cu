@@ -26,17 +26,30 @@ __device__ __forceinline__ uint4 shr8(uint4 v) { return make_uint4(v.x >> 8, v.y
 
 __global__ void __launch_bounds__(kThreads)
 preprocess_u8_kernel(const uint8_t* __restrict__ frames, int pairs, const uint8_t* __restrict__ reset,
-                     const uint8_t* prev, uint8_t* next, ResizeTables tabs, int64_t n_envs) {
+                     const uint8_t* prev, uint8_t* next, ResizeTables tabs, int64_t n_envs, const StepScalars sc) {
   __shared__ __align__(16) uint8_t plane[PAACB_OBS * PAACB_FRAME_W];
   __shared__ int s_row[PAACB_OBS];
   __shared__ int s_col[PAACB_OBS];
+  __shared__ int s_rst;
   const int tid = threadIdx.x;
   if (tid < PAACB_OBS) {
     s_row[tid] = tabs.row[tid] * PAACB_FRAME_W;
     s_col[tid] = tabs.col[tid];
   }
   for (int64_t env = blockIdx.x; env < n_envs; env += gridDim.x) {
-  const bool rst = (reset != nullptr) && (pairs >= PAACB_STACK) && (reset[env] != 0);
+  if (sc.over_in != nullptr) {
+    // paacb_observe_u8: this step's reward and episode-over flag go into their row of the rollout buffers in the same
+    // launch (paac.py:119-123), and the flag is the reset flag of emulator_runner.py:26-27 (one load, shared by the CTA)
+    __syncthreads();                       // the previous environment's s_rst has been consumed
+    if (tid == 0) {
+      const float ov = sc.over_in[env];
+      sc.over_out[env] = ov;
+      sc.rewards_out[env] = sc.rewards_in[env];
+      s_rst = (sc.over_is_reset && ov != 0.f) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  const bool rst = (pairs >= PAACB_STACK) && (((reset != nullptr) && (reset[env] != 0)) || (sc.over_in != nullptr && s_rst != 0));
   const uint4* prev4 = reinterpret_cast<const uint4*>(prev + env * (int64_t)(kStateVec * 16));
   uint4* next4 = reinterpret_cast<uint4*>(next + env * (int64_t)(kStateVec * 16));
 
@@ -87,26 +100,34 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int pairs, const uint8_
 }
 
 int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
-                      const uint8_t* prev, uint8_t* next, int64_t n, cudaStream_t st) {
+                      const uint8_t* prev, uint8_t* next, int64_t n, const StepScalars& sc, cudaStream_t st) {
   if (n == 0) return PAACB_OK;
   // Frames in pinned, mapped HOST memory (the runners' buffers, read zero-copy): the kernel is PCIe-bound and needs only
   // ~100 KB of loads in flight, so it runs as a narrow grid-stride grid (one CTA on a subset of the SMs) that leaves
   // room for the persistent tensor-core kernels of the next environment slice to run beside it.  Device-resident frames:
   // HBM-bound, one CTA per environment.
   unsigned grid = (unsigned)n;
-  cudaPointerAttributes attr;
-  if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess) {
-    if (attr.type == cudaMemoryTypeHost) {
-      unsigned narrow = 96;
-      const char* knob = getenv("PAACB_K1_HOST_GRID");      // tuning knob for tools/experiments/pcie_probe.py
-      if (knob != nullptr && atoi(knob) > 0) narrow = (unsigned)atoi(knob);
-      if (n > narrow) grid = narrow;
-    }
-  } else {
-    cudaGetLastError();
+  // is the frame buffer host memory?  The answer is cached per 2 MB-aligned address range the caller has used (a runner's
+  // buffer is registered once and then read every step: no driver query on the hot path)
+  int is_host = -1;
+  const uintptr_t key = (uintptr_t)frames >> 21;
+  for (int i = 0; i < ctx->k1_cache_n; ++i)
+    if (ctx->k1_cache_key[i] == key) { is_host = ctx->k1_cache_host[i]; break; }
+  if (is_host < 0) {
+    cudaPointerAttributes attr;
+    is_host = 0;
+    if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess) is_host = (attr.type == cudaMemoryTypeHost) ? 1 : 0;
+    else cudaGetLastError();
+    const int slot = ctx->k1_cache_n < paacb_ctx::kK1Cache ? ctx->k1_cache_n++ : (int)(key % paacb_ctx::kK1Cache);
+    ctx->k1_cache_key[slot] = key;
+    ctx->k1_cache_host[slot] = is_host;
+  }
+  if (is_host) {
+    unsigned narrow = (unsigned)ctx->k1_host_grid;
+    if (n > narrow) grid = narrow;
   }
   PAACB_LAUNCH_BEGIN(ctx, K_PREPROCESS, st);
-  preprocess_u8_kernel<<<grid, kThreads, 0, st>>>(frames, pairs, reset, prev, next, ctx->tabs, n);
+  preprocess_u8_kernel<<<grid, kThreads, 0, st>>>(frames, pairs, reset, prev, next, ctx->tabs, n, sc);
   PAACB_LAUNCH_END(ctx, K_PREPROCESS, st);
   return PAACB_OK;
 }

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
 #pragma unroll 1
           for (int piece = 0; piece < (Ge::A_LO ? 2 : 1); ++piece) {
             mbar_wait(&empty_bar[slot], phase ^ 1u);
-            if (p.dbg & 1024) { mbar_arrive(&full_bar[slot]); if (++slot == NSLOTS) { slot = 0; phase ^= 1u; } continue; }
+            if (PAACB_DBGV(p.dbg) & 1024) { mbar_arrive(&full_bar[slot]); if (++slot == NSLOTS) { slot = 0; phase ^= 1u; } continue; }
             mbar_arrive_expect_tx(&full_bar[slot], Cfg::BOX_BYTES);
             uint8_t* dst = ring + slot * Ge::SLOT;
             if constexpr (Ge::DGRAD) {
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
               const int jw = Ge::jw(part, t);
               const uint64_t bd = desc_with_addr(bdesc0, w_a + (uint32_t)((jw / 4) * Cfg::KB_BYTES + (jw % 4) * 32));
               if (piece == 0) umma_bf16(d0, ad, bd, idesc_full, (part | t) ? 1u : 0u);    // A_hi * [W_hi | W_lo]
-              else if (!(p.dbg & 256)) umma_bf16(d0, ad, bd, idesc_half, 1u);              // A_lo * W_hi
+              else if (!(PAACB_DBGV(p.dbg) & 256)) umma_bf16(d0, ad, bd, idesc_half, 1u);              // A_lo * W_hi
             }
             umma_commit(&empty_bar[slot]);
           }
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
         uint8_t* tile_p = stg + ph * Cfg::STG_TILE;
         const uint32_t t_row = stg_a + (uint32_t)(ph * Cfg::STG_TILE) + srow * 128u;
         uint32_t lw[2][16];
-        const bool direct_hi = (p.dbg & 8192) != 0;                         // experiment: no staging at all
+        const bool direct_hi = (PAACB_DBGV(p.dbg) & 8192) != 0;                         // experiment: no staging at all
         if (!direct_hi) {
           if (io) tma_store_wait_read();                                    // previous tile's hi plane has been read out
           named_bar_sync(1 + ph, 128);
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
 #pragma unroll
         for (int j = 0; j < 32; ++j) o[0][j] += o[1][j];
         bsum += warp_transpose_sum(o[0], lane);
-        if (p.dbg & 4096) {
+        if (PAACB_DBGV(p.dbg) & 4096) {
           // (first staged version, kept for A/B timing: the lo plane follows the hi plane through the same staging tile --
           // two more barriers and a second wait for the TMA engine per tile)
           if (io) tma_store_wait_read();
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
             split_bf16x2(o0, o1, hw[2 * j], lw[2 * j]);
             split_bf16x2(o2, o3, hw[2 * j + 1], lw[2 * j + 1]);
           }
-          if (ok && !(p.dbg & 512)) {
+          if (ok && !(PAACB_DBGV(p.dbg) & 512)) {
             uint8_t* dh = p.out_hi + (pix * BN + c * 32) * 2;
             uint8_t* dl = p.out_lo + (pix * BN + c * 32) * 2;
 #pragma unroll
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
               o[2 * j + 1] = (ok && a1 != 0u && a1 < 0x8000u) ? __uint_as_float(v[2 * j + 1]) : 0.f;
             }
           }
-          if (ok && !(p.dbg & 512)) {
+          if (ok && !(PAACB_DBGV(p.dbg) & 512)) {
             uint32_t hw[16], lw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) split_bf16x2(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
@@ -708,8 +708,8 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
 template <int G>
 static int launch_convk(const paacb_ctx* ctx, const ConvKParams& p, int slot, cudaStream_t st) {
   using Cfg = ConvKCfg<G>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;   // kernel attributes are per device: one bit per device index
+  if (!attr_set.done(ctx->device)) {
     if (cudaFuncSetAttribute(convk_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
       cudaGetLastError();
       set_error("convk<%d>: cannot set %d bytes of dynamic shared memory", G, Cfg::SMEM_BYTES);
@@ -719,7 +719,7 @@ static int launch_convk(const paacb_ctx* ctx, const ConvKParams& p, int slot, cu
     // on conv1 forward: the same code ran 10 % slower when its request dropped from 160 KB to 86 KB)
     cudaFuncSetAttribute(convk_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
-    attr_set = true;
+    attr_set.mark(ctx->device);
   }
   const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, slot, st);

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(C1<NC>::THREADS, 1) conv1_i8_kernel(const __gr
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&empty_bar[slot], phase ^ 1u);
-        if (p.dbg & 8) { mbar_arrive(&full_bar[slot]); if (++slot == kC1_NSLOTS) { slot = 0; phase ^= 1u; } continue; }
+        if (PAACB_DBGV(p.dbg) & 8) { mbar_arrive(&full_bar[slot]); if (++slot == kC1_NSLOTS) { slot = 0; phase ^= 1u; } continue; }
         mbar_arrive_expect_tx(&full_bar[slot], kC1_BOX);
         tma_load_3d(ring + slot * kC1_SLOT, &p.tmA, 0, tile * kC1_TROWS, 0, &full_bar[slot]);
         if (++slot == kC1_NSLOTS) { slot = 0; phase ^= 1u; }
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(C1<NC>::THREADS, 1) conv1_i8_kernel(const __gr
       tc_fence_after();
       if (leader) {
 #pragma unroll
-        for (int kh = 0; kh < ((p.dbg & 4) ? 1 : 8); ++kh) {           // filter row kh: parity plane kh & 3, one plane row further down for kh >= 4
+        for (int kh = 0; kh < ((PAACB_DBGV(p.dbg) & 4) ? 1 : 8); ++kh) {           // filter row kh: parity plane kh & 3, one plane row further down for kh >= 4
           const uint32_t a = ring_a + (uint32_t)(slot * kC1_SLOT + (kh & 3) * kC1_PLANE + (kh >> 2) * kC1_WU * 16);
           const uint64_t bd = desc_with_addr(bdesc0, w_a + (uint32_t)((kh / 4) * (kC1_ND * 128) + (kh % 4) * 32));
           umma_i8(d0, desc_with_addr(adesc0, a), bd, idesc, kh ? 1u : 0u);
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(C1<NC>::THREADS, 1) conv1_i8_kernel(const __gr
       mbar_arrive(&tempty_bar[grp]);           // the accumulator is in registers: release the buffer before the arithmetic
       uint32_t hw[8], lw[8];
       float of[F32OUT ? 16 : 1];
-      if (p.dbg & 2) {
+      if (PAACB_DBGV(p.dbg) & 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { hw[j] = v0[2 * j] ^ v1[2 * j + 1]; lw[j] = v2[2 * j] ^ v0[2 * j + 1]; }
       } else
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(C1<NC>::THREADS, 1) conv1_i8_kernel(const __gr
         if constexpr (F32OUT) { of[2 * j] = o[0]; of[2 * j + 1] = o[1]; }
         else split_bf16x2(o[0], o[1], hw[j], lw[j]);
       }
-      if (ok && !(p.dbg & 1)) {                 // 16 channels = one full 32-byte sector per plane
+      if (ok && !(PAACB_DBGV(p.dbg) & 1)) {                 // 16 channels = one full 32-byte sector per plane
         const uint32_t oh = g - n * (uint32_t)kC1_HQ;
         const int64_t oe = (((int64_t)n * kC1_OH + oh) * kC1_OW + ju) * NC + half * 16;      // element index
         if constexpr (F32OUT) {
@@ -277,8 +277,8 @@ static int launch_conv1_inst(const paacb_ctx* ctx, const float* params, const ui
   const int64_t plane_rows = batch * kC1_HQ;
   if (plane_rows * kC1_WU >= (1LL << 31) - 256) return PAACB_EUNSUPPORTED;
   constexpr int SMEM = kC1_SMEM_FIXED + C1<NC>::WBYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;   // kernel attributes are per device: one bit per device index
+  if (!attr_set.done(ctx->device)) {
     if (cudaFuncSetAttribute(conv1_i8_kernel<NC, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       cudaGetLastError();
       set_error("conv1_i8: cannot set %d bytes of dynamic shared memory", SMEM);
@@ -288,7 +288,7 @@ static int launch_conv1_inst(const paacb_ctx* ctx, const float* params, const ui
     // on conv1 forward: the same code ran 10 % slower when its request dropped from 160 KB to 86 KB)
     cudaFuncSetAttribute(conv1_i8_kernel<NC, F32OUT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
-    attr_set = true;
+    attr_set.mark(ctx->device);
   }
   Conv1Params p;
   memset(&p, 0, sizeof(p));

@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_gemm_kernel(const __
 template <int BN, int MODE>
 static int launch_stream(const paacb_ctx* ctx, const StreamParams& p, int slot, cudaStream_t st) {
   using Cfg = StreamCfg<BN, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;   // kernel attributes are per device: one bit per device index
+  if (!attr_set.done(ctx->device)) {
     if (cudaFuncSetAttribute(stream_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
         cudaSuccess) {
       cudaGetLastError();
@@ -328,7 +328,7 @@ static int launch_stream(const paacb_ctx* ctx, const StreamParams& p, int slot, 
     // on conv1 forward: the same code ran 10 % slower when its request dropped from 160 KB to 86 KB)
     cudaFuncSetAttribute(stream_gemm_kernel<BN, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
-    attr_set = true;
+    attr_set.mark(ctx->device);
   }
   const int units = p.m_tiles * p.n_tiles * p.k_splits;
   const unsigned grid = (unsigned)(units < ctx->num_sms ? units : ctx->num_sms);

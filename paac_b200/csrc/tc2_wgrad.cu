@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
       uint32_t phase = 0;
       for (int s = s_begin; s < s_end; ++s) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (p.dbg & 32) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1u; } continue; }
+        if (PAACB_DBGV(p.dbg) & 32) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1u; } continue; }
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
         uint8_t* a = a_sm + stage * Cfg::A_STAGE;
         uint8_t* b = b_sm + stage * Cfg::B_STAGE;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
         const uint32_t first = (s == s_begin) ? 0u : 1u;
 #pragma unroll
         for (int kt = 0; kt < W::KT; ++kt) {
-          if ((p.dbg & 128) && kt >= W::KT / 2) continue;
+          if ((PAACB_DBGV(p.dbg) & 128) && kt >= W::KT / 2) continue;
           const uint32_t d = tmem_base + (uint32_t)(kt * Cfg::ACC_COLS);
           const uint64_t adesc0 = make_smem_desc(0, (uint32_t)W::a_lbo(kt), W::A_SBO, W::A_SWZ);
           uint32_t a_hi, a_lo = 0;
@@ -218,10 +218,10 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
               umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc_full, t > 0 ? 1u : first);
             } else {
               umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, t > 0 ? 1u : first);
-              if (!(p.dbg & 16)) umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_lo + bo), idesc, 1u);
+              if (!(PAACB_DBGV(p.dbg) & 16)) umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_lo + bo), idesc, 1u);
             }
             if constexpr (W::A_PIECES == 2)
-              if (!(p.dbg & 16)) umma_bf16(d, desc_with_addr(adesc0, a_lo + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, 1u);
+              if (!(PAACB_DBGV(p.dbg) & 16)) umma_bf16(d, desc_with_addr(adesc0, a_lo + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, 1u);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
           const int w = ct + i * Cfg::CONV_THREADS;
           const int R = row0 + w / 21, u = w % 21;
           const int n = R / 21, q = R - n * 21;
-          const bool ok = (w < UNITS) && (s < s_end) && (n < p.batch) && !(p.dbg & 64);
+          const bool ok = (w < UNITS) && (s < s_end) && (n < p.batch) && !(PAACB_DBGV(p.dbg) & 64);
 #pragma unroll
           for (int part = 0; part < 4; ++part) {
             b[part][i] = make_uint4(0u, 0u, 0u, 0u);
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
 #pragma unroll
           for (int i = 0; i < UPT; ++i) {
             const int w = ct + i * Cfg::CONV_THREADS;
-            if (w < UNITS && !(p.dbg & 64)) {
+            if (w < UNITS && !(PAACB_DBGV(p.dbg) & 64)) {
               const uint32_t wd[4] = {b[part][i].x, b[part][i].y, b[part][i].z, b[part][i].w};
               uint32_t o[8];
 #pragma unroll
@@ -350,8 +350,8 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
 template <int L>
 static int launch_wg2(const paacb_ctx* ctx, const Wg2Params& p, cudaStream_t st) {
   using Cfg = Wg2Cfg<L>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;   // kernel attributes are per device: one bit per device index
+  if (!attr_set.done(ctx->device)) {
     if (cudaFuncSetAttribute(wgrad2_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) {
       cudaGetLastError();
       set_error("wgrad2<%d>: cannot set %d bytes of dynamic shared memory", L, Cfg::SMEM_BYTES);
@@ -361,7 +361,7 @@ static int launch_wg2(const paacb_ctx* ctx, const Wg2Params& p, cudaStream_t st)
     // on conv1 forward: the same code ran 10 % slower when its request dropped from 160 KB to 86 KB)
     cudaFuncSetAttribute(wgrad2_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
-    attr_set = true;
+    attr_set.mark(ctx->device);
   }
   const unsigned grid = (unsigned)(p.stages_total < ctx->num_sms ? p.stages_total : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, K_WGRAD0 + L, st);

@@ -397,14 +397,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgParams 
 template <int BN, bool U8, bool SPLIT>
 static int launch_wg_inst(const paacb_ctx* ctx, const WgParams& p, cudaStream_t st) {
   using Cfg = WgCfg<BN, U8, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;   // kernel attributes are per device: one bit per device index
+  if (!attr_set.done(ctx->device)) {
     if (cudaFuncSetAttribute(wgrad_tc_kernel<BN, U8, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess) {
       set_error("wgrad_tc: cannot set %d bytes of dynamic shared memory", Cfg::SMEM_BYTES);
       return PAACB_ECUDA;
     }
-    attr_set = true;
+    attr_set.mark(ctx->device);
   }
   const int64_t units = (int64_t)p.k_tiles * p.n_tiles * p.splits;
   const unsigned grid = (unsigned)(units < ctx->num_sms ? units : ctx->num_sms);

@@ -163,15 +163,23 @@ class Network(object):
     def workspace_floats(self, batch):
         return int(self._lib.paacb_forward_workspace_floats(self.ctx, int(batch)))
 
-    def forward(self, states, pi, v, ws, uniforms=None, actions=None, onehot=None, ws_capacity=None, ws_first=0):
+    def forward(self, states, pi, v, ws, uniforms=None, actions=None, onehot=None, ws_capacity=None, ws_first=0,
+                rng=None, draw=0, first_sample=0):
         """Asynchronous forward on the current torch stream; all arguments are CUDA tensors.
-        ws_capacity / ws_first: write samples [ws_first, ws_first + b) of a workspace laid out for ws_capacity samples."""
+        ws_capacity / ws_first: write samples [ws_first, ws_first + b) of a workspace laid out for ws_capacity samples.
+        Sampling: ``uniforms`` (float32 [b], injected) or ``rng`` (int64 [2] device tensor {seed, draw base}: the heads kernel
+        draws Philox uniforms itself for draw index ``draw`` and global sample indices first_sample .. first_sample + b)."""
         b = states.shape[0]
-        st = torch.cuda.current_stream(self.torch_device).cuda_stream
+        st = C.c_void_p(torch.cuda.current_stream(self.torch_device).cuda_stream)
         p = _lib.ptr
-        _lib.check(self._lib.paacb_policy_forward_at(self.ctx, p(self.params), p(states), b, p(ws),
-                                                     b if ws_capacity is None else int(ws_capacity), int(ws_first),
-                                                     p(pi), p(v), p(uniforms), p(actions), p(onehot), C.c_void_p(st)),
+        cap = b if ws_capacity is None else int(ws_capacity)
+        if rng is not None:
+            _lib.check(self._lib.paacb_policy_forward_sample(self.ctx, p(self.params), p(states), b, p(ws), cap, int(ws_first),
+                                                             p(pi), p(v), p(rng), int(draw), int(first_sample), p(actions),
+                                                             p(onehot), st), 'paacb_policy_forward_sample')
+            return
+        _lib.check(self._lib.paacb_policy_forward_at(self.ctx, p(self.params), p(states), b, p(ws), cap, int(ws_first),
+                                                     p(pi), p(v), p(uniforms), p(actions), p(onehot), st),
                    'paacb_policy_forward_at')
 
     def launch_count(self):

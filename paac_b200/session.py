@@ -60,12 +60,14 @@ class Saver(object):
     """tf.train.Saver stand-in (actor_learner.py:79-93).  Checkpoints are TensorFlow-1 tensor bundles
     (``<folder>/-<step>.index`` + ``.data-00000-of-00001`` + the ``checkpoint`` state file, tf_bundle.py) holding the
     variables under the reference's names -- ``<name>_1/conv1_weights`` ... for the trunk, ``<name>_2/actor_output_*`` /
-    ``critic_output_*`` for the heads, ``.../OptimizerVariables[_1]`` for the RMSProp slots -- so the
-    folders are interchangeable with the reference's ``pretrained/*`` layout.  ``max_to_keep`` honoured; ``.pt`` files
+    ``critic_output_*`` for the heads, ``.../OptimizerVariables[_1]`` for the RMSProp slots (the network
+    bundle carries them as well, like the reference's ``tf.train.Saver()``) -- so the folders are interchangeable with the
+    reference's ``pretrained/*`` layout in both directions.  ``max_to_keep`` honoured; ``.pt`` files
     written by earlier versions are still restored."""
 
-    def __init__(self, get_state, set_state, max_to_keep=5, name='Saver', scope='local_learning'):
+    def __init__(self, get_state, set_state, max_to_keep=5, name='Saver', scope='local_learning', optional=None):
         self.get_state, self.set_state, self.max_to_keep, self.name, self.scope = get_state, set_state, max_to_keep, name, scope
+        self.optional = optional or (lambda key: False)      # keys a checkpoint may lack (restore passes what it finds)
 
     def _tf_name(self, key):
         base = key.split('/')[0]
@@ -112,7 +114,7 @@ class Saver(object):
         tensors = tf_bundle.read_bundle(path)
         wanted = self.get_state().keys()
         by_key = {name.split('/', 1)[1]: torch.from_numpy(a) for name, a in tensors.items() if '/' in name}
-        missing = [k for k in wanted if k not in by_key]
+        missing = [k for k in wanted if k not in by_key and not self.optional(k)]
         if missing:
             raise KeyError('checkpoint %s lacks variables %s' % (path, missing[:4]))
-        self.set_state({k: by_key[k] for k in wanted})
+        self.set_state({k: by_key[k] for k in wanted if k in by_key})

@@ -1,6 +1,7 @@
 """train.py mirror (train.py:14-109): same flag names, dests and defaults, same
 ``get_network_and_environment_creator`` / ``main``.  Additions are additive flags only:
-``--math`` (fp32 | tf32x3 | tf32 | bf16x3), ``--raw_frames``, ``--synthetic_actions``, and multi-GPU launch through
+``--math`` (fp32 | tf32x3 | tf32 | bf16x3), ``--raw_frames``, ``--train_forward``, ``--graphs``, ``--summaries``,
+``--synthetic_actions``, and multi-GPU launch through
 torchrun (one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK read from the environment).
 
     python -m paac_b200.train -g synthetic -d /gpu:0 --arch NATURE -ec 32 -ew 8
@@ -116,6 +117,10 @@ def get_arg_parser():
     # ---- additions (not in the reference) ----
     parser.add_argument('--math', default='auto', choices=['auto', 'fp32', 'tf32x3', 'tf32', 'bf16x3'], help="Arithmetic of the conv/fc contractions", dest="math")
     parser.add_argument('--raw_frames', default=True, type=bool_arg, help="Workers write raw frame pairs; the GPU does max-pool/resize/stack", dest="raw_frames")
+    parser.add_argument('--train_forward', default='reuse', choices=['reuse', 'stepwise', 'batched'], help="Schedule of the training forward (bit-identical results): reuse the acting forwards' activations, issue it per step on a side stream, or run it inside the update like the reference", dest="train_forward")
+    parser.add_argument('--graphs', default='auto', choices=['auto', 'true', 'false'], help="Replay act/update as CUDA graphs (auto: when <= 1024 environments per GPU)", dest="graphs")
+    parser.add_argument('--summaries', default=False, type=bool_arg, help="Write per-update gradient statistics and episode scalars as JSONL under the debugging folder (the reference's TensorBoard summaries, opt-in)", dest="summaries")
+    parser.add_argument('--summary_interval', default=100, type=int, help="Updates between gradient-statistics records", dest="summary_interval")
     parser.add_argument('--synthetic_actions', default=6, type=int, help="num_actions of the synthetic environment", dest="synthetic_actions")
     return parser
 

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_version_and_error_channel(lib):
-    assert lib.paacb_version() == 101
+    assert lib.paacb_version() == 102
     h = C.c_void_p()
     rc = lib.paacb_create(C.byref(h), 7, 6, 0)    # bad arch -> EINVAL, message set, no exception
     assert rc == -1 and b'arch' in lib.paacb_last_error()

@@ -1,15 +1,19 @@
-"""GPU: the update path at BASELINE.json's full size (cfg3: NatureNetwork, 4096 envs, t_max 5, B = 20,480) through
-size-independent properties -- the CPU oracle takes minutes at this size, so the checks are: schedule invariance of the
-forward (bit-exact), determinism, linearity of the backward, closed forms of the returns recurrence and of the first
-RMSProp step, all evaluated with torch ops on the GPU."""
+"""GPU: the update path at BASELINE.json's full size (cfg3: NatureNetwork, 4096 envs, t_max 5, B = 20,480).
+  * against the oracle: 64 random samples of the benchmarked bf16x3 cycle -- every layer's activations, pi and v -- vs the
+    fp64 restatement (oracle.network.forward), and the FULL-size gradient / pi / v vs the fp32 SIMT anchor (itself
+    oracle-checked at small sizes) run on the same 20,480-sample batch;
+  * size-independent properties: schedule invariance of the forward (bit-exact), determinism, linearity of the backward,
+    closed forms of the returns recurrence and of the first RMSProp step, evaluated with torch ops on the GPU."""
 import ctypes as C
 
 import numpy as np
 import pytest
 import torch
 
+from oracle import network
 from paac_b200 import _lib
 from paac_b200.engine import RolloutEngine
+from util import assert_close
 import gpu_util as G
 
 pytestmark = pytest.mark.gpu
@@ -31,7 +35,7 @@ def run_cycle(mode, rollout, lr=0.0224, scale=1.0):
     states, rewards, over = rollout
     net = G.make_net(ARCH, A, seed=5, math='bf16x3')
     eng = RolloutEngine(net, N, T, seed=9, train_forward=mode)
-    eng.states.copy_(states)
+    eng.set_states(states)
     eng.draw_uniforms()
     for t in range(T):
         eng.act(t)
@@ -40,7 +44,7 @@ def run_cycle(mode, rollout, lr=0.0224, scale=1.0):
             eng.train_forward_step(t, 1000, N)
     eng.rewards.copy_(rewards * scale); eng.over.copy_(over)
     p0 = net.params.clone()
-    eng.update(lr)
+    eng.update(lr, roll=False)           # keep this rollout's states addressable for the checks below
     torch.cuda.synchronize()
     return net, eng, p0
 
@@ -82,7 +86,7 @@ def test_backward_is_linear_in_the_head_gradients_at_full_size(rollout):
     B = N * T
     p = _lib.ptr
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    flat = eng.states[:T].view((B, 84, 84, 4))
+    flat = eng.flat_states
     # two backward passes over the cycle's own workspace under the same (post-update) parameters: dlogits, dv and 4 x them
     dl4, dv4 = eng.dlogits * 4.0, eng.dv * 4.0
     _lib.check(net._lib.paacb_backward(net.ctx, p(net.params), p(flat), B, p(eng.fwd_ws), p(dl4), p(dv4), p(eng.bwd_ws),
@@ -111,3 +115,41 @@ def test_first_rmsprop_step_closed_form_at_full_size(rollout):
     err = (net.params - want).abs().max().item()
     assert err <= 1e-6 * want.abs().max().item() + 1e-9
     assert torch.allclose(eng.ms, ms, rtol=1e-6, atol=1e-9)
+
+
+def test_full_size_cycle_vs_oracle_and_fp32_anchor(rollout):
+    """The benchmarked configuration itself (cfg3, bf16x3, B = 20,480), not a scaled-down stand-in."""
+    net, eng, p0 = run_cycle('batched', rollout)
+    B = N * T
+    flat = eng.flat_states
+    p0_np = p0.cpu().numpy()
+    params = network.unflatten_params(p0_np, ARCH, A)
+    # (1) 64 random samples of the training batch against the fp64 oracle
+    idx = np.sort(np.random.RandomState(1).choice(B, 64, replace=False))
+    tidx = torch.from_numpy(idx).cuda()
+    ref = network.forward(params, flat[tidx].cpu().numpy(), ARCH, dtype=torch.float64, keep=True)
+    layers = [t[tidx].cpu().numpy() for t in net.layer_tensors(eng.fwd_ws, B)]
+    for i, a in enumerate(ref['acts']):
+        assert_close(layers[i], a.numpy(), 1e-4, 'full-size conv%d activation (64 samples)' % (i + 1))
+    assert_close(layers[-1], ref['h'].numpy(), 1e-4, 'full-size hidden fc (64 samples)')
+    assert_close(eng.pi[tidx].cpu().numpy(), ref['pi'].numpy(), 1e-4, 'full-size pi (64 samples)')
+    assert_close(eng.v[tidx].cpu().numpy(), ref['v'].numpy(), 1e-4, 'full-size v (64 samples)')
+    del layers
+    # (2) the whole batch against the fp32 SIMT anchor: forward outputs and the flat gradient from the SAME dlogits / dv
+    net32 = G.make_net(ARCH, A, seed=5, math='fp32')
+    net32.set_params(p0_np)
+    pi32 = torch.empty((B, A), device='cuda'); v32 = torch.empty((B,), device='cuda')
+    ws32 = torch.empty((net32.workspace_floats(B),), device='cuda')
+    net32.forward(flat, pi32, v32, ws32)
+    bws32 = torch.empty((int(net32._lib.paacb_backward_workspace_floats(net32.ctx, B)),), device='cuda')
+    g32 = torch.empty((net32.param_count,), device='cuda')
+    p = _lib.ptr
+    _lib.check(net32._lib.paacb_backward(net32.ctx, p(net32.params), p(flat), B, p(ws32), p(eng.dlogits), p(eng.dv), p(bws32),
+                                         p(g32), C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'paacb_backward')
+    torch.cuda.synchronize()
+    assert_close(eng.pi.cpu().numpy(), pi32.cpu().numpy(), 1e-4, 'full-size pi vs fp32 anchor')
+    assert_close(eng.v.cpu().numpy(), v32.cpu().numpy(), 1e-4, 'full-size v vs fp32 anchor')
+    got = network.unflatten_params(eng.grads.cpu().numpy(), ARCH, A)
+    want = network.unflatten_params(g32.cpu().numpy(), ARCH, A)
+    for name, _, _ in network.param_specs(ARCH, A):
+        assert_close(got[name], want[name], 1e-4, 'full-size gradient ' + name)

@@ -29,7 +29,7 @@ def test_train_raw_and_classic_protocols_agree(tmp_path):
         assert learner.global_step == 8 * 5 * 3
         loss = float(learner.last_loss.item())
         assert np.isfinite(loss) and np.isfinite(float(learner.last_norm.item()))
-        results.append((learner.engine.states.cpu().numpy(), learner.network.get_params(), loss))
+        results.append((learner.engine.get_states().cpu().numpy(), learner.network.get_params(), loss))
         assert learner.network.launch_count() > 0
     # same seeds, same sampled actions => the GPU-preprocessed states equal the host-preprocessed ones, bit for bit
     assert np.array_equal(results[0][0], results[1][0])

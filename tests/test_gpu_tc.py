@@ -76,7 +76,7 @@ def test_engine_update_tc_vs_oracle_composite(math):
     eng = RolloutEngine(net, N, T, seed=9)
     rng = np.random.RandomState(0)
     states = rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)
-    eng.states.copy_(G.dev(states))
+    eng.set_states(G.dev(states))
     eng.draw_uniforms()
     for t in range(T):
         eng.act(t)
@@ -121,7 +121,7 @@ def test_sliced_act_observe_equals_whole_batch():
     for slices in ([(0, N)], [(0, 8), (8, 24)]):
         net = G.make_net(arch, A, seed=5, math='bf16x3')
         eng = RolloutEngine(net, N, T, seed=9)
-        eng.states[0].copy_(G.dev(s0))
+        eng.state(0).copy_(G.dev(s0))
         eng.draw_uniforms()
         for t in range(T):
             for lo, hi in slices:
@@ -129,7 +129,7 @@ def test_sliced_act_observe_equals_whole_batch():
             for lo, hi in slices:
                 eng.observe_frames(t, frames[t, lo].data_ptr(), 1, None, rew[t], over[t], lo, hi)
         torch.cuda.synchronize()
-        outs.append((eng.actions.cpu().numpy(), eng.values.cpu().numpy(), eng.states.cpu().numpy(), eng.rewards.cpu().numpy()))
+        outs.append((eng.actions.cpu().numpy(), eng.values.cpu().numpy(), eng.get_states().cpu().numpy(), eng.rewards.cpu().numpy()))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][2], outs[1][2])
     assert np.array_equal(outs[0][3], outs[1][3])
     assert_close(outs[1][1], outs[0][1], 1e-6, 'values of sliced vs whole-batch forward')
@@ -150,7 +150,7 @@ def test_training_forward_schedules_are_bit_identical(math):
     for mode in ('batched', 'stepwise', 'reuse'):
         net = G.make_net(arch, A, seed=5, math=math)
         eng = RolloutEngine(net, N, T, seed=9, train_forward=mode)
-        eng.states.copy_(G.dev(states))
+        eng.set_states(G.dev(states))
         eng.draw_uniforms()
         for t in range(T):
             eng.act(t, 0, 16)
@@ -205,7 +205,7 @@ def test_cached_weight_images_follow_the_parameters():
     assert not np.array_equal(v0, v1)
     # an update through the library refreshes the images in-stream
     eng = RolloutEngine(net, N, T, seed=9)
-    eng.states.copy_(G.dev(rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)))
+    eng.set_states(G.dev(rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)))
     eng.draw_uniforms()
     for t in range(T):
         eng.act(t)
@@ -230,7 +230,7 @@ def test_sliced_bootstrap_equals_whole_batch():
     for sliced in (False, True):
         net = G.make_net(arch, A, seed=5, math='bf16x3')
         eng = RolloutEngine(net, N, T, seed=9)
-        eng.states.copy_(G.dev(states))
+        eng.set_states(G.dev(states))
         eng.draw_uniforms()
         for t in range(T):
             eng.act(t)

@@ -147,22 +147,24 @@ def test_fused_optimizer_equals_two_pass_bitwise(arch, monkeypatch):
         assert a[3] == b[3]
 
 
-def test_two_updates_match_reference_tf_graph(golden_dir):
-    """The same two train steps the reference's shipped graph was evaluated on (NIPS, A=4, b=12)."""
+@pytest.mark.parametrize('math', ['fp32', 'tf32x3', 'bf16x3'])
+def test_two_updates_match_reference_tf_graph(golden_dir, math):
+    """The same two train steps the reference's shipped graph was evaluated on (NIPS, A=4, b=12), in the fp32 anchor AND in
+    both tensor-core parity modes: the reference's own serialized graph pins every arithmetic path directly."""
     g = np.load(os.path.join(golden_dir, 'tf_graph_nips.npz'))
     A, b = int(g['A']), int(g['b'])
-    net = G.make_net('NIPS', A, seed=int(g['wseed']))
+    net = G.make_net('NIPS', A, seed=int(g['wseed']), math=math)
     eng = RolloutEngine(net, n_envs=b, t_max=1, gamma=1.0, rho=0.99, eps=0.1, clip_norm=3.0, clip_norm_type='global')
     for step in range(2):
         states, acts, adv, tgt = gen_train_batch(int(g['bseed']) + step, b, A)
         # make paacb_returns_loss_grad reproduce the fed placeholders: gamma = 1, r = 0, no terminal => y = V(s_T) := tgt,
         # adv = y - values with values := tgt - adv.  The bootstrap forward is overwritten by injecting boot_v.
-        eng.states[0].copy_(G.dev(states)); eng.states[1].copy_(G.dev(states))
+        eng.state(0).copy_(G.dev(states)); eng.state(1).copy_(G.dev(states))
         eng.actions.copy_(G.dev(acts.reshape(1, b), torch.int32))
         eng.rewards.zero_(); eng.over.zero_()
         eng.values.copy_(G.dev((tgt - adv).reshape(1, b)))
         p = _lib.ptr
-        flat_states = eng.states[:1].view(b, 84, 84, 4)
+        flat_states = eng.flat_states
         net.forward(flat_states, eng.pi, eng.v, eng.fwd_ws)
         eng.boot_v.copy_(G.dev(tgt))
         _lib.check(eng.lib.paacb_returns_loss_grad(eng.ctx, p(eng.rewards), p(eng.over), p(eng.values), p(eng.boot_v),
@@ -191,7 +193,7 @@ def test_engine_update_vs_oracle_composite():
     eng = RolloutEngine(net, N, T, seed=9)
     rng = np.random.RandomState(0)
     states = rng.randint(0, 256, (T + 1, N, 84, 84, 4)).astype(np.uint8)
-    eng.states.copy_(G.dev(states))
+    eng.set_states(G.dev(states))
     eng.draw_uniforms()
     for t in range(T):
         eng.act(t)
@@ -225,4 +227,5 @@ def test_engine_update_vs_oracle_composite():
     got = net.get_params()
     assert_close(got, want, 1e-5, 'post-RMSProp weights')
     assert_close(got - p0, want - p0, 2e-3, 'weight delta')
-    assert torch.equal(eng.states[0], eng.states[T])
+    # the rollout's last state is the next rollout's first (paac.py:99-112), without a copy: the halves flipped
+    assert torch.equal(eng.state(0), G.dev(states[T]))

@@ -27,8 +27,10 @@ class FakeNet(object):
     def workspace_floats(self, b):
         return 8 * b
 
-    def forward(self, states, pi, v, ws, uniforms=None, actions=None, onehot=None, ws_capacity=None, ws_first=0):
-        self.calls.append(dict(b=states.shape[0], cap=ws_capacity, first=ws_first, sample=uniforms is not None,
+    def forward(self, states, pi, v, ws, uniforms=None, actions=None, onehot=None, ws_capacity=None, ws_first=0, rng=None,
+                draw=0, first_sample=0):
+        self.calls.append(dict(b=states.shape[0], cap=ws_capacity, first=ws_first, sample=uniforms is not None or rng is not None,
+                               draw=draw, first_sample=first_sample,
                                ws=ws.data_ptr(), pi=pi.data_ptr(), v=v.data_ptr()))
 
 
@@ -85,15 +87,8 @@ def test_bootstrap_slices_are_completed_by_update_bookkeeping():
     net, eng = make('batched')
     eng.bootstrap(4, 8)
     net.calls.clear()
-    # forward_backward's bootstrap part only (the C calls that follow need a GPU): replicate its bookkeeping
-    pos, issued = 0, []
-    for lo, hi in sorted(eng._booted):
-        if lo > pos:
-            issued.append((pos, lo))
-        pos = max(pos, hi)
-    if pos < eng.N:
-        issued.append((pos, eng.N))
-    assert issued == [(0, 4), (8, eng.N)]
+    # forward_backward's bootstrap bookkeeping (the C calls that follow need a GPU)
+    assert eng._missing_bootstraps() == [(0, 4), (8, eng.N)]
     eng.bootstrap(0, 4); eng.bootstrap(8, eng.N)
     assert [(c['b']) for c in net.calls] == [4, eng.N - 8]
     assert all(not c['sample'] and c['cap'] is None for c in net.calls)

@@ -11,17 +11,19 @@ import torch
 
 from paac_b200 import parallel
 from paac_b200.engine import RolloutEngine
-from paac_b200.policy_v_network import NaturePolicyVNetwork
+from paac_b200.policy_v_network import NaturePolicyVNetwork, NIPSPolicyVNetwork
+
+ARCH = os.environ.get('PAACB_CHECK_ARCH', 'NATURE').upper()
 
 
 def make(local, math):
     conf = dict(name='local_learning', num_actions=6, clip_norm=3.0, clip_norm_type='global', device='/gpu:%d' % local,
                 entropy_regularisation_strength=0.02, seed=3, math=math)
-    return NaturePolicyVNetwork(conf)
+    return (NIPSPolicyVNetwork if ARCH == 'NIPS' else NaturePolicyVNetwork)(conf)
 
 
 def fill(eng, states, actions, values, rewards, over, lo, hi):
-    eng.states.copy_(torch.from_numpy(states[:, lo:hi]).cuda())
+    eng.set_states(torch.from_numpy(np.ascontiguousarray(states[:, lo:hi])).cuda())
     eng.actions.copy_(torch.from_numpy(actions[:, lo:hi]).cuda())
     eng.values.copy_(torch.from_numpy(values[:, lo:hi]).cuda())
     eng.rewards.copy_(torch.from_numpy(rewards[:, lo:hi]).cuda())
@@ -61,7 +63,7 @@ def main():
         d_one = ref.get_params() - p0
         err = np.max(np.abs(d_multi - d_one)) / np.max(np.abs(d_one))
         nerr = abs(eng.norm.item() - eng1.norm.item()) / eng1.norm.item()
-        print('multi_gpu_check world=%d math=%s: delta err %.2e, norm err %.2e' % (world, math, err, nerr), flush=True)
+        print('multi_gpu_check world=%d arch=%s math=%s: delta err %.2e, norm err %.2e' % (world, ARCH, math, err, nerr), flush=True)
         assert err <= 2e-3 and nerr <= 1e-4
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
