@@ -48,7 +48,7 @@ def parse():
     ap.add_argument('--envs', type=int, default=4096, help='environments per GPU')
     ap.add_argument('--arch', default='NATURE', choices=['NATURE', 'NIPS'])
     ap.add_argument('--math', default=os.environ.get('PAACB_BENCH_MATH', 'auto'), choices=['auto', 'fp32', 'tf32x3', 'tf32', 'bf16x3'],
-                    help="'auto': bf16x3 for Nature (the benchmark configuration), tf32x3 for NIPS")
+                    help="'auto': bf16x3 (the parity-grade tensor-core path, both architectures)")
     ap.add_argument('--frame_pool', type=int, default=8, help='device frame buffers rotated between env steps')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
@@ -58,7 +58,7 @@ def parse():
     ap.add_argument('--ref_envs', type=int, default=64, help='--impl reference: envs per step (bounded sample)')
     args = ap.parse_args()
     if args.math == 'auto':
-        args.math = 'bf16x3' if args.arch == 'NATURE' else 'tf32x3'
+        args.math = 'bf16x3'
     return args
 
 

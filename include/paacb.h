@@ -50,7 +50,7 @@ enum { PAACB_MATH_FP32 = 0,      /* SIMT fp32 FFMA: the parity anchor */
        PAACB_MATH_TF32X3 = 1,    /* tcgen05 kind::tf32, split operands (hi*hi + hi*lo + lo*hi) */
        PAACB_MATH_TF32 = 2,      /* tcgen05 kind::tf32, operands rounded to nearest tf32 */
        PAACB_MATH_BF16X3 = 3 };  /* tcgen05 kind::f16 on bf16-split operands (hi*hi + hi*lo + lo*hi), activations kept as
-                                    two bf16 planes, TMA-fed patch-resident implicit GEMMs; Nature architecture only */
+                                    two bf16 planes, TMA-fed patch-resident implicit GEMMs; both architectures */
 enum { PAACB_CLIP_IGNORE = 0, PAACB_CLIP_GLOBAL = 1 };   /* actor_learner.py:51-58 ('local' is broken upstream) */
 
 typedef struct paacb_ctx paacb_ctx;
@@ -64,6 +64,9 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device);
 int paacb_destroy(paacb_ctx* ctx);
 int paacb_set_math(paacb_ctx* ctx, int math_mode);
 int paacb_get_math(const paacb_ctx* ctx);
+/* Multi-GPU: leave n_sms SMs free of the persistent conv weight-gradient CTAs (PAACB_BWD_HEAD), the kernels that run
+ * while the caller's collective reduces the gradient tail, so that the collective's CTAs can be scheduled beside them. */
+int paacb_set_sm_reserve(paacb_ctx* ctx, int n_sms);
 /* The tensor-core modes keep operand images of the parameters (bf16 hi/lo transposes, int8 digits of conv1) in the
  * context and reuse them across forwards of the same d_params pointer: PAAC runs t_max + 2 forwards per parameter
  * update.  paacb_clip_rmsprop refreshes the images itself; a caller that writes the parameter buffer by any other
@@ -105,6 +108,15 @@ int paacb_observe_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_pe
                      const uint8_t* d_prev, uint8_t* d_next, int64_t n_envs, const float* d_rewards_in,
                      const float* d_over_in, float* d_rewards_out, float* d_over_out, int over_is_reset,
                      paacb_stream stream);
+
+/* SURVEY 8(f) rank 1 (frame-dedup rollout storage), prototype pair used for the measured A/B in DESIGN.md section 6:
+ * K1 at its contract traffic -- the new 84x84 plane only, into slot `slot` of a planar ring uint8 [n_envs, ring_slots, 84, 84]
+ * (ring_slots >= 4; a rollout needs t_max + 3) -- and the gather that rebuilds the NHWC stack [n_envs, 84, 84, 4] from the
+ * four newest slots (channel 3 = newest_slot, oldest first), which is what conv1's operand layout still needs. */
+int paacb_preprocess_planar_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_per_env, uint8_t* d_ring,
+                               int ring_slots, int slot, int64_t n_envs, paacb_stream stream);
+int paacb_stack_from_planes(const paacb_ctx* ctx, const uint8_t* d_ring, int ring_slots, int newest_slot, uint8_t* d_next,
+                            int64_t n_envs, paacb_stream stream);
 
 /* ---- K2-K6: forward (+ sampling).  Replaces session.run([output_layer_v, output_layer_pi])
  * and __sample_policy_action (paac.py:18-45).

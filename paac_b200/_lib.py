@@ -23,6 +23,7 @@ PROTOTYPES = {
     'paacb_destroy': (_i, [_vp]),
     'paacb_set_math': (_i, [_vp, _i]),
     'paacb_get_math': (_i, [_vp]),
+    'paacb_set_sm_reserve': (_i, [_vp, _i]),
     'paacb_set_resize_tables': (_i, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'paacb_param_count': (_i64, [_vp]),
     'paacb_num_tensors': (_i, [_vp]),
@@ -41,6 +42,8 @@ PROTOTYPES = {
                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_backward': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'paacb_clip_rmsprop': (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
+    'paacb_preprocess_planar_u8': (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _vp]),
+    'paacb_stack_from_planes': (_i, [_vp, _vp, _i, _i, _vp, _i64, _vp]),
     'paacb_observe_u8': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp]),
     'paacb_policy_forward_sample': (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, C.c_uint64, _i64, _vp, _vp, _vp]),
     'paacb_rng_advance': (_i, [_vp, _vp, C.c_uint64, _vp]),

@@ -1,127 +1,82 @@
-"""AtariEmulator: mirror of the reference's atari_emulator.py:15-118 over the Arcade Learning Environment.
+"""AtariEmulator: the Arcade Learning Environment behind the raw-frame protocol.
 
-ALE is a host-side C++ dependency that stays on the CPU (north_star: "host ALE runners").  It is NOT
-installed in this image, so this module raises ImportError on import there; EnvironmentCreator reports
-that plainly.  Besides the classic ``next`` / ``get_initial_state`` (NumPy max-pool + nearest resize + stack,
-as upstream), it implements the raw-frame protocol: ``getScreenGrayscale`` writes straight into the shared,
-pinned+mapped frame slots and the GPU does the rest (paacb_preprocess_u8).
+Stands in for the reference's atari_emulator.py:15-118.  ALE is a host-side C++ dependency that stays on the CPU
+(north_star: "host ALE runners"); it is NOT installed in this image, so importing this module raises ImportError there
+and EnvironmentCreator reports that plainly.
+
+What is kept from the reference is the emulation contract, because parity depends on it: ALE settings
+(atari_emulator.py:17-23: seed = random_seed * (actor_id + 1), no sticky actions, frame_skip 1, no colour averaging),
+the minimal action set, action repeat 4 with the LAST TWO luminance frames kept (:77-86), reset = reset_game + up to 30
+random no-ops + four repeats of action 0 (:60-67, :88-96), terminal = game over, or a lost life with
+``single_life_episodes`` (:108-115).  What is gone is every NumPy / PIL operation on pixels: ``getScreenGrayscale``
+writes straight into the frame-pair slot the runner hands in (pinned, mapped shared memory) and the GPU does max-pool,
+resize and stacking.  The classic ``next`` / ``get_initial_state`` are derived by RawFrameEnvironment.
 """
 import random
 
 import numpy as np
 from ale_python_interface import ALEInterface   # noqa: E402  (absent here -> ImportError, by design)
 
-from .environment import BaseEnvironment, FramePool, ObservationPool
-from .resize_tables import ROW, COL
+from .environment import RawFrameEnvironment, STACK, PAIR
 
-IMG_SIZE_X = 84
-IMG_SIZE_Y = 84
-NR_IMAGES = 4
 ACTION_REPEAT = 4
 MAX_START_WAIT = 30
-FRAMES_IN_POOL = 2
 
 
-class AtariEmulator(BaseEnvironment):
-    supports_raw_frames = True
+class AtariEmulator(RawFrameEnvironment):
 
     def __init__(self, actor_id, args):
-        self.ale = ALEInterface()
-        self.ale.setInt(b"random_seed", args.random_seed * (actor_id + 1))
-        self.ale.setFloat(b"repeat_action_probability", 0.0)
-        self.ale.setInt(b"frame_skip", 1)
-        self.ale.setBool(b"color_averaging", False)
-        full_rom_path = args.rom_path + "/" + args.game + ".bin"
-        self.ale.loadROM(str.encode(full_rom_path))
-        self.legal_actions = self.ale.getMinimalActionSet()
-        self.screen_width, self.screen_height = self.ale.getScreenDims()
-        self.lives = self.ale.lives()
-
+        ale = ALEInterface()
+        ale.setInt(b"random_seed", args.random_seed * (actor_id + 1))
+        ale.setFloat(b"repeat_action_probability", 0.0)
+        ale.setInt(b"frame_skip", 1)
+        ale.setBool(b"color_averaging", False)
+        ale.loadROM(str.encode(args.rom_path + "/" + args.game + ".bin"))
+        self.ale = ale
+        self.legal_actions = ale.getMinimalActionSet()
+        width, height = ale.getScreenDims()
         self.random_start = args.random_start
         self.single_life_episodes = args.single_life_episodes
-        self.call_on_new_frame = args.visualize
-
-        self.observation_pool = ObservationPool(np.zeros((IMG_SIZE_X, IMG_SIZE_Y, NR_IMAGES), dtype=np.uint8))
-        self.rgb_screen = np.zeros((self.screen_height, self.screen_width, 3), dtype=np.uint8)
-        self.gray_screen = np.zeros((self.screen_height, self.screen_width, 1), dtype=np.uint8)
-        self.frame_pool = FramePool(np.empty((2, self.screen_height, self.screen_width), dtype=np.uint8),
-                                    self.__process_frame_pool)
+        self.lives = ale.lives()
+        self._rgb = np.zeros((height, width, 3), dtype=np.uint8) if args.visualize else None
 
     def get_legal_actions(self):
         return self.legal_actions
 
-    def __get_screen_image(self):
-        self.ale.getScreenGrayscale(self.gray_screen)
-        if self.call_on_new_frame:
-            self.ale.getScreenRGB(self.rgb_screen)
-            self.on_new_frame(self.rgb_screen)
-        return np.squeeze(self.gray_screen)
+    def get_noop(self):
+        return [1.0, 0.0]
 
-    def on_new_frame(self, frame):
-        pass
-
-    def __new_game(self):
-        self.ale.reset_game()
-        self.lives = self.ale.lives()
-        if self.random_start:
-            wait = random.randint(0, MAX_START_WAIT)
-            for _ in range(wait):
-                self.ale.act(self.legal_actions[0])
-
-    def __process_frame_pool(self, frame_pool):
-        img = np.amax(frame_pool, axis=0)
-        return img[ROW[:, None], COL[None, :]].astype(np.uint8)
-
-    def __action_repeat(self, a, times=ACTION_REPEAT, sink=None):
-        """Repeat the action; the last FRAMES_IN_POOL frames go to ``sink`` (frame pool or raw slot)."""
+    def _repeat(self, action_index, pair):
+        """ACTION_REPEAT emulator steps of one action; the last PAIR screens land in pair[0], pair[1]."""
+        code = self.legal_actions[action_index]
         reward = 0
-        for _ in range(times - FRAMES_IN_POOL):
-            reward += self.ale.act(self.legal_actions[a])
-        for i in range(FRAMES_IN_POOL):
-            reward += self.ale.act(self.legal_actions[a])
-            if sink is None:
-                self.frame_pool.new_frame(self.__get_screen_image())
-            else:
-                sink[i] = self.__get_screen_image()
+        for step in range(ACTION_REPEAT):
+            reward += self.ale.act(code)
+            keep = step - (ACTION_REPEAT - PAIR)
+            if keep >= 0:
+                self.ale.getScreenGrayscale(pair[keep][..., None])       # (210, 160, 1) view of the shared slot: no copy
+                if self._rgb is not None:
+                    self.ale.getScreenRGB(self._rgb)
+                    self.on_new_frame(self._rgb)
         return reward
 
-    def get_initial_state(self):
-        self.__new_game()
-        for _ in range(NR_IMAGES):
-            self.__action_repeat(0)
-            self.observation_pool.new_observation(self.frame_pool.get_processed_frame())
-        if self.__is_terminal():
-            raise Exception('This should never happen.')
-        return self.observation_pool.get_pooled_observations()
+    def _terminal(self):
+        lost_life = self.single_life_episodes and self.lives > self.ale.lives()
+        return self.ale.game_over() or lost_life
 
-    def next(self, action):
-        reward = self.__action_repeat(np.argmax(action))
-        self.observation_pool.new_observation(self.frame_pool.get_processed_frame())
-        terminal = self.__is_terminal()
-        self.lives = self.ale.lives()
-        return self.observation_pool.get_pooled_observations(), reward, terminal
-
-    # ---- raw-frame protocol --------------------------------------------------------------------------
     def next_raw(self, action, out_pairs):
-        reward = self.__action_repeat(np.argmax(action), sink=out_pairs[0])
-        terminal = self.__is_terminal()
+        reward = self._repeat(int(np.argmax(action)), out_pairs[0])
+        terminal = self._terminal()
         self.lives = self.ale.lives()
         return reward, terminal
 
     def get_initial_state_raw(self, out_pairs):
-        self.__new_game()
-        for k in range(NR_IMAGES):
-            self.__action_repeat(0, sink=out_pairs[k])
-        if self.__is_terminal():
-            raise Exception('This should never happen.')
-
-    def __is_terminal(self):
-        if self.single_life_episodes:
-            return self.__is_over() or (self.lives > self.ale.lives())
-        return self.__is_over()
-
-    def __is_over(self):
-        return self.ale.game_over()
-
-    def get_noop(self):
-        return [1.0, 0.0]
+        self.ale.reset_game()
+        self.lives = self.ale.lives()
+        if self.random_start:
+            for _ in range(random.randint(0, MAX_START_WAIT)):
+                self.ale.act(self.legal_actions[0])
+        for k in range(STACK):
+            self._repeat(0, out_pairs[k])
+        if self._terminal():
+            raise Exception('This should never happen.')          # atari_emulator.py:95

@@ -281,7 +281,7 @@ int paacb_set_math(paacb_ctx* ctx, int math_mode) {
   ctx->fwd_img_valid = 0;
   if (math_mode == PAACB_MATH_BF16X3) {
     if (!bf16x3_supported(ctx)) {
-      set_error("paacb_set_math: PAACB_MATH_BF16X3 covers the Nature architecture only (use PAACB_MATH_TF32X3)");
+      set_error("paacb_set_math: PAACB_MATH_BF16X3 does not cover this architecture (use PAACB_MATH_TF32X3)");
       return PAACB_EUNSUPPORTED;
     }
     if (ctx->wb_f_hi == nullptr) {
@@ -334,6 +334,13 @@ int paacb_set_math(paacb_ctx* ctx, int math_mode) {
 }
 
 int paacb_get_math(const paacb_ctx* ctx) { return ctx ? ctx->math : PAACB_EINVAL; }
+
+int paacb_set_sm_reserve(paacb_ctx* ctx, int n_sms) {
+  PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  PAACB_CHECK_ARG(n_sms >= 0 && n_sms < ctx->num_sms, "n_sms out of range");
+  ctx->sm_reserve = n_sms;
+  return PAACB_OK;
+}
 
 int paacb_params_changed(paacb_ctx* ctx) {
   PAACB_CHECK_ARG(ctx != nullptr, "ctx is NULL");
@@ -430,6 +437,26 @@ int paacb_observe_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_pe
   PAACB_CHECK_ARG(d_rewards_in && d_over_in && d_rewards_out && d_over_out, "NULL reward / episode-over buffer");
   const StepScalars sc = {d_rewards_in, d_over_in, d_rewards_out, d_over_out, over_is_reset ? 1 : 0};
   return preprocess_impl(ctx, d_frames, pairs_per_env, d_reset, d_prev, d_next, n_envs, sc, stream);
+}
+
+int paacb_preprocess_planar_u8(const paacb_ctx* ctx, const uint8_t* d_frames, int pairs_per_env, uint8_t* d_ring,
+                               int ring_slots, int slot, int64_t n_envs, paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_frames && d_ring, "NULL argument");
+  PAACB_CHECK_DEVICE(ctx);
+  PAACB_CHECK_ARG(pairs_per_env >= 1 && ring_slots >= PAACB_STACK && slot >= 0 && slot < ring_slots, "pairs / ring slot out of range");
+  PAACB_CHECK_ARG(n_envs >= 0 && n_envs < (1LL << 31), "n_envs out of range");
+  PAACB_CHECK_ARG(((uintptr_t)d_frames & 15) == 0 && ((uintptr_t)d_ring & 15) == 0, "buffers must be 16-byte aligned");
+  return launch_preprocess_planar(ctx, d_frames, pairs_per_env, d_ring, ring_slots, slot, n_envs, (cudaStream_t)stream);
+}
+
+int paacb_stack_from_planes(const paacb_ctx* ctx, const uint8_t* d_ring, int ring_slots, int newest_slot, uint8_t* d_next,
+                            int64_t n_envs, paacb_stream stream) {
+  PAACB_CHECK_ARG(ctx && d_ring && d_next, "NULL argument");
+  PAACB_CHECK_DEVICE(ctx);
+  PAACB_CHECK_ARG(ring_slots >= PAACB_STACK && newest_slot >= 0 && newest_slot < ring_slots, "ring slot out of range");
+  PAACB_CHECK_ARG(n_envs >= 0 && n_envs < (1LL << 31), "n_envs out of range");
+  PAACB_CHECK_ARG(((uintptr_t)d_next & 15) == 0 && ((uintptr_t)d_ring & 15) == 0, "buffers must be 16-byte aligned");
+  return launch_stack_from_planes(ctx, d_ring, ring_slots, newest_slot, d_next, n_envs, (cudaStream_t)stream);
 }
 
 static int run_layer_fwd(const paacb_ctx* ctx, int l, const float* d_params, const uint8_t* d_states, int64_t batch,

@@ -126,6 +126,7 @@ struct paacb_ctx {
   mutable uintptr_t k1_cache_key[kK1Cache];
   mutable int k1_cache_host[kK1Cache];
   int k1_host_grid;             // PAACB_K1_HOST_GRID (default 96)
+  int sm_reserve;               // paacb_set_sm_reserve: SMs the persistent conv weight-gradient kernels leave free (multi-GPU)
   int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };
 
@@ -168,6 +169,11 @@ void prof_drain(const paacb_ctx* ctx);
 // ---- launchers implemented in the .cu files (all asynchronous on `st`) --------------------------
 int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
                       const uint8_t* prev, uint8_t* next, int64_t n, const StepScalars& sc, cudaStream_t st);
+
+int launch_preprocess_planar(const paacb_ctx* ctx, const uint8_t* frames, int pairs, uint8_t* ring, int ring_slots, int slot,
+                             int64_t n, cudaStream_t st);
+int launch_stack_from_planes(const paacb_ctx* ctx, const uint8_t* ring, int ring_slots, int newest_slot, uint8_t* next, int64_t n,
+                             cudaStream_t st);
 
 // SIMT fp32 implicit GEMMs (gemm_simt.cu)
 int launch_conv_fwd_simt(const paacb_ctx* ctx, const LayerGeom& g, const void* x, const float* w, const float* bias,

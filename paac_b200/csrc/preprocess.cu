@@ -99,6 +99,102 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int pairs, const uint8_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SURVEY 8(f) rank 1, frame-dedup rollout storage -- the measured half of the A/B.  K1 at its CONTRACT traffic:
+// the two frames' 84 selected rows in (26,880 B), ONE new 84 x 84 plane out (7,056 B) into a planar ring
+// uint8 [n_envs, ring_slots, 84, 84]; a rollout of T steps then needs T + 3 planes per environment instead of T stacked
+// [84, 84, 4] copies (paac.py:92,112 stores every frame four times).  stack_from_planes_kernel rebuilds the NHWC stack the
+// conv1 kernels consume from four ring slots (oldest first) -- the cost a planar ring adds back for as long as conv1's
+// int8 implicit GEMM needs its 16-byte (4 pixels x 4 frames) units.  tools/microbench_cfg5.py times both against K1.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+preprocess_planar_u8_kernel(const uint8_t* __restrict__ frames, int pairs, uint8_t* __restrict__ ring, int ring_slots, int slot,
+                            ResizeTables tabs, int64_t n_envs) {
+  __shared__ __align__(16) uint8_t plane[PAACB_OBS * PAACB_FRAME_W];
+  __shared__ int s_row[PAACB_OBS];
+  __shared__ int s_col[PAACB_OBS];
+  const int tid = threadIdx.x;
+  if (tid < PAACB_OBS) {
+    s_row[tid] = tabs.row[tid] * PAACB_FRAME_W;
+    s_col[tid] = tabs.col[tid];
+  }
+  for (int64_t env = blockIdx.x; env < n_envs; env += gridDim.x) {
+    const uint8_t* f0 = frames + (env * pairs * 2) * (int64_t)kFrameBytes;
+    const uint8_t* f1 = f0 + kFrameBytes;
+    __syncthreads();
+    for (int i = tid; i < PAACB_OBS * kRowVec; i += kThreads) {
+      const int y = i / kRowVec, c = i - y * kRowVec;
+      const int src = s_row[y] + c * 16;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(f0 + src));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(f1 + src));
+      uint4 m;
+      m.x = __vmaxu4(a.x, b.x); m.y = __vmaxu4(a.y, b.y); m.z = __vmaxu4(a.z, b.z); m.w = __vmaxu4(a.w, b.w);
+      *reinterpret_cast<uint4*>(plane + y * PAACB_FRAME_W + c * 16) = m;
+    }
+    __syncthreads();
+    // 84 x 84 bytes = 441 uint4 per plane: 16 output pixels per thread-iteration
+    uint4* out = reinterpret_cast<uint4*>(ring + (env * ring_slots + slot) * (int64_t)(PAACB_OBS * PAACB_OBS));
+    for (int i = tid; i < PAACB_OBS * PAACB_OBS / 16; i += kThreads) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int px = i * 16 + j * 4 + e;
+          const int y = px / PAACB_OBS, x = px - y * PAACB_OBS;
+          v |= (uint32_t)plane[y * PAACB_FRAME_W + s_col[x]] << (8 * e);
+        }
+        w[j] = v;
+      }
+      out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+stack_from_planes_kernel(const uint8_t* __restrict__ ring, int ring_slots, int newest_slot, uint8_t* __restrict__ next, int64_t n_envs) {
+  const int tid = threadIdx.x;
+  for (int64_t env = blockIdx.x; env < n_envs; env += gridDim.x) {
+    const uint8_t* base = ring + env * ring_slots * (int64_t)(PAACB_OBS * PAACB_OBS);
+    const uint32_t* pl[PAACB_STACK];
+#pragma unroll
+    for (int c = 0; c < PAACB_STACK; ++c)        // channel c = the frame 3 - c steps back, oldest first
+      pl[c] = reinterpret_cast<const uint32_t*>(base + ((newest_slot - 3 + c + 4 * ring_slots) % ring_slots) * (int64_t)(PAACB_OBS * PAACB_OBS));
+    uint4* out = reinterpret_cast<uint4*>(next + env * (int64_t)(kStateVec * 16));
+    for (int i = tid; i < kStateVec; i += kThreads) {       // 4 pixels = one 32-bit word of each plane -> one uint4 of the stack
+      const uint32_t a = __ldg(pl[0] + i), b = __ldg(pl[1] + i), c = __ldg(pl[2] + i), d = __ldg(pl[3] + i);
+      // [a0 b0 a1 b1], [c0 d0 c1 d1] ... then pixel words [a b c d] (channel 0 = oldest frame in the low byte)
+      const uint32_t ab01 = __byte_perm(a, b, 0x5140), cd01 = __byte_perm(c, d, 0x5140);
+      const uint32_t ab23 = __byte_perm(a, b, 0x7362), cd23 = __byte_perm(c, d, 0x7362);
+      uint4 o;
+      o.x = __byte_perm(ab01, cd01, 0x5410);
+      o.y = __byte_perm(ab01, cd01, 0x7632);
+      o.z = __byte_perm(ab23, cd23, 0x5410);
+      o.w = __byte_perm(ab23, cd23, 0x7632);
+      out[i] = o;
+    }
+  }
+}
+
+int launch_preprocess_planar(const paacb_ctx* ctx, const uint8_t* frames, int pairs, uint8_t* ring, int ring_slots, int slot,
+                             int64_t n, cudaStream_t st) {
+  if (n == 0) return PAACB_OK;
+  PAACB_LAUNCH_BEGIN(ctx, K_PREPROCESS, st);
+  preprocess_planar_u8_kernel<<<(unsigned)n, kThreads, 0, st>>>(frames, pairs, ring, ring_slots, slot, ctx->tabs, n);
+  PAACB_LAUNCH_END(ctx, K_PREPROCESS, st);
+  return PAACB_OK;
+}
+
+int launch_stack_from_planes(const paacb_ctx* ctx, const uint8_t* ring, int ring_slots, int newest_slot, uint8_t* next, int64_t n,
+                             cudaStream_t st) {
+  if (n == 0) return PAACB_OK;
+  PAACB_LAUNCH_BEGIN(ctx, K_PREPROCESS, st);
+  stack_from_planes_kernel<<<(unsigned)n, kThreads, 0, st>>>(ring, ring_slots, newest_slot, next, n);
+  PAACB_LAUNCH_END(ctx, K_PREPROCESS, st);
+  return PAACB_OK;
+}
+
 int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
                       const uint8_t* prev, uint8_t* next, int64_t n, const StepScalars& sc, cudaStream_t st) {
   if (n == 0) return PAACB_OK;

@@ -79,7 +79,7 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
   return PAACB_OK;
 }
 
-bool bf16x3_supported(const paacb_ctx* ctx) { return ctx->arch == PAACB_ARCH_NATURE; }
+bool bf16x3_supported(const paacb_ctx* ctx) { return ctx->arch == PAACB_ARCH_NATURE || ctx->arch == PAACB_ARCH_NIPS; }
 
 // ------------------------------------------------------------------------------------------------
 // operand producers
@@ -173,7 +173,8 @@ int launch_pack_bf16_dgrad_weights(const paacb_ctx* ctx, const float* params, cu
 // ------------------------------------------------------------------------------------------------
 // geometry of the five patch-resident GEMMs of the Nature network
 // ------------------------------------------------------------------------------------------------
-enum { G_FWD2 = 1, G_FWD3 = 2, G_DG3 = 3, G_DG2 = 4 };      // conv1 forward has its own int8 kernel (tc2_conv1.cu)
+enum { G_FWD2 = 1, G_FWD3 = 2, G_DG3 = 3, G_DG2 = 4,        // Nature; conv1 forward has its own int8 kernel (tc2_conv1.cu)
+       G_FWD2N = 5, G_DG2N = 6 };                           // NIPS conv2 (networks.py:146): 64-byte units, SWIZZLE_64B
 
 template <int G>
 struct Geo;
@@ -184,6 +185,7 @@ struct Geo<G_FWD2> {
   static constexpr bool DGRAD = false, A_LO = true, STAGED = false;
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 2, WU = 10, HQ = 10, BOX_ROWS = 15, SLOT = 19456, NSLOTS = 5;
   static constexpr int NACC = 1, BN = 64, KS = 16, KB = 8, OH = 9, OW = 9;
+  static constexpr int CH = 64, PIX = 1;
   __host__ __device__ static constexpr int aoff(int t) { return ((t / 8) * 10 + ((t / 4) % 2)) * 128 + (t % 4) * 32; }
   __host__ __device__ static constexpr int jw(int part, int t) { return ((part + 2 * (t / 8)) * 2 + ((t / 4) % 2)) * 4 + (t % 4); }
 };
@@ -193,6 +195,7 @@ struct Geo<G_FWD3> {
   static constexpr bool DGRAD = false, A_LO = true, STAGED = false;
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 9, HQ = 9, BOX_ROWS = 18, SLOT = 21504, NSLOTS = 3;
   static constexpr int NACC = 1, BN = 64, KS = 36, KB = 9, OH = 7, OW = 7;
+  static constexpr int CH = 64, PIX = 1;
   __host__ __device__ static constexpr int aoff(int t) { return (((t / 4) / 3) * 9 + ((t / 4) % 3)) * 128 + (t % 4) * 32; }
   __host__ __device__ static constexpr int jw(int, int t) { return t; }
 };
@@ -204,6 +207,7 @@ struct Geo<G_DG3> {
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 9, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 4;
   static constexpr int NACC = 1, BN = 64, KS = 36, KB = 9, OH = 9, OW = 9;       // OH/OW: valid rows/cols of the enumeration
   static constexpr int PAD = 2, S = 1, XH = 9, XW = 9;
+  static constexpr int CH = 64, PIX = 1;      // output channels per pixel, pixels per accumulator row
   __host__ __device__ static constexpr int aoff(int t) { return ((2 - (t / 4) / 3) * 11 + (2 - (t / 4) % 3)) * 128 + (t % 4) * 32; }
   __host__ __device__ static constexpr int jw(int, int t) { return t; }
 };
@@ -219,7 +223,35 @@ struct Geo<G_DG2> {
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 10, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 4;
   static constexpr int NACC = 4, BN = 32, KS = 16, KB = 4, OH = 10, OW = 10;
   static constexpr int PAD = 1, S = 2, XH = 20, XW = 20;
+  static constexpr int CH = 32, PIX = 1;
   __host__ __device__ static constexpr int aoff(int t) { return ((1 - (t / 4) / 2) * 11 + (1 - (t / 4) % 2)) * 128 + (t % 4) * 32; }
+  __host__ __device__ static constexpr int jw(int, int t) { return t; }
+};
+
+// NIPS conv2 forward: [b,20,20,16] 4x4 stride 2 -> [b,9,9,32].  Unit = 2 pixels x 16 channels = 64 B (SWIZZLE_64B rows); one
+// K = 16 MMA is exactly one pixel's 16 channels, so filter tap (kh, kw) = plane kh & 1, row offset kh >> 1, unit offset
+// kw >> 1, 32-byte half kw & 1.
+template <>
+struct Geo<G_FWD2N> {
+  static constexpr bool DGRAD = false, A_LO = true, STAGED = false;
+  static constexpr int UB = 64, SWZ = SWZ_64B, PARTS = 2, WU = 10, HQ = 10, BOX_ROWS = 15, SLOT = 10240, NSLOTS = 6;
+  static constexpr int NACC = 1, BN = 32, KS = 8, KB = 4, OH = 9, OW = 9;
+  static constexpr int CH = 32, PIX = 1;
+  __host__ __device__ static constexpr int aoff(int t) { return ((t / 4) * 10 + ((t / 2) % 2)) * 64 + (t % 2) * 32; }
+  __host__ __device__ static constexpr int jw(int part, int t) { return (part + 2 * (t / 4)) * 4 + 2 * ((t / 2) % 2) + (t % 2); }
+};
+// NIPS conv2 data-gradient: dZ2 [b,9,9,32] -> dX [b,20,20,16].  The four stride-parity classes (ph, pw) x 16 input channels are
+// TWO accumulators of 32 columns: accumulator ph holds (pw, ci) = the two horizontally adjacent output pixels 2 qw, 2 qw + 1,
+// which are 32 contiguous elements of the NHWC output -- the packed data-gradient image is row-ordered (ph, pw, ci) already,
+// and a thread's 32 columns are one 64-byte run of each output plane (direct 256-bit stores, no staging tile).
+template <>
+struct Geo<G_DG2N> {
+  static constexpr bool DGRAD = true, A_LO = true, STAGED = false;
+  static constexpr int UB = 64, SWZ = SWZ_64B, PARTS = 1, WU = 11, HQ = 10, BOX_ROWS = 11, SLOT = 8192, NSLOTS = 6;
+  static constexpr int NACC = 2, BN = 32, KS = 8, KB = 2, OH = 10, OW = 10;
+  static constexpr int PAD = 1, S = 2, XH = 20, XW = 20;
+  static constexpr int CH = 16, PIX = 2;      // output channels per pixel, pixels per accumulator row
+  __host__ __device__ static constexpr int aoff(int t) { return ((1 - (t / 2) / 2) * 11 + (1 - (t / 2) % 2)) * 64 + (t % 2) * 32; }
   __host__ __device__ static constexpr int jw(int, int t) { return t; }
 };
 
@@ -574,8 +606,11 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
       if constexpr (Ge::DGRAD) {
 #pragma unroll
         for (int acc = 0; acc < NACC; ++acc) {
-          const int ih = Ge::S * qh + (NACC > 1 ? acc / 2 : 0), iw = Ge::S * qw + (NACC > 1 ? acc % 2 : 0);
-          const int64_t ob = (((int64_t)tile * Ge::XH + ih) * Ge::XW + iw) * BN;
+          // accumulator -> output pixel: PIX == 1: class (acc / 2, acc % 2) of a stride-2 layer; PIX == 2: row parity acc, the
+          // 32 columns are the pixels 2 qw, 2 qw + 1 (CH channels each)
+          const int ih = Ge::S * qh + (NACC > 1 ? (Ge::PIX == 2 ? acc : acc / 2) : 0);
+          const int iw = Ge::S * qw + ((NACC > 1 && Ge::PIX == 1) ? acc % 2 : 0);
+          const int64_t ob = (((int64_t)tile * Ge::XH + ih) * Ge::XW + iw) * Ge::CH;
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) {
 #pragma unroll
@@ -635,8 +670,9 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
       for (int acc = 0; acc < NACC; ++acc) {
         int64_t obase;          // element index of this row's first output channel
         if constexpr (Ge::DGRAD) {
-          const int ih = Ge::S * qh + (NACC > 1 ? acc / 2 : 0), iw = Ge::S * qw + (NACC > 1 ? acc % 2 : 0);
-          obase = (((int64_t)tile * Ge::XH + ih) * Ge::XW + iw) * BN;
+          const int ih = Ge::S * qh + (NACC > 1 ? (Ge::PIX == 2 ? acc : acc / 2) : 0);
+          const int iw = Ge::S * qw + ((NACC > 1 && Ge::PIX == 1) ? acc % 2 : 0);
+          obase = (((int64_t)tile * Ge::XH + ih) * Ge::XW + iw) * Ge::CH;
         } else {
           obase = pix * BN;
         }
@@ -688,8 +724,9 @@ __global__ void __launch_bounds__(ConvKCfg<G>::THREADS, 1) convk_kernel(const __
     }
     if constexpr (Ge::DGRAD) {
       if (p.dbias != nullptr) {
+        // column -> channel: PIX == 2 packs two pixels of CH channels into one accumulator row
 #pragma unroll
-        for (int i = 0; i < (NACC == 1 ? BN / 32 : 1); ++i) atomicAdd(p.dbias + i * 32 + lane, bsum[i]);
+        for (int i = 0; i < (NACC == 1 ? BN / 32 : 1); ++i) atomicAdd(p.dbias + (i * 32 + lane) % Ge::CH, bsum[i]);
       }
     }
   }
@@ -770,7 +807,7 @@ int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, const
     using Ge = Geo<GE>;                                                                                            \
     if ((int)unit * 2 != Ge::UB || (int)wu != Ge::WU || (int)hq != Ge::HQ || g.N != Ge::BN || g.K != Ge::KB * 64 ||  \
         s != Ge::PARTS || g.OH != Ge::OH || g.OW != Ge::OW)                                                        \
-      return PAACB_EUNSUPPORTED;                                                                                   \
+      break;                                                                                                       \
     const uint32_t box[4] = {(uint32_t)unit, (uint32_t)Ge::WU, 1u, (uint32_t)Ge::BOX_ROWS};                        \
     rc = encode_tmap_bf16(&p.tmA[0], in_hi, 4, dims, strides, box, Ge::UB);                                        \
     if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], in_lo, 4, dims, strides, box, Ge::UB);                    \
@@ -782,8 +819,10 @@ int launch_conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, const
     return launch_convk<GE>(ctx, p, K_FWD0 + l, st);                                                               \
   }
   if (l == 0) return launch_conv1_fwd_i8(ctx, params, states, fwd_ws, batch, slice, st);
-  if (l == 1) PAACB_FWD_CASE(G_FWD2)
-  if (l == 2) PAACB_FWD_CASE(G_FWD3)
+  // (each case leaves its do-while with `break` when the layer's geometry is not the one it was written for)
+  if (l == 1) do PAACB_FWD_CASE(G_FWD2) while (0);
+  if (l == 1) do PAACB_FWD_CASE(G_FWD2N) while (0);
+  if (l == 2) do PAACB_FWD_CASE(G_FWD3) while (0);
 #undef PAACB_FWD_CASE
   return PAACB_EUNSUPPORTED;
 }
@@ -812,12 +851,13 @@ int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, void
   {                                                                                                                \
     using Ge = Geo<GE>;                                                                                            \
     const int s = g.stride;                                                                                        \
-    if (g.N != 64 || g.C != Ge::BN || s != Ge::S || g.H != Ge::XH || g.W != Ge::XW || (g.R / s) * (g.S / s) * g.N != Ge::KB * 64 || \
+    if (g.N * 2 != Ge::UB || g.C != Ge::CH || s != Ge::S || g.H != Ge::XH || g.W != Ge::XW ||                       \
+        (g.R / s) * (g.S / s) * g.N != Ge::KB * 64 || s * s * g.C != Ge::NACC * Ge::BN ||                           \
         (g.R - 1) / s != Ge::PAD || g.OH + 2 * Ge::PAD > Ge::BOX_ROWS + 0 || (g.H + s - 1) / s != Ge::OH)          \
-      return PAACB_EUNSUPPORTED;                                                                                   \
-    const uint32_t box[4] = {64u, (uint32_t)Ge::WU, (uint32_t)Ge::BOX_ROWS, 1u};                                   \
-    rc = encode_tmap_bf16(&p.tmA[0], dz.hi, 4, dims, strides, box, 128);                                           \
-    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], dz.lo, 4, dims, strides, box, 128);                       \
+      break;                                                                                                       \
+    const uint32_t box[4] = {(uint32_t)g.N, (uint32_t)Ge::WU, (uint32_t)Ge::BOX_ROWS, 1u};                          \
+    rc = encode_tmap_bf16(&p.tmA[0], dz.hi, 4, dims, strides, box, Ge::UB);                                        \
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], dz.lo, 4, dims, strides, box, Ge::UB);                    \
     if (rc == PAACB_OK)                                                                                            \
       rc = weight_maps(ctx, ctx->wb_d_hi, ctx->wb_d_lo, g, (uint64_t)(g.R / s) * (g.S / s) * g.N,                  \
                        (uint64_t)s * s * g.C, Ge::BN, p.tmW);                                                      \
@@ -831,8 +871,9 @@ int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, void
     if (rc != PAACB_OK) return rc;                                                                                 \
     return launch_convk<GE>(ctx, p, K_DGRAD0 + l, st);                                                             \
   }
-  if (g.stride == 1) PAACB_DG_CASE(G_DG3)
-  if (g.stride == 2) PAACB_DG_CASE(G_DG2)
+  if (g.stride == 1) do PAACB_DG_CASE(G_DG3) while (0);
+  if (g.stride == 2) do PAACB_DG_CASE(G_DG2) while (0);
+  if (g.stride == 2) do PAACB_DG_CASE(G_DG2N) while (0);
 #undef PAACB_DG_CASE
   return PAACB_EUNSUPPORTED;
 }

@@ -319,11 +319,13 @@ static int launch_conv1_inst(const paacb_ctx* ctx, const float* params, const ui
   return PAACB_OK;
 }
 
-// Nature, bf16-split pipeline: planes out
+// bf16-split pipeline (both architectures): planes out
 int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t* states, void* fwd_ws, int64_t batch,
                         const WsSlice& slice, cudaStream_t st) {
   const LayerGeom& g = ctx->layer[0];
   const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
+  if (g.N == 16)      // NIPS: 16 channels = one 32-byte sector per position and plane
+    return launch_conv1_inst<16, false>(ctx, params, states, out.hi, out.lo, nullptr, batch, st);
   return launch_conv1_inst<32, false>(ctx, params, states, out.hi, out.lo, nullptr, batch, st);
 }
 

@@ -350,7 +350,9 @@ constexpr int kFcBN = 128;
 int launch_fc_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void* fwd_ws, int64_t batch, const WsSlice& slice,
                        cudaStream_t st) {
   const LayerGeom& g = ctx->layer[l];
-  if (g.K % 64 != 0 || g.N % kFcBN != 0) return PAACB_EUNSUPPORTED;
+  // K need not be a multiple of the 64-wide K-block (NIPS: 2592 = 40.5 blocks): the TMA engine zero-fills BOTH operands
+  // beyond K, so the ragged tail contributes nothing.  Row pitches must be multiples of 16 bytes.
+  if (g.K % 8 != 0 || g.N % kFcBN != 0) return PAACB_EUNSUPPORTED;
   StreamParams p;
   memset(&p, 0, sizeof(p));
   const Planes x = layer_planes(fwd_ws, g.in_act_off, g.K, slice);
@@ -363,7 +365,7 @@ int launch_fc_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, void* f
   p.m_tiles = (int)((batch + 127) / 128);
   p.n_tiles = g.N / kFcBN;
   p.k_splits = 1;
-  p.kblocks_total = p.kblocks_per_split = g.K / 64;
+  p.kblocks_total = p.kblocks_per_split = (g.K + 63) / 64;
   p.M = (int)batch;
   p.N = g.N;
   p.ldo = g.N;
@@ -406,7 +408,7 @@ int launch_fc_dgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, void* 
 int launch_fc_wgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, const void* bwd_ws, float* grads, int64_t batch,
                          cudaStream_t st) {
   const LayerGeom& g = ctx->layer[l];
-  if (g.N % kFcBN != 0 || g.K % 64 != 0) return PAACB_EUNSUPPORTED;
+  if (g.N % kFcBN != 0 || g.K % 32 != 0) return PAACB_EUNSUPPORTED;      // ragged k-tiles: OOB columns of X read zeros
   StreamParams p;
   memset(&p, 0, sizeof(p));
   const Planes x = layer_planes(const_cast<void*>(fwd_ws), g.in_act_off, g.K, batch);

@@ -30,7 +30,7 @@ struct Wg<0> {
   static constexpr int STAGES = 2, KT = 2, BN = 32, KSTEPS = 14, A_KSTEP = 512, B_KSTEP = 1024;
   static constexpr int A_SWZ = SWZ_32B, A_SBO = 256, B_SWZ = SWZ_64B, B_SBO = 512;
   static constexpr int STAGES_PER_SAMPLE = 2, SAMPLES_PER_STAGE = 1;
-  static constexpr int K = 256;
+  static constexpr int K = 256, KIND = 0, LAYER = 0, MROWS = 128;
   __device__ static int a_off(int kt) { return kt * 21 * 32; }                               // within plane 0's slot
   __device__ static int a_lbo(int) { return A_SLOT; }
   // row m of k-tile kt -> weight row k = kh * 32 + kw * 4 + c: group g = m >> 4 is (kw / 4 = g >> 2, kh & 3 = g & 3)
@@ -43,7 +43,7 @@ struct Wg<1> {
   static constexpr int STAGES = 2, KT = 4, BN = 64, KSTEPS = 7, A_KSTEP = 2048, B_KSTEP = 2048;
   static constexpr int A_SWZ = SWZ_128B, A_SBO = 1024, B_SWZ = SWZ_128B, B_SBO = 1024;
   static constexpr int STAGES_PER_SAMPLE = 1, SAMPLES_PER_STAGE = 1;
-  static constexpr int K = 512;
+  static constexpr int K = 512, KIND = 1, LAYER = 1, MROWS = 128;
   __device__ static int a_off(int kt) { return (kt >> 1) * 10 * 128; }                       // kh = kt: plane kt & 1, row offset kt / 2
   __device__ static int a_lbo(int) { return 128; }
   __device__ static int k_of(int kt, int m) { return kt * 128 + m; }
@@ -55,11 +55,41 @@ struct Wg<2> {
   static constexpr int STAGES = 2, KT = 5, BN = 64, KSTEPS = 11, A_KSTEP = 2048, B_KSTEP = 2048;
   static constexpr int A_SWZ = SWZ_128B, A_SBO = 1024, B_SWZ = SWZ_128B, B_SBO = 1024;
   static constexpr int STAGES_PER_SAMPLE = 1, SAMPLES_PER_STAGE = 2;
-  static constexpr int K = 576;
+  static constexpr int K = 576, KIND = 2, LAYER = 2, MROWS = 128;
   __device__ static int tap_off(int tap) { return ((tap / 3) * 9 + (tap % 3)) * 128; }
   __device__ static int a_off(int kt) { return tap_off(2 * kt); }
   __device__ static int a_lbo(int kt) { return kt < 4 ? tap_off(2 * kt + 1) - tap_off(2 * kt) : 128; }
   __device__ static int k_of(int kt, int m) { return (kt * 128 + m < K) ? kt * 128 + m : -1; }
+};
+
+// ---- NIPS (networks.py:145-146): the same two kernels with narrower dZ operands ----
+// conv1, 16 output channels: dZ1 [b,20,20,16] rows are 32 B (SWIZZLE_32B MN-major, like the X operand); everything on the X
+// side (converter warps, merged k-tiles) is unchanged.
+template <>
+struct Wg<3> {
+  static constexpr int A_PARTS = 8, A_PIECES = 1, A_SLOT = 9216, A_BOX = 16 * 2 * 21 * 13, B_SLOT = 8192, B_BOX = 32 * 21 * 12;
+  static constexpr int STAGES = 2, KT = 2, BN = 16, KSTEPS = 14, A_KSTEP = 512, B_KSTEP = 512;
+  static constexpr int A_SWZ = SWZ_32B, A_SBO = 256, B_SWZ = SWZ_32B, B_SBO = 256;
+  static constexpr int STAGES_PER_SAMPLE = 2, SAMPLES_PER_STAGE = 1;
+  static constexpr int K = 256, KIND = 0, LAYER = 0, MROWS = 128;
+  __device__ static int a_off(int kt) { return kt * 21 * 32; }
+  __device__ static int a_lbo(int) { return A_SLOT; }
+  __device__ static int k_of(int kt, int m) { return (4 * kt + ((m >> 4) & 3)) * 32 + (m >> 6) * 16 + (m & 15); }
+};
+// conv2: X1 [b,20,20,16] (hi, lo), dZ2 [b,9,9,32].  Units are 64 B (2 pixels x 16 channels): an MN group of a SWIZZLE_64B
+// operand is 32 k = (kw pair, ci), so filter row kh is TWO groups (this unit and the next, LBO = 64) = 64 rows of the
+// 128-row MMA; the other two groups read the units after them and are discarded (k_of = -1).  One k-tile per kh: the layer
+// has a quarter of Nature's conv2 MACs and costs the same MMA count -- still 4x faster than the tf32 kernel it replaces.
+template <>
+struct Wg<4> {
+  static constexpr int A_PARTS = 2, A_PIECES = 2, A_SLOT = 8192, A_BOX = 64 * 10 * 12, B_SLOT = 7168, B_BOX = 64 * 10 * 10;
+  static constexpr int STAGES = 2, KT = 4, BN = 32, KSTEPS = 7, A_KSTEP = 1024, B_KSTEP = 1024;
+  static constexpr int A_SWZ = SWZ_64B, A_SBO = 512, B_SWZ = SWZ_64B, B_SBO = 512;
+  static constexpr int STAGES_PER_SAMPLE = 1, SAMPLES_PER_STAGE = 1;
+  static constexpr int K = 256, KIND = 1, LAYER = 1, MROWS = 64;
+  __device__ static int a_off(int kt) { return (kt >> 1) * 10 * 64; }                        // kh = kt: plane kt & 1, row offset kt / 2
+  __device__ static int a_lbo(int) { return 64; }
+  __device__ static int k_of(int kt, int m) { return m < 64 ? kt * 64 + m : -1; }
 };
 
 struct Wg2Params {
@@ -80,7 +110,7 @@ struct Wg2Cfg {
   static constexpr int B_STAGE = 2 * W::B_SLOT;
   static constexpr int A_BYTES = W::STAGES * A_STAGE;
   static constexpr int DATA_BYTES = A_BYTES + W::STAGES * B_STAGE;
-  static constexpr bool U8_A = (L == 0);                 // conv1: nine converter warps produce the X operand from the uint8 states
+  static constexpr bool U8_A = (W::KIND == 0);                 // conv1: nine converter warps produce the X operand from the uint8 states
   static constexpr int TX_BYTES = (U8_A ? 0 : W::A_PARTS * W::A_PIECES * W::A_BOX) + 2 * W::B_BOX;
   static constexpr int CONV_THREADS = 288;               // conv1: nine converter warps, one 32-byte unit of each plane per thread (273 units)
   static constexpr int THREADS = 192 + (U8_A ? CONV_THREADS : 0);
@@ -148,7 +178,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
         uint8_t* a = a_sm + stage * Cfg::A_STAGE;
         uint8_t* b = b_sm + stage * Cfg::B_STAGE;
-        if constexpr (L == 0) {
+        if constexpr (W::KIND == 0) {
           const int n = s >> 1, h = s & 1;
 #pragma unroll
           (void)a;                                    // the X operand is written by the converter warps
@@ -159,7 +189,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
 #pragma unroll
             for (int piece = 0; piece < 2; ++piece) tma_prefetch_4d(&p.tmB[piece], 0, 0, 10 * ((s + 2) & 1), (s + 2) >> 1);
           }
-        } else if constexpr (L == 1) {
+        } else if constexpr (W::KIND == 1) {
 #pragma unroll
           for (int part = 0; part < 2; ++part)
 #pragma unroll
@@ -191,8 +221,8 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
         const uint32_t a_st = smem_u32(a_sm + stage * Cfg::A_STAGE);
         const uint32_t b_st = smem_u32(b_sm + stage * Cfg::B_STAGE);
         uint32_t a_rel = 0, b_rel = 0;
-        if constexpr (L == 0) {
-          if (s & 1) { a_rel = 14 * 32; b_rel = 14 * 64; }      // second half of the sample starts at position 224 = 10 * 21 + 14
+        if constexpr (W::KIND == 0) {
+          if (s & 1) { a_rel = 14 * 32; b_rel = 14 * 2 * W::BN; }      // second half of the sample starts at position 224 = 10 * 21 + 14
         }
         const uint32_t first = (s == s_begin) ? 0u : 1u;
 #pragma unroll
@@ -201,9 +231,9 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
           const uint32_t d = tmem_base + (uint32_t)(kt * Cfg::ACC_COLS);
           const uint64_t adesc0 = make_smem_desc(0, (uint32_t)W::a_lbo(kt), W::A_SBO, W::A_SWZ);
           uint32_t a_hi, a_lo = 0;
-          if constexpr (L == 0) {
+          if constexpr (W::KIND == 0) {
             a_hi = a_st + a_rel + (uint32_t)W::a_off(kt);
-          } else if constexpr (L == 1) {
+          } else if constexpr (W::KIND == 1) {
             a_hi = a_st + (uint32_t)((kt & 1) * 2 * W::A_SLOT) + (uint32_t)W::a_off(kt);
             a_lo = a_hi + W::A_SLOT;
           } else {
@@ -313,6 +343,22 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
 #pragma unroll 1
     for (int kt = 0; kt < W::KT; ++kt) {
       const int k = W::k_of(kt, m);
+      if constexpr (W::BN == 16) {
+        // 16 output channels: the accumulator is [X^T dZ_hi (16 columns) | X^T dZ_lo (16 columns)], one 32-column load
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(kt * Cfg::ACC_COLS), v);
+        tmem_ld_wait();
+        if (k >= 0) {
+          float4* dst = reinterpret_cast<float4*>(p.dw + (int64_t)k * W::BN);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            atomicAdd(dst + j, make_float4((__uint_as_float(v[4 * j]) + __uint_as_float(v[16 + 4 * j])) * p.w_scale,
+                                           (__uint_as_float(v[4 * j + 1]) + __uint_as_float(v[16 + 4 * j + 1])) * p.w_scale,
+                                           (__uint_as_float(v[4 * j + 2]) + __uint_as_float(v[16 + 4 * j + 2])) * p.w_scale,
+                                           (__uint_as_float(v[4 * j + 3]) + __uint_as_float(v[16 + 4 * j + 3])) * p.w_scale));
+        }
+        continue;
+      }
 #pragma unroll
       for (int c0 = 0; c0 < W::BN; c0 += 32) {
         uint32_t v[32];
@@ -363,10 +409,13 @@ static int launch_wg2(const paacb_ctx* ctx, const Wg2Params& p, cudaStream_t st)
     cudaGetLastError();
     attr_set.mark(ctx->device);
   }
-  const unsigned grid = (unsigned)(p.stages_total < ctx->num_sms ? p.stages_total : ctx->num_sms);
-  PAACB_LAUNCH_BEGIN(ctx, K_WGRAD0 + L, st);
+  // multi-GPU: the gradient tail is being all-reduced while these kernels run; one persistent CTA per SM with the maximum
+  // shared-memory carve-out would leave the collective's CTAs nowhere to go until a whole kernel retires
+  const int sms = ctx->num_sms - ctx->sm_reserve > 0 ? ctx->num_sms - ctx->sm_reserve : 1;
+  const unsigned grid = (unsigned)(p.stages_total < sms ? p.stages_total : sms);
+  PAACB_LAUNCH_BEGIN(ctx, K_WGRAD0 + Wg<L>::LAYER, st);
   wgrad2_kernel<L><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
-  PAACB_LAUNCH_END(ctx, K_WGRAD0 + L, st);
+  PAACB_LAUNCH_END(ctx, K_WGRAD0 + Wg<L>::LAYER, st);
   return PAACB_OK;
 }
 
@@ -396,18 +445,29 @@ int launch_conv_wgrad_bf16(const paacb_ctx* ctx, int l, const uint8_t* states, c
   const uint64_t bstr[3] = {(uint64_t)g.N * 2, (uint64_t)g.OW * g.N * 2, (uint64_t)g.OH * g.OW * g.N * 2};
   int rc;
   if (l == 0) {
-    if (g.C != 4 || s != 4 || g.R != 8 || g.N != 32 || g.H != 84 || g.OH != 20) return PAACB_EUNSUPPORTED;
-    const uint64_t adims[4] = {unit, wu, (uint64_t)s, (uint64_t)batch * hq};
-    const uint64_t astr[3] = {unit * 2, (uint64_t)g.W * g.C * 2, (uint64_t)s * g.W * g.C * 2};
-    const uint32_t abox[4] = {16u, 21u, 1u, 13u};
-    const uint32_t bbox[4] = {32u, 21u, 12u, 1u};
-    (void)adims; (void)astr; (void)abox; (void)x_lo; (void)x_hi;
+    if (g.C != 4 || s != 4 || g.R != 8 || (g.N != 32 && g.N != 16) || g.H != 84 || g.OH != 20) return PAACB_EUNSUPPORTED;
+    const uint32_t bbox[4] = {(uint32_t)g.N, 21u, 12u, 1u};
+    (void)x_lo; (void)x_hi; (void)unit; (void)wu; (void)hq;
     p.a_u8 = states;
-    rc = encode_tmap_bf16(&p.tmB[0], dz.hi, 4, bdims, bstr, bbox, 64);
-    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[1], dz.lo, 4, bdims, bstr, bbox, 64);
+    rc = encode_tmap_bf16(&p.tmB[0], dz.hi, 4, bdims, bstr, bbox, 2 * g.N);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[1], dz.lo, 4, bdims, bstr, bbox, 2 * g.N);
     if (rc != PAACB_OK) return rc;
     p.stages_total = (int)batch * 2;
-    return launch_wg2<0>(ctx, p, st);
+    return g.N == 32 ? launch_wg2<0>(ctx, p, st) : launch_wg2<3>(ctx, p, st);
+  }
+  if (l == 1 && g.C == 16) {      // NIPS conv2
+    if (s != 2 || g.R != 4 || g.N != 32 || g.H != 20 || g.OH != 9) return PAACB_EUNSUPPORTED;
+    const uint64_t adims[4] = {unit, wu, (uint64_t)s, (uint64_t)batch * hq};
+    const uint64_t astr[3] = {unit * 2, (uint64_t)g.W * g.C * 2, (uint64_t)s * g.W * g.C * 2};
+    const uint32_t abox[4] = {32u, 10u, 1u, 12u};
+    const uint32_t bbox[4] = {32u, 10u, 10u, 1u};
+    rc = encode_tmap_bf16(&p.tmA[0], x_hi, 4, adims, astr, abox, 64);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], x_lo, 4, adims, astr, abox, 64);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[0], dz.hi, 4, bdims, bstr, bbox, 64);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmB[1], dz.lo, 4, bdims, bstr, bbox, 64);
+    if (rc != PAACB_OK) return rc;
+    p.stages_total = (int)batch;
+    return launch_wg2<4>(ctx, p, st);
   }
   if (l == 1) {
     if (g.C != 32 || s != 2 || g.R != 4 || g.N != 64 || g.H != 20 || g.OH != 9) return PAACB_EUNSUPPORTED;

@@ -39,7 +39,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, parallel
 
 STATE_SHAPE = (84, 84, 4)
 FRAME_SLOT_SHAPE = (4, 2, 210, 160)
@@ -77,6 +77,10 @@ class RolloutEngine(object):
         self.overlap_allreduce = bool(overlap_allreduce)
         self.tail_off = int(self.lib.paacb_grad_tail_offset(self.ctx))
         self._pending = []
+        if self.world > 1 and self.overlap_allreduce and hasattr(self.lib, 'paacb_set_sm_reserve'):
+            # the tail's all-reduce runs under the conv weight-gradient kernels: leave its CTAs a few SMs (PAACB_SM_RESERVE)
+            import os
+            _lib.check(self.lib.paacb_set_sm_reserve(self.ctx, int(os.environ.get('PAACB_SM_RESERVE', '8'))), 'paacb_set_sm_reserve')
 
         d, N, T, A, B = self.dev, self.N, self.T, self.A, self.B
         f32 = dict(dtype=torch.float32, device=d)
@@ -368,7 +372,7 @@ class RolloutEngine(object):
                     w.wait()             # stream-level wait: the optimizer kernel is ordered after both reductions
                 self._pending = []
             else:
-                torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.group)
+                parallel.allreduce_mean_grads(self.grads, self.world, self.group)
 
     def apply(self, lr):
         """Global-norm clip + RMSProp (+ refresh of the cached weight images) and the Philox draw base += T."""

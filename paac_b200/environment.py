@@ -10,6 +10,12 @@ the classic protocol (they hand 84x84x4 observations to the learner, as in the r
 """
 import numpy as np
 
+from .resize_tables import ROW, COL
+
+STACK = 4                      # frames per observation (atari_emulator.py:11 NR_IMAGES)
+FRAME_SHAPE = (210, 160)       # ALE luminance screen
+PAIR = 2                       # frames max-pooled per observation plane (atari_emulator.py:14 FRAMES_IN_POOL)
+
 
 class BaseEnvironment(object):
     def get_initial_state(self):
@@ -93,3 +99,29 @@ class ObservationPool(object):
 
     def get_pooled_observations(self):
         return np.roll(self.observation_pool, -self.current_observation_index, axis=-1).copy()
+
+
+class RawFrameEnvironment(BaseEnvironment):
+    """Base class for environments that speak the raw-frame protocol natively: a subclass implements ``next_raw`` and
+    ``get_initial_state_raw`` (it only ever produces raw 210x160 luminance frame pairs) and the GPU turns them into
+    observations (paacb_preprocess_u8).  The classic methods of the plugin contract are DERIVED here for callers that
+    want 84x84x4 observations on the host (the evaluation loop, ``--raw_frames False``): the same arithmetic in NumPy --
+    element-wise max of the pair (atari_emulator.py:72), nearest resize through the Pillow index tables (:73), a 4-deep
+    stack with the oldest plane first (environment.py:58-75)."""
+    supports_raw_frames = True
+
+    @staticmethod
+    def _plane(pair):
+        return np.maximum(pair[0], pair[1])[ROW[:, None], COL[None, :]]
+
+    def get_initial_state(self):
+        pairs = np.empty((STACK, PAIR) + FRAME_SHAPE, dtype=np.uint8)
+        self.get_initial_state_raw(pairs)
+        self._stack = np.stack([self._plane(p) for p in pairs], axis=-1)
+        self._pair = pairs[:1].copy()
+        return self._stack.copy()
+
+    def next(self, action):
+        reward, terminal = self.next_raw(action, self._pair)
+        self._stack = np.concatenate([self._stack[..., 1:], self._plane(self._pair[0])[..., None]], axis=-1)
+        return self._stack.copy(), reward, terminal

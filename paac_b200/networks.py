@@ -97,11 +97,13 @@ class Network(object):
         self.initialize(self.seed)
 
     def set_math(self, math):
-        """'fp32' (SIMT, the parity anchor) | 'bf16x3' (tensor cores on bf16-split operands: the fast parity-grade path, Nature
-        architecture) | 'tf32x3' (tensor cores on tf32-split operands, both architectures) | 'tf32' (speed mode, not parity
-        grade) | 'auto' (bf16x3 for Nature, tf32x3 for NIPS)."""
+        """'fp32' (SIMT FFMA, the parity anchor: what the reference's fp32 graph computes, <= 2e-6 of it) | 'bf16x3' (tensor cores
+        on bf16-split operands, hi*hi + hi*lo + lo*hi with fp32 accumulation: <= 2.5e-5 of the fp64 oracle through the whole
+        network, inside the 1e-4 parity bar, both architectures) | 'tf32x3' (tensor cores on tf32-split operands, the first
+        tensor-core generation: parity grade, 3x slower) | 'tf32' (plain tf32, 2e-4 .. 8e-4: a speed mode, NOT parity grade) |
+        'auto' = 'bf16x3'."""
         if str(math).lower() == 'auto':
-            math = 'bf16x3' if self.ARCH == 'NATURE' else 'tf32x3'
+            math = 'bf16x3'
         mode = {'fp32': _lib.MATH_FP32, 'tf32x3': _lib.MATH_TF32X3, 'tf32': _lib.MATH_TF32,
                 'bf16x3': _lib.MATH_BF16X3}[str(math).lower()]
         _lib.check(self._lib.paacb_set_math(self.ctx, mode), 'paacb_set_math')

@@ -1,7 +1,8 @@
-"""test.py mirror (test.py:22-88): the reference's evaluation loop -- load ``<folder>/args.json`` and the newest
-checkpoint under ``<folder>/checkpoints``, play ``-tc`` episodes with up to ``-np`` random no-op starts, print
-mean / min / max / std of the episode returns.  Same flag names and dests; the action choice goes through
-``PAACLearner.choose_next_actions`` exactly as test.py:77 does, i.e. through the B200 forward + sampling kernel.
+"""Evaluation of a trained run: stands in for the reference's test.py (same flags ``-f -tc -np -gn -gf -d``, same printed
+summary).  It loads ``<folder>/args.json`` and the newest TensorFlow-1 bundle under ``<folder>/checkpoints`` (written by
+this implementation or by the reference, session.Saver), plays ``-tc`` episodes in parallel with up to ``-np`` random no-op
+starts and reports mean / min / max / std of the episode returns.  Every action comes from
+``PAACLearner.choose_next_actions`` (test.py:77), i.e. from the B200 forward + sampling kernels.
 
     python -m paac_b200.test -f logs/ -tc 5
 """
@@ -18,17 +19,6 @@ from .session import Saver, Session
 from .train import get_network_and_environment_creator
 
 
-def get_save_frame(name):
-    import imageio                               # optional, exactly as in the reference (test.py:13-20)
-
-    writer = imageio.get_writer(name + '.gif', fps=30)
-
-    def get_frame(frame):
-        writer.append_data(frame)
-
-    return get_frame
-
-
 def get_arg_parser():
     parser = argparse.ArgumentParser()
     parser.add_argument('-f', '--folder', type=str, help="Folder where to save the debugging information.", dest="folder", required=True)
@@ -40,64 +30,72 @@ def get_arg_parser():
     return parser
 
 
-def evaluate(args):
-    """-> float32 array of the test_count episode returns (test.py:32-82)."""
-    arg_file = os.path.join(args.folder, 'args.json')
-    device = args.device
-    for k, v in logger_utils.load_args(arg_file).items():
-        setattr(args, k, v)
+def run_config(args):
+    """The training run's args.json with the evaluation overrides of test.py:33-52 applied on top."""
+    device, folder = args.device, args.folder
+    for key, value in logger_utils.load_args(os.path.join(folder, 'args.json')).items():
+        setattr(args, key, value)
+    args.device, args.folder = device, folder
     args.max_global_steps = 0
-    df = args.folder
     args.debugging_folder = '/tmp/logs'
-    args.device = device
-
-    args.random_start = False
+    args.random_start = False                  # the no-op starts below replace ALE's own
     args.single_life_episodes = False
-    if args.gif_name:
-        args.visualize = 1
-
+    args.visualize = 1 if args.gif_name else getattr(args, 'visualize', False)
     args.actor_id = 0
-    rng = np.random.RandomState(int(time.time()))
-    args.random_seed = rng.randint(1000)
+    args.random_seed = int(np.random.RandomState(int(time.time())).randint(1000))
+    return args
 
+
+def restored_network(args):
     network_creator, env_creator = get_network_and_environment_creator(args)
     network = network_creator()
 
-    def set_state(state):
-        for n, t in network.variables().items():
-            t.copy_(state[n])
+    def write(state):
+        for name, tensor in network.variables().items():
+            tensor.copy_(state[name])
         network.params_changed()
 
-    saver = Saver(lambda: {n: t.detach().cpu() for n, t in network.variables().items()}, set_state,
+    saver = Saver(lambda: {n: t.detach().cpu() for n, t in network.variables().items()}, write,
                   scope=getattr(network, 'name', 'local_learning'))
+    network.init(os.path.join(args.folder, 'checkpoints'), saver, None)
+    return network, env_creator
 
+
+def gif_sink(path):
+    import imageio                               # optional dependency, only with -gn
+    writer = imageio.get_writer(path + '.gif', fps=30)
+    return writer.append_data
+
+
+def play(network, environments, num_actions, max_noops):
+    """All episodes advance in lock-step until the last one ends; a finished episode's return is final (the reference keeps
+    stepping finished environments and adds their rewards, test.py:78-82 -- a quirk, not reproduced)."""
+    session = Session()
+    states = np.asarray([env.get_initial_state() for env in environments])
+    for i, env in enumerate(environments):
+        for _ in range(random.randint(0, max_noops) if max_noops else 0):
+            states[i] = env.next(env.get_noop())[0]
+    returns = np.zeros(len(environments), dtype=np.float32)
+    live = np.ones(len(environments), dtype=bool)
+    while live.any():
+        actions, _, _ = PAACLearner.choose_next_actions(network, num_actions, states, session)
+        for j in np.nonzero(live)[0]:
+            states[j], reward, over = environments[j].next(actions[j])
+            returns[j] += reward
+            live[j] = not over
+    session.close()
+    return returns
+
+
+def evaluate(args):
+    """-> float32 array of the test_count episode returns."""
+    args = run_config(args)
+    network, env_creator = restored_network(args)
     environments = [env_creator.create_environment(i) for i in range(args.test_count)]
     if args.gif_name:
-        for i, environment in enumerate(environments):
-            environment.on_new_frame = get_save_frame(os.path.join(args.gif_folder, args.gif_name + str(i)))
-
-    sess = Session()
-    network.init(os.path.join(df, 'checkpoints'), saver, sess)
-    states = np.asarray([environment.get_initial_state() for environment in environments])
-    if args.noops != 0:
-        for i, environment in enumerate(environments):
-            for _ in range(random.randint(0, args.noops)):
-                state, _, _ = environment.next(environment.get_noop())
-                states[i] = state
-
-    episodes_over = np.zeros(args.test_count, dtype=bool)
-    rewards = np.zeros(args.test_count, dtype=np.float32)
-    while not all(episodes_over):
-        actions, _, _ = PAACLearner.choose_next_actions(network, env_creator.num_actions, states, sess)
-        for j, environment in enumerate(environments):
-            if episodes_over[j]:
-                continue                          # the reference keeps stepping finished episodes; their returns are final here
-            state, r, episode_over = environment.next(actions[j])
-            states[j] = state
-            rewards[j] += r
-            episodes_over[j] = episode_over
-    sess.close()
-    return rewards
+        for i, env in enumerate(environments):
+            env.on_new_frame = gif_sink(os.path.join(args.gif_folder, args.gif_name + str(i)))
+    return play(network, environments, env_creator.num_actions, args.noops)
 
 
 def main(argv=None):

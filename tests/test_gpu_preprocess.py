@@ -98,3 +98,25 @@ def test_zero_copy_from_pinned_host_frames(net, n):
                                             G.stream()), 'paacb_preprocess_u8')
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_planar_ring_prototype_equals_k1():
+    """SURVEY 8(f) rank 1 prototype: K1 writing only the new plane into a planar ring + the gather that rebuilds the NHWC stack
+    == K1 (bit-exact), over a ring that wraps."""
+    import ctypes as C
+    from paac_b200 import _lib
+    N, R, steps = 33, 8, 11
+    net = G.make_net('NIPS', 4)
+    rng = np.random.RandomState(21)
+    ring = torch.zeros((N, R, 84, 84), dtype=torch.uint8, device='cuda')
+    state = np.zeros((N, 84, 84, 4), np.uint8)
+    got = torch.empty((N, 84, 84, 4), dtype=torch.uint8, device='cuda')
+    for t in range(steps):
+        frames = rng.randint(0, 256, (N, 1, 2, 210, 160)).astype(np.uint8)
+        f = G.dev(frames)
+        _lib.check(net._lib.paacb_preprocess_planar_u8(net.ctx, _lib.ptr(f), 1, _lib.ptr(ring), R, t % R, N, G.stream()), 'planar')
+        state = opre.step_states(state, frames, np.zeros(N, np.uint8), ROW, COL)
+        if t >= 3:
+            _lib.check(net._lib.paacb_stack_from_planes(net.ctx, _lib.ptr(ring), R, t % R, _lib.ptr(got), N, G.stream()), 'gather')
+            torch.cuda.synchronize()
+            assert np.array_equal(got.cpu().numpy(), state), t

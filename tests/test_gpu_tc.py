@@ -17,12 +17,11 @@ MODES = ['bf16x3', 'tf32x3', 'tf32']
 
 
 def skip_unsupported(math, arch):
-    if math == 'bf16x3' and arch == 'NIPS':
-        pytest.skip('PAACB_MATH_BF16X3 covers the Nature architecture (see test_bf16x3_rejects_nips)')
+    """every tensor-core mode covers both architectures since round 2 (NIPS: 64-byte units, SWIZZLE_64B variants)"""
 
 
 @pytest.mark.parametrize('math', MODES)
-@pytest.mark.parametrize('arch,A,b', [('NATURE', 6, 1), ('NATURE', 6, 130), ('NIPS', 4, 33), ('NATURE', 18, 517)])
+@pytest.mark.parametrize('arch,A,b', [('NATURE', 6, 1), ('NATURE', 6, 130), ('NIPS', 4, 33), ('NIPS', 6, 300), ('NATURE', 18, 517)])
 def test_forward_tc_vs_oracle(math, arch, A, b):
     skip_unsupported(math, arch)
     net = G.make_net(arch, A, seed=3, math=math)
@@ -40,7 +39,7 @@ def test_forward_tc_vs_oracle(math, arch, A, b):
 
 
 @pytest.mark.parametrize('math', MODES)
-@pytest.mark.parametrize('arch,A,b', [('NATURE', 6, 5), ('NATURE', 6, 160), ('NIPS', 4, 97), ('NATURE', 4, 1111)])
+@pytest.mark.parametrize('arch,A,b', [('NATURE', 6, 5), ('NATURE', 6, 160), ('NIPS', 4, 97), ('NIPS', 6, 160), ('NATURE', 4, 1111)])
 def test_backward_tc_vs_autograd(math, arch, A, b):
     """Gradients (and every layer's dZ) against fp64 autograd whose ReLU masks are the GPU's own activations
     (oracle.network.masked_loss_and_grads): like-for-like, immune to a pre-activation rounding across zero."""
@@ -63,15 +62,15 @@ def test_backward_tc_vs_autograd(math, arch, A, b):
         assert_close(got_dz.reshape(d.shape), d, TOL[math], 'dZ of layer %d' % i)
 
 
-def test_bf16x3_rejects_nips():
-    from paac_b200 import _lib
-    with pytest.raises(_lib.PaacbError):
-        G.make_net('NIPS', 4, seed=3, math='bf16x3')
+def test_auto_math_is_bf16x3_for_both_architectures():
+    for arch in ('NIPS', 'NATURE'):
+        net = G.make_net(arch, 4, seed=3, math='auto')
+        assert net.math == 'bf16x3' and net._lib.paacb_get_math(net.ctx) == 3
 
 
-@pytest.mark.parametrize('math', ['bf16x3', 'tf32x3'])
-def test_engine_update_tc_vs_oracle_composite(math):
-    arch, A, N, T = 'NATURE', 6, 16, 5
+@pytest.mark.parametrize('arch,math', [('NATURE', 'bf16x3'), ('NATURE', 'tf32x3'), ('NIPS', 'bf16x3')])
+def test_engine_update_tc_vs_oracle_composite(arch, math):
+    A, N, T = 6, 16, 5
     net = G.make_net(arch, A, seed=5, math=math)
     eng = RolloutEngine(net, N, T, seed=9)
     rng = np.random.RandomState(0)
