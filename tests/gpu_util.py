@@ -102,3 +102,35 @@ def clip_rmsprop(net, params, ms, mom, grads, gscale, lr, rho, eps, momentum, cl
                                            clip_type, p(norm), p(ws), stream()), 'paacb_clip_rmsprop')
     torch.cuda.synchronize()
     return t[0].cpu().numpy(), t[1].cpu().numpy(), t[2].cpu().numpy(), float(norm.item())
+
+
+def fp64_masked_grads_cuda(arch, A, params_flat, flat_states, acts, dlogits, dv, chunk=1024):
+    """The fp64 arbiter at sizes the CPU oracle cannot reach: oracle.network.masked_loss_and_grads restated with torch ops ON
+    THE GPU (float64 conv2d / matmul), chunk by chunk.  The backward is linear in (dlogits, dv), so the gradient of the loss
+    is the vector-Jacobian product of (logits, v) with the head gradients the implementation itself was given; every ReLU
+    is a multiplication with the implementation's own 0/1 mask (acts[i] > 0), exactly as in the CPU oracle.
+    acts: per-layer activations [B, ...] NHWC + hidden [B, F] (CUDA tensors); returns dict name -> float64 numpy."""
+    from oracle import network
+    import torch.nn.functional as F
+    names = [n for n, _, _ in network.param_specs(arch, A)]
+    P = {n: torch.as_tensor(v).cuda().double().requires_grad_(True)
+         for n, v in network.unflatten_params(np.asarray(params_flat), arch, A).items()}
+    a = network.ARCH[arch.upper()]
+    total = {n: torch.zeros_like(P[n]) for n in names}
+    B = flat_states.shape[0]
+    scale = torch.tensor(float(network.INPUT_SCALE), dtype=torch.float64, device='cuda')
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        x = (flat_states[lo:hi].double() * scale).permute(0, 3, 1, 2)
+        for li, (name, k, cin, cout, stride) in enumerate(a['convs']):
+            z = F.conv2d(x, P[name + '_weights'].permute(3, 2, 0, 1), P[name + '_biases'], stride=stride)
+            x = z * (acts[li][lo:hi] > 0).double().permute(0, 3, 1, 2)
+        flat = x.permute(0, 2, 3, 1).reshape(hi - lo, -1)
+        fname = a['fc'][0]
+        h = (flat @ P[fname + '_weights'] + P[fname + '_biases']) * (acts[len(a['convs'])][lo:hi] > 0).double()
+        logits = h @ P['actor_output_weights'] + P['actor_output_biases']
+        v = (h @ P['critic_output_weights'] + P['critic_output_biases']).reshape(-1)
+        gs = torch.autograd.grad([logits, v], [P[n] for n in names], [dlogits[lo:hi].double(), dv[lo:hi].double()])
+        for n, g in zip(names, gs):
+            total[n] += g
+    return {n: total[n].cpu().numpy() for n in names}

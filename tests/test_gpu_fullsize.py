@@ -135,7 +135,9 @@ def test_full_size_cycle_vs_oracle_and_fp32_anchor(rollout):
     assert_close(eng.pi[tidx].cpu().numpy(), ref['pi'].numpy(), 1e-4, 'full-size pi (64 samples)')
     assert_close(eng.v[tidx].cpu().numpy(), ref['v'].numpy(), 1e-4, 'full-size v (64 samples)')
     del layers
-    # (2) the whole batch against the fp32 SIMT anchor: forward outputs and the flat gradient from the SAME dlogits / dv
+    # (2) the whole batch: forward outputs against the fp32 SIMT anchor, and the flat gradient of BOTH arithmetic modes
+    # against the fp64 arbiter evaluated with torch on the GPU (gpu_util.fp64_masked_grads_cuda: same dlogits / dv, each
+    # implementation's own ReLU masks -- the convention of every backward parity test)
     net32 = G.make_net(ARCH, A, seed=5, math='fp32')
     net32.set_params(p0_np)
     pi32 = torch.empty((B, A), device='cuda'); v32 = torch.empty((B,), device='cuda')
@@ -149,7 +151,15 @@ def test_full_size_cycle_vs_oracle_and_fp32_anchor(rollout):
     torch.cuda.synchronize()
     assert_close(eng.pi.cpu().numpy(), pi32.cpu().numpy(), 1e-4, 'full-size pi vs fp32 anchor')
     assert_close(eng.v.cpu().numpy(), v32.cpu().numpy(), 1e-4, 'full-size v vs fp32 anchor')
-    got = network.unflatten_params(eng.grads.cpu().numpy(), ARCH, A)
-    want = network.unflatten_params(g32.cpu().numpy(), ARCH, A)
-    for name, _, _ in network.param_specs(ARCH, A):
-        assert_close(got[name], want[name], 1e-4, 'full-size gradient ' + name)
+    failures = []
+    for label, nn, ws, g in (('bf16x3', net, eng.fwd_ws, eng.grads), ('fp32 anchor', net32, ws32, g32)):
+        acts = nn.layer_tensors(ws, B)
+        want = G.fp64_masked_grads_cuda(ARCH, A, p0_np, flat, acts, eng.dlogits, eng.dv)
+        del acts
+        got = network.unflatten_params(g.cpu().numpy(), ARCH, A)
+        for name, _, _ in network.param_specs(ARCH, A):
+            try:
+                assert_close(got[name], want[name], 1e-4, 'full-size gradient %s [%s vs fp64]' % (name, label))
+            except AssertionError as e:
+                failures.append(str(e))
+    assert not failures, '\n'.join(failures)

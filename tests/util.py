@@ -27,7 +27,7 @@ def elem_err(x, r, significant=SIGNIFICANT):
     """(max, median, count) of the element-wise relative error over entries with |r| > significant * max|r|."""
     x = np.asarray(x, np.float64).reshape(-1)
     r = np.asarray(r, np.float64).reshape(-1)
-    if not r.size:
+    if not r.size or np.max(np.abs(r)) < 1e-30:        # a tensor that is zero to fp32 has no relative error to speak of
         return 0.0, 0.0, 0
     m = np.abs(r) > significant * np.max(np.abs(r))
     if not m.any():
