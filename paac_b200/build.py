@@ -25,10 +25,6 @@ if os.environ.get('PAACB_ABLATIONS'):          # measurement build: keeps the PA
     CFLAGS.append('-DPAACB_ABLATIONS')
     OBJ_DIR = os.path.join(ROOT, 'build', 'paacb_abl')
     LIB = os.path.join(HERE, 'libpaacb_abl.so')
-if os.environ.get('PAACB_ABLATIONS'):          # measurement build: keeps the PAACB_DBG ablation switches in the kernels
-    CFLAGS.append('-DPAACB_ABLATIONS')
-    OBJ_DIR = os.path.join(ROOT, 'build', 'paacb_abl')
-    LIB = os.path.join(HERE, 'libpaacb_abl.so')
 
 
 def sources():

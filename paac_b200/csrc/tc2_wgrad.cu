@@ -30,7 +30,8 @@ struct Wg<0> {
   static constexpr int STAGES = 2, KT = 2, BN = 32, KSTEPS = 14, A_KSTEP = 512, B_KSTEP = 1024;
   static constexpr int A_SWZ = SWZ_32B, A_SBO = 256, B_SWZ = SWZ_64B, B_SBO = 512;
   static constexpr int STAGES_PER_SAMPLE = 2, SAMPLES_PER_STAGE = 1;
-  static constexpr int K = 256, KIND = 0, LAYER = 0, MROWS = 128;
+  static constexpr int K = 256, KIND = 0, LAYER = 0, MROWS = 128, CONCAT_KT = 2;
+  __device__ static constexpr int pos(int t) { return 16 * t; }
   __device__ static int a_off(int kt) { return kt * 21 * 32; }                               // within plane 0's slot
   __device__ static int a_lbo(int) { return A_SLOT; }
   // row m of k-tile kt -> weight row k = kh * 32 + kw * 4 + c: group g = m >> 4 is (kw / 4 = g >> 2, kh & 3 = g & 3)
@@ -40,10 +41,13 @@ struct Wg<0> {
 template <>
 struct Wg<1> {
   static constexpr int A_PARTS = 2, A_PIECES = 2, A_SLOT = 15360, A_BOX = 128 * 10 * 12, B_SLOT = 14336, B_BOX = 128 * 10 * 10;
-  static constexpr int STAGES = 2, KT = 4, BN = 64, KSTEPS = 7, A_KSTEP = 2048, B_KSTEP = 2048;
+  // K-steps: dZ2 is 9 x 9 inside the 10 x 10 enumeration, so the last position that carries data is 10 * 8 + 8 = 88:
+  // 6 steps of 16 positions, not 7
+  static constexpr int STAGES = 2, KT = 4, BN = 64, KSTEPS = 6, A_KSTEP = 2048, B_KSTEP = 2048;
   static constexpr int A_SWZ = SWZ_128B, A_SBO = 1024, B_SWZ = SWZ_128B, B_SBO = 1024;
   static constexpr int STAGES_PER_SAMPLE = 1, SAMPLES_PER_STAGE = 1;
-  static constexpr int K = 512, KIND = 1, LAYER = 1, MROWS = 128;
+  static constexpr int K = 512, KIND = 1, LAYER = 1, MROWS = 128, CONCAT_KT = 4;
+  __device__ static constexpr int pos(int t) { return 16 * t; }
   __device__ static int a_off(int kt) { return (kt >> 1) * 10 * 128; }                       // kh = kt: plane kt & 1, row offset kt / 2
   __device__ static int a_lbo(int) { return 128; }
   __device__ static int k_of(int kt, int m) { return kt * 128 + m; }
@@ -52,10 +56,16 @@ struct Wg<1> {
 template <>
 struct Wg<2> {
   static constexpr int A_PARTS = 1, A_PIECES = 2, A_SLOT = 24576, A_BOX = 128 * 9 * 21, B_SLOT = 22528, B_BOX = 128 * 9 * 9 * 2;
-  static constexpr int STAGES = 2, KT = 5, BN = 64, KSTEPS = 11, A_KSTEP = 2048, B_KSTEP = 2048;
+  // K-steps: the reduction index of an MMA is 16 CONSECUTIVE positions starting anywhere (a start address, like a tap), so
+  // the positions that carry no data are skipped: dZ3 is 7 x 7 inside the 9 x 9 enumeration, its last data position is
+  // 9 * 6 + 6 = 60 -> 4 steps per sample starting at the sample's position 0 (8 per stage instead of the 11 a flat walk
+  // over 162 positions takes).  TMEM: 3 k-tiles accumulate [X_hi^T dZ_hi + X_lo^T dZ_hi | X_hi^T dZ_lo] (two MMAs per
+  // step, N = 128 and N = 64), the other 2 a single 64-column sum (three MMAs of N = 64): 3 * 128 + 2 * 64 = 512 columns.
+  static constexpr int STAGES = 2, KT = 5, BN = 64, KSTEPS = 8, A_KSTEP = 2048, B_KSTEP = 2048;
   static constexpr int A_SWZ = SWZ_128B, A_SBO = 1024, B_SWZ = SWZ_128B, B_SBO = 1024;
   static constexpr int STAGES_PER_SAMPLE = 1, SAMPLES_PER_STAGE = 2;
-  static constexpr int K = 576, KIND = 2, LAYER = 2, MROWS = 128;
+  static constexpr int K = 576, KIND = 2, LAYER = 2, MROWS = 128, CONCAT_KT = 3;
+  __device__ static constexpr int pos(int t) { return (t >> 2) * 81 + (t & 3) * 16; }
   __device__ static int tap_off(int tap) { return ((tap / 3) * 9 + (tap % 3)) * 128; }
   __device__ static int a_off(int kt) { return tap_off(2 * kt); }
   __device__ static int a_lbo(int kt) { return kt < 4 ? tap_off(2 * kt + 1) - tap_off(2 * kt) : 128; }
@@ -71,7 +81,8 @@ struct Wg<3> {
   static constexpr int STAGES = 2, KT = 2, BN = 16, KSTEPS = 14, A_KSTEP = 512, B_KSTEP = 512;
   static constexpr int A_SWZ = SWZ_32B, A_SBO = 256, B_SWZ = SWZ_32B, B_SBO = 256;
   static constexpr int STAGES_PER_SAMPLE = 2, SAMPLES_PER_STAGE = 1;
-  static constexpr int K = 256, KIND = 0, LAYER = 0, MROWS = 128;
+  static constexpr int K = 256, KIND = 0, LAYER = 0, MROWS = 128, CONCAT_KT = 2;
+  __device__ static constexpr int pos(int t) { return 16 * t; }
   __device__ static int a_off(int kt) { return kt * 21 * 32; }
   __device__ static int a_lbo(int) { return A_SLOT; }
   __device__ static int k_of(int kt, int m) { return (4 * kt + ((m >> 4) & 3)) * 32 + (m >> 6) * 16 + (m & 15); }
@@ -83,10 +94,11 @@ struct Wg<3> {
 template <>
 struct Wg<4> {
   static constexpr int A_PARTS = 2, A_PIECES = 2, A_SLOT = 8192, A_BOX = 64 * 10 * 12, B_SLOT = 7168, B_BOX = 64 * 10 * 10;
-  static constexpr int STAGES = 2, KT = 4, BN = 32, KSTEPS = 7, A_KSTEP = 1024, B_KSTEP = 1024;
+  static constexpr int STAGES = 2, KT = 4, BN = 32, KSTEPS = 6, A_KSTEP = 1024, B_KSTEP = 1024;      // 6 steps: see Wg<1>
   static constexpr int A_SWZ = SWZ_64B, A_SBO = 512, B_SWZ = SWZ_64B, B_SBO = 512;
   static constexpr int STAGES_PER_SAMPLE = 1, SAMPLES_PER_STAGE = 1;
-  static constexpr int K = 256, KIND = 1, LAYER = 1, MROWS = 64;
+  static constexpr int K = 256, KIND = 1, LAYER = 1, MROWS = 64, CONCAT_KT = 4;
+  __device__ static constexpr int pos(int t) { return 16 * t; }
   __device__ static int a_off(int kt) { return (kt >> 1) * 10 * 64; }                        // kh = kt: plane kt & 1, row offset kt / 2
   __device__ static int a_lbo(int) { return 64; }
   __device__ static int k_of(int kt, int m) { return m < 64 ? kt * 64 + m : -1; }
@@ -116,11 +128,13 @@ struct Wg2Cfg {
   static constexpr int THREADS = 192 + (U8_A ? CONV_THREADS : 0);
   static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + (2 * W::STAGES + 1) * 8 + 16;
   // dZ_hi and dZ_lo slots lie back to back: one MMA of N = 2 * BN evaluates X_hi^T * [dZ_hi | dZ_lo] (X is read from shared
-  // memory once), a second of N = BN adds X_lo^T * dZ_hi.  conv3 has 5 k-tiles: 5 * 128 columns do not fit in TMEM, it
-  // keeps three MMAs of N = BN per K-step.
-  static constexpr bool CONCAT = (W::KT * 2 * W::BN <= 512);
-  static constexpr int ACC_COLS = CONCAT ? 2 * W::BN : W::BN;
-  static constexpr int TMEM_COLS = (W::KT * ACC_COLS <= 128) ? 128 : ((W::KT * ACC_COLS <= 256) ? 256 : 512);
+  // memory once), a second of N = BN adds X_lo^T * dZ_hi.  The first CONCAT_KT k-tiles work that way (2 * BN columns each);
+  // conv3's 5 x 128 columns do not fit in TMEM: its last two k-tiles keep three MMAs of N = BN per K-step (BN columns).
+  static constexpr int NCAT = W::CONCAT_KT;
+  __host__ __device__ static constexpr int acc_col(int kt) { return kt < NCAT ? kt * 2 * W::BN : NCAT * 2 * W::BN + (kt - NCAT) * W::BN; }
+  static constexpr int ACC_TOTAL = NCAT * 2 * W::BN + (W::KT - NCAT) * W::BN;
+  static constexpr int TMEM_COLS = (ACC_TOTAL <= 128) ? 128 : ((ACC_TOTAL <= 256) ? 256 : 512);
+  static_assert(ACC_TOTAL <= 512, "TMEM columns");
   static_assert(W::A_BOX <= W::A_SLOT && W::B_BOX <= W::B_SLOT, "slot too small");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -211,7 +225,8 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc = make_idesc_bf16(W::BN, 1, 1);
     constexpr uint32_t idesc_full = make_idesc_bf16(2 * W::BN, 1, 1);
-    const uint64_t bdesc0 = make_smem_desc(0, Cfg::CONCAT ? W::B_SLOT : 16, W::B_SBO, W::B_SWZ);
+    const uint64_t bdesc_cat = make_smem_desc(0, W::B_SLOT, W::B_SBO, W::B_SWZ);      // N = 2 BN: the second 64-wide atom is the lo slot
+    const uint64_t bdesc_one = make_smem_desc(0, 16, W::B_SBO, W::B_SWZ);
     int stage = 0;
     uint32_t phase = 0;
     for (int s = s_begin; s < s_end; ++s) {
@@ -228,7 +243,9 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
 #pragma unroll
         for (int kt = 0; kt < W::KT; ++kt) {
           if ((PAACB_DBGV(p.dbg) & 128) && kt >= W::KT / 2) continue;
-          const uint32_t d = tmem_base + (uint32_t)(kt * Cfg::ACC_COLS);
+          const uint32_t d = tmem_base + (uint32_t)Cfg::acc_col(kt);
+          const bool cat = kt < Cfg::NCAT;
+          const uint64_t bdesc0 = cat ? bdesc_cat : bdesc_one;
           const uint64_t adesc0 = make_smem_desc(0, (uint32_t)W::a_lbo(kt), W::A_SBO, W::A_SWZ);
           uint32_t a_hi, a_lo = 0;
           if constexpr (W::KIND == 0) {
@@ -243,8 +260,8 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
           const uint32_t b_hi = b_st + b_rel, b_lo = b_hi + W::B_SLOT;
 #pragma unroll
           for (int t = 0; t < W::KSTEPS; ++t) {
-            const uint32_t ao = (uint32_t)(t * W::A_KSTEP), bo = (uint32_t)(t * W::B_KSTEP);
-            if constexpr (Cfg::CONCAT) {
+            const uint32_t ao = (uint32_t)(W::pos(t) * (W::A_KSTEP / 16)), bo = (uint32_t)(W::pos(t) * (W::B_KSTEP / 16));
+            if (cat) {
               umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc_full, t > 0 ? 1u : first);
             } else {
               umma_bf16(d, desc_with_addr(adesc0, a_hi + ao), desc_with_addr(bdesc0, b_hi + bo), idesc, t > 0 ? 1u : first);
@@ -346,7 +363,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
       if constexpr (W::BN == 16) {
         // 16 output channels: the accumulator is [X^T dZ_hi (16 columns) | X^T dZ_lo (16 columns)], one 32-column load
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(kt * Cfg::ACC_COLS), v);
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)Cfg::acc_col(kt), v);
         tmem_ld_wait();
         if (k >= 0) {
           float4* dst = reinterpret_cast<float4*>(p.dw + (int64_t)k * W::BN);
@@ -362,9 +379,9 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
 #pragma unroll
       for (int c0 = 0; c0 < W::BN; c0 += 32) {
         uint32_t v[32];
-        const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(kt * Cfg::ACC_COLS + c0);
+        const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(Cfg::acc_col(kt) + c0);
         tmem_ld32(tcol, v);
-        if constexpr (Cfg::CONCAT) {
+        if (kt < Cfg::NCAT) {
           uint32_t v2[32];
           tmem_ld32(tcol + (uint32_t)W::BN, v2);
           tmem_ld_wait();

@@ -13,14 +13,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SWITCHES = [(0, 'baseline'), (1, 'conv1 fwd: no stores'), (2, 'conv1 fwd: no epilogue arithmetic'), (4, 'conv1 fwd: 1 of 8 MMAs'),
             (8, 'conv1 fwd: no A loads'), (16, 'wgrad: hi*hi MMAs only'), (32, 'wgrad: no TMA loads'),
             (64, 'conv1 wgrad: no uint8 conversion'), (128, 'wgrad: half the k-tiles'),
-            (256, 'conv fwd/dgrad: no A_lo MMAs'), (512, 'conv fwd/dgrad: no stores'), (1024, 'conv fwd/dgrad: no patch loads')]
-KERNELS = ['conv1_fwd', 'conv2_fwd', 'conv3_fwd', 'conv2_dgrad', 'conv3_dgrad', 'conv1_wgrad', 'conv2_wgrad', 'conv3_wgrad']
+            (256, 'conv fwd/dgrad: no A_lo MMAs'), (512, 'conv fwd/dgrad: no stores'), (1024, 'conv fwd/dgrad: no patch loads'),
+            (2048, 'fc fwd/dgrad/wgrad: no TMA loads')]
+KERNELS = ['conv1_fwd', 'conv2_fwd', 'conv3_fwd', 'fc4_fwd', 'conv2_dgrad', 'conv3_dgrad', 'fc4_dgrad', 'conv1_wgrad', 'conv2_wgrad',
+           'conv3_wgrad', 'fc4_wgrad']
 
 
 def main():
+    # the switches exist only in the measurement build (PAACB_ABLATIONS=1 python -m paac_b200.build -> libpaacb_abl.so)
+    abl = os.path.join(ROOT, 'paac_b200', 'libpaacb_abl.so')
+    if not os.path.exists(abl):
+        raise SystemExit('build the measurement library first: PAACB_ABLATIONS=1 python -m paac_b200.build')
+    only = [int(a) for a in sys.argv[1:]]           # optional: the switches to run (0 = baseline is always run)
     rows = []
     for dbg, what in SWITCHES:
-        env = dict(os.environ, PAACB_DBG=str(dbg))
+        if only and dbg and dbg not in only:
+            continue
+        env = dict(os.environ, PAACB_DBG=str(dbg), PAACB_LIB=abl)
         out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '10', '--no_cpu_baseline', '--no_variants',
                               '--no_e2e'], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
         line = [l for l in out.splitlines() if l.startswith('{')][-1]
