@@ -84,7 +84,7 @@ def run_reference(args):
         return
     from oracle import cpu_baseline
     cores = os.cpu_count() or 1
-    warm = max(args.warmup, 1)
+    warm = max(args.warmup, 3)              # the same warm-up rule as the B200 arm
     sps, ms, done, cores = cpu_baseline.time_cycles(args.arch, args.ref_envs, T_MAX, NUM_ACTIONS, steps=args.steps,
                                                     warmup=warm, cores=cores, max_seconds=240)
     sample = ('restated reference CPU path (oracle port, not TF1): %d timed update cycles (after %d warm-up cycles) of %d envs x '

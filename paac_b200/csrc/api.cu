@@ -204,7 +204,9 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     // but 13-60 % SLOWER than one launch per layer (profiles/r02_pipe_tune.json; DESIGN.md section 3.3 says why), so the
     // product path launches the layers one by one.  Role sizes: CTAs of conv1 / conv2 / conv3 out of the device's SMs, the fc
     // layer takes the rest; PAACB_PIPE_SPLIT="a,b,c" overrides the split, PAACB_PIPE_MIN_BATCH the smallest batch that uses it.
-    const char* e = getenv("PAACB_PIPE");
+    const char* e = getenv("PAACB_PDL");
+    c->pdl_on = (e == nullptr) ? 1 : atoi(e);
+    e = getenv("PAACB_PIPE");
     c->pipe_on = (e == nullptr) ? 0 : atoi(e);
     e = getenv("PAACB_PIPE_MIN_BATCH");
     c->pipe_min_batch = (e == nullptr) ? 1 : atoll(e);
@@ -408,7 +410,12 @@ int paacb_params_changed(paacb_ctx* ctx) {
 // the operand images of the forward for the parameters at d_params: bf16 hi/lo transposes + conv1 int8 digits (bf16x3), or
 // the pre-swizzled tf32 images (+ NIPS conv1 int8 digits) of the tf32 modes.  Cached in the context between calls.
 static int pack_forward_images(const paacb_ctx* ctx, const float* d_params, cudaStream_t st) {
-  if (ctx->math == PAACB_MATH_BF16X3) return launch_pack_bf16_weights(ctx, d_params, st);
+  if (ctx->math == PAACB_MATH_BF16X3) {
+    // forward AND data-gradient images: the backward then starts with no pack kernel in front of its first GEMM (the
+    // kernels of a backward are launched as programmatic dependents of each other and load their weights early)
+    const int rc = launch_pack_bf16_weights(ctx, d_params, st);
+    return rc != PAACB_OK ? rc : launch_pack_bf16_dgrad_weights(ctx, d_params, st);
+  }
   if (ctx->math == PAACB_MATH_FP32) return PAACB_OK;
   for (int l = 0; l < ctx->n_layers; ++l) {
     const LayerGeom& g = ctx->layer[l];
@@ -634,7 +641,8 @@ static int backward_bf16_tail(const paacb_ctx* ctx, const float* d_params, const
                               d_grads + ctx->layer[L - 1].b_off, d_params + ctx->actor_w_off, d_params + ctx->critic_w_off,
                               d_dlogits, d_dv, batch, nullptr, d_grads + ctx->actor_w_off, d_grads + ctx->actor_b_off,
                               d_grads + ctx->critic_w_off, d_grads + ctx->critic_b_off, st);
-    if (rc == PAACB_OK) rc = launch_pack_bf16_dgrad_weights(ctx, d_params, st);
+    // (the data-gradient images of the weights are cached with the forward images; the forward that produced d_fwd_ws made them)
+    if (rc == PAACB_OK && !(ctx->fwd_img_valid && ctx->fwd_img_src == d_params)) rc = launch_pack_bf16_dgrad_weights(ctx, d_params, st);
     // data gradients first (they produce the dZ planes and the bias gradients), then the weight gradients
     if (rc == PAACB_OK) rc = launch_fc_dgrad_bf16(ctx, L - 1, d_fwd_ws, d_bwd_ws, d_grads, batch, st);
     for (int l = L - 2; l >= 1 && rc == PAACB_OK; --l) rc = launch_conv_dgrad_bf16(ctx, l, d_fwd_ws, d_bwd_ws, d_grads, batch, st);

@@ -137,6 +137,7 @@ struct paacb_ctx {
   uint32_t* pipe_err;
   mutable int pipe_nbuf;
   mutable void* pipe_stream[kPipeBufs];
+  int pdl_on;                   // PAACB_PDL (default 1): programmatic dependent launch between the kernels of one forward / backward
   int sm_reserve;               // paacb_set_sm_reserve: SMs the persistent conv weight-gradient kernels leave free (multi-GPU)
   int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };
@@ -154,6 +155,24 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 void prof_drain(const paacb_ctx* ctx);
+
+// kernel<<<grid, block, smem, st>>>(args...), optionally with the programmatic-stream-serialization attribute (tc_ptx.cuh)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 // bracket a kernel launch: PAACB_LAUNCH_BEGIN(ctx, kid, st); kernel<<<...>>>(...); PAACB_LAUNCH_END(ctx, kid, st);
 #define PAACB_LAUNCH_BEGIN(ctx, kid, st)                                               \
   do {                                                                                 \

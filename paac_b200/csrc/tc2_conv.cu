@@ -175,6 +175,7 @@ int launch_pack_bf16_dgrad_weights(const paacb_ctx* ctx, const float* params, cu
 // ------------------------------------------------------------------------------------------------
 template <int G>
 static int launch_convk(const paacb_ctx* ctx, const ConvKParams& p, int slot, cudaStream_t st) {
+  // always the successor of another kernel of the same forward / backward: programmatic dependent launch (tc_ptx.cuh)
   using Cfg = ConvKCfg<G>;
   static DeviceOnce attr_set;   // kernel attributes are per device: one bit per device index
   if (!attr_set.done(ctx->device)) {
@@ -191,7 +192,7 @@ static int launch_convk(const paacb_ctx* ctx, const ConvKParams& p, int slot, cu
   }
   const unsigned grid = (unsigned)(p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, slot, st);
-  convk_kernel<G><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  launch_kernel(convk_kernel<G>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, ctx->pdl_on != 0, p);
   PAACB_LAUNCH_END(ctx, slot, st);
   return PAACB_OK;
 }

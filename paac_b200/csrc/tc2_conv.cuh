@@ -172,6 +172,7 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
+  pdl_launch_dependents();                        // the next kernel's prologue may run under this kernel's tail (tc_ptx.cuh)
   if (tid == 0) {
     for (int s = 0; s < NSLOTS; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -186,6 +187,12 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmW[0]);
+    // the layer's weights depend on no kernel of this forward / backward: their loads start before the wait below
+    mbar_arrive_expect_tx(w_bar, Cfg::W_BYTES);
+    for (int piece = 0; piece < 2; ++piece)
+      for (int acc = 0; acc < NACC; ++acc)
+        for (int kb = 0; kb < Ge::KB; ++kb)
+          tma_load_2d(wsm + kb * Cfg::KB_BYTES + (piece * NACC + acc) * (BN * 128), &p.tmW[piece], kb * 64, acc * BN, w_bar);
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   if constexpr (!Ge::DGRAD) {
@@ -194,16 +201,12 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                     // everything below reads or writes what other kernels produce / consume
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one_sync()) {
-      mbar_arrive_expect_tx(w_bar, Cfg::W_BYTES);
-      for (int piece = 0; piece < 2; ++piece)
-        for (int acc = 0; acc < NACC; ++acc)
-          for (int kb = 0; kb < Ge::KB; ++kb)
-            tma_load_2d(wsm + kb * Cfg::KB_BYTES + (piece * NACC + acc) * (BN * 128), &p.tmW[piece], kb * 64, acc * BN, w_bar);
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = cta; tile < p.num_tiles; tile += ncta) {

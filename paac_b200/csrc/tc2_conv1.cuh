@@ -85,6 +85,7 @@ __device__ __forceinline__ void conv1_i8_body(const Conv1Params& p, const int ct
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
+  pdl_launch_dependents();                        // tc_ptx.cuh: the next kernel's prologue may run under this kernel's tail
   if (tid == 0) {
     for (int s = 0; s < kC1_NSLOTS; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -98,20 +99,21 @@ __device__ __forceinline__ void conv1_i8_body(const Conv1Params& p, const int ct
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmW);
+    mbar_arrive_expect_tx(w_bar, kC1_WBYTES);     // the weights depend on no kernel of this forward: loaded before pdl_wait
+    tma_load_2d(wsm, &p.tmW, 0, 0, w_bar);
+    tma_load_2d(wsm + kC1_ND * 128, &p.tmW, 128, 0, w_bar);
   }
   if (tid >= 64 && tid < 64 + NC) s_sb[tid - 64] = make_float2(__ldg(p.wscale + tid - 64), __ldg(p.bias + tid - 64));
   if (warp == 1) tmem_alloc(tmem_slot, kC1_TMEM);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (elect_one_sync()) {
-      mbar_arrive_expect_tx(w_bar, kC1_WBYTES);
-      tma_load_2d(wsm, &p.tmW, 0, 0, w_bar);
-      tma_load_2d(wsm + kC1_ND * 128, &p.tmW, 128, 0, w_bar);
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = cta; tile < p.num_tiles; tile += ncta) {

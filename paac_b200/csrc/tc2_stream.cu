@@ -32,7 +32,7 @@ static int launch_stream(const paacb_ctx* ctx, const StreamParams& p, int slot, 
   const int units = p.m_tiles * p.n_tiles * p.k_splits;
   const unsigned grid = (unsigned)(units < ctx->num_sms ? units : ctx->num_sms);
   PAACB_LAUNCH_BEGIN(ctx, slot, st);
-  stream_gemm_kernel<BN, MODE><<<grid, kStreamThreads, Cfg::SMEM_BYTES, st>>>(p);
+  launch_kernel(stream_gemm_kernel<BN, MODE>, grid, kStreamThreads, Cfg::SMEM_BYTES, st, ctx->pdl_on != 0, p);
   PAACB_LAUNCH_END(ctx, slot, st);
   return PAACB_OK;
 }

@@ -76,6 +76,7 @@ __device__ __forceinline__ void stream_gemm_body(const StreamParams& p, const in
   const int warp = tid >> 5, lane = tid & 31;
   const int units = p.m_tiles * p.n_tiles * p.k_splits;
 
+  pdl_launch_dependents();                        // tc_ptx.cuh: the next kernel's prologue may run under this kernel's tail
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -93,6 +94,7 @@ __device__ __forceinline__ void stream_gemm_body(const StreamParams& p, const in
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   // unit -> (split, m-tile, n-tile); n fastest so that CTAs running together share the A tile in L2

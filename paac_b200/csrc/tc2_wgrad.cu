@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
   const int s_begin = (int)blockIdx.x * per;
   const int s_end = (s_begin + per < p.stages_total) ? s_begin + per : p.stages_total;
 
+  pdl_launch_dependents();                        // tc_ptx.cuh: the next kernel's prologue may run under this kernel's tail
   // zero the operand area once: rows of a slot the TMA boxes never write must read as 0 (dZ) / finite (X)
   for (int i = tid * 16; i < Cfg::DATA_BYTES; i += Cfg::THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(Wg2Cfg<L>::THREADS, 1) wgrad2_kernel(const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                     // the shared-memory zero fill above ran under the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -431,7 +433,7 @@ static int launch_wg2(const paacb_ctx* ctx, const Wg2Params& p, cudaStream_t st)
   const int sms = ctx->num_sms - ctx->sm_reserve > 0 ? ctx->num_sms - ctx->sm_reserve : 1;
   const unsigned grid = (unsigned)(p.stages_total < sms ? p.stages_total : sms);
   PAACB_LAUNCH_BEGIN(ctx, K_WGRAD0 + Wg<L>::LAYER, st);
-  wgrad2_kernel<L><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  launch_kernel(wgrad2_kernel<L>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, ctx->pdl_on != 0, p);
   PAACB_LAUNCH_END(ctx, K_WGRAD0 + Wg<L>::LAYER, st);
   return PAACB_OK;
 }

@@ -273,6 +273,16 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// Programmatic dependent launch.  A kernel launched with the programmatic-stream-serialization attribute may START before
+// the kernel in front of it in the stream has finished (as soon as every CTA of that kernel has called
+// pdl_launch_dependents() or exited, and an SM has room); it must not touch anything the earlier kernel produces, or write
+// anything it reads, before pdl_wait() returns (= the earlier kernel has completed and its writes are visible).  The
+// persistent kernels here do everything that depends on no other kernel first -- barrier init, TMEM allocation, the TMA loads
+// of their resident weights -- and that prologue then runs under the tail of the previous kernel.  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): |x - hi - lo| <= 2^-18 |x| (round to nearest twice)
 __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
   const __nv_bfloat16 h = __float2bfloat16_rn(x);

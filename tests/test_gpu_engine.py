@@ -168,7 +168,10 @@ def test_graph_replay_equals_eager(arch, math, mode):
             assert np.array_equal(e[0], g[0]) and np.array_equal(e[1].view(np.int32), g[1].view(np.int32))
             assert np.array_equal(e[2].view(np.int32), g[2].view(np.int32)) and e[3] == g[3]
         assert abs(e[3] - g[3]) <= 1e-4 * max(1.0, abs(e[3])) and abs(e[4] - g[4]) <= 1e-4 * e[4]
-        assert_close(g[5], e[5], 1e-5, 'parameters after cycle %d, graph replay vs eager' % c, elem_max=None)
+        # the fp32 atomics of the weight gradients land in a different order on every run: after the first update the two
+        # runs differ by rounding, and a pre-activation that rounds across zero flips a ReLU (observed: a repeatable 3.6e-5
+        # jump at cycle 3 in about half of the runs, eager vs eager as well) -- later cycles are held to the parity bar
+        assert_close(g[5], e[5], 1e-5 if c == 0 else 1e-4, 'parameters after cycle %d, graph replay vs eager' % c, elem_max=None)
     assert not np.array_equal(out[True][0][5], out[True][-1][5])
 
 
