@@ -115,7 +115,7 @@ def get_arg_parser():
     parser.add_argument('-df', '--debugging_folder', default='logs/', type=str, help="Folder where to save the debugging information.", dest="debugging_folder")
     parser.add_argument('-rs', '--random_start', default=True, type=bool_arg, help="Whether or not to start with 30 noops for each env. Default True", dest="random_start")
     # ---- additions (not in the reference) ----
-    parser.add_argument('--math', default='auto', choices=['auto', 'fp32', 'tf32x3', 'tf32', 'bf16x3'], help="Arithmetic of the conv/fc contractions. The reference trains in fp32; 'auto' = bf16x3: tensor cores on bf16-split operands with fp32 accumulation, within 2.5e-5 of an fp64 evaluation through the whole network (the parity bar is 1e-4). 'fp32' is the bit-faithful anchor (13x slower), 'tf32x3' the older parity-grade path, 'tf32' a speed mode outside the bar", dest="math")
+    parser.add_argument('--math', default='auto', choices=['auto', 'fp32', 'tf32x3', 'tf32', 'bf16x3'], help="Arithmetic of the conv/fc contractions. The reference trains in fp32; 'auto' = bf16x3: tensor cores on bf16-split operands with fp32 accumulation, within 5.4e-5 of an fp64 evaluation of the full-size gradient, 1.5e-5 of the forward (the parity bar is 1e-4). 'fp32' is the bit-faithful anchor (13x slower), 'tf32x3' the older parity-grade path, 'tf32' a speed mode outside the bar", dest="math")
     parser.add_argument('--raw_frames', default=True, type=bool_arg, help="Workers write raw frame pairs; the GPU does max-pool/resize/stack", dest="raw_frames")
     parser.add_argument('--train_forward', default='reuse', choices=['reuse', 'stepwise', 'batched'], help="Schedule of the training forward (bit-identical results): reuse the acting forwards' activations, issue it per step on a side stream, or run it inside the update like the reference", dest="train_forward")
     parser.add_argument('--graphs', default='auto', choices=['auto', 'true', 'false'], help="Replay act/update as CUDA graphs (auto: when <= 1024 environments per GPU)", dest="graphs")
