@@ -316,7 +316,7 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
         for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
           for (int j = 0; j < 4; ++j) mk[pw][j] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) {
+        if (ok && !(PAACB_DBGV(p.dbg) & 16384)) {
 #pragma unroll
           for (int pw = 0; pw < 2; ++pw) {
             ldg256(mask_ptr(tile, pw), mk[pw][0], mk[pw][1]);
@@ -468,7 +468,7 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
           for (int c = 0; c < BN / 32; ++c) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) mk[acc][c][j] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok) {
+            if (ok && !(PAACB_DBGV(p.dbg) & 16384)) {
               ldg256(p.mask_hi + (ob + c * 32) * 2, mk[acc][c][0], mk[acc][c][1]);
               ldg256(p.mask_hi + (ob + c * 32) * 2 + 32, mk[acc][c][2], mk[acc][c][3]);
             }

@@ -14,7 +14,7 @@ SWITCHES = [(0, 'baseline'), (1, 'conv1 fwd: no stores'), (2, 'conv1 fwd: no epi
             (8, 'conv1 fwd: no A loads'), (16, 'wgrad: hi*hi MMAs only'), (32, 'wgrad: no TMA loads'),
             (64, 'conv1 wgrad: no uint8 conversion'), (128, 'wgrad: half the k-tiles'),
             (256, 'conv fwd/dgrad: no A_lo MMAs'), (512, 'conv fwd/dgrad: no stores'), (1024, 'conv fwd/dgrad: no patch loads'),
-            (2048, 'fc fwd/dgrad/wgrad: no TMA loads')]
+            (2048, 'fc fwd/dgrad/wgrad: no TMA loads'), (16384, 'conv dgrad: no ReLU-mask loads')]
 KERNELS = ['conv1_fwd', 'conv2_fwd', 'conv3_fwd', 'fc4_fwd', 'conv2_dgrad', 'conv3_dgrad', 'fc4_dgrad', 'conv1_wgrad', 'conv2_wgrad',
            'conv3_wgrad', 'fc4_wgrad']
 
