@@ -77,3 +77,37 @@ def test_evaluation_loop_restores_tf_bundle_checkpoint(tmp_path):
     eargs = evaluation.get_arg_parser().parse_args(['-f', args.debugging_folder, '-tc', '3', '-np', '2'])
     rewards = evaluation.evaluate(eargs)
     assert rewards.shape == (3,) and np.all(np.isfinite(rewards))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('arch,single_life', [('NIPS', False), ('NATURE', True)])
+def test_train_on_the_atari_emulator_both_protocols_agree(tmp_path, arch, single_life):
+    """cfg1 / cfg2's code path with the reference's emulator class in the loop: EnvironmentCreator -> AtariEmulator (on the
+    scripted ALE stand-in of tests/fake_ale: real ALE is not installable here) -> 2 forked worker processes -> shared, pinned +
+    mapped buffers -> K1 / forward / update on the GPU.  The raw-frame protocol (workers write raw frame pairs, the GPU
+    preprocesses) and the classic protocol (workers hand over 84x84x4 observations) must see the same states.  The learning
+    rate is 0: this game's frames depend on the actions, and two runs whose weights differ by the rounding of their fp32
+    atomics would eventually sample a different action; with frozen weights both runs play the same 80 steps per emulator
+    (through game-over and lost-life resets) and every state must match bit for bit."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fake_ale'))
+    from paac_b200 import train
+    from paac_b200.paac import PAACLearner
+    results = []
+    for raw in (True, False):
+        a = train.get_arg_parser().parse_args(['-g', 'fake_breakout', '--rom_path', str(tmp_path), '-d', '/gpu:0', '--arch', arch, '-ec', '8',
+                                               '-ew', '2', '--max_global_steps', str(8 * 5 * 16), '-df', str(tmp_path / ('r%d' % raw)) + '/',
+                                               '--raw_frames', 'True' if raw else 'False', '--single_life_episodes', str(single_life), '-lr', '0.0',
+                                               '--random_start', 'False'])
+        # (no random no-op starts: Python re-seeds the global `random` stream of a forked worker from OS entropy, so the no-op
+        # counts of the resets inside the workers differ from run to run -- in the reference as well)
+        nc, ec = train.get_network_and_environment_creator(a)
+        assert ec.num_actions == 4
+        learner = PAACLearner(nc, ec, a)
+        learner.train()
+        assert learner.global_step == 8 * 5 * 16
+        results.append((learner.engine.get_states().cpu().numpy(), learner.network.get_params(), float(learner.last_loss.item())))
+    assert np.array_equal(results[0][0], results[1][0])
+    assert results[0][0].max() > 0 and np.isfinite(results[0][2])
+    assert np.array_equal(results[0][1], results[1][1]) and abs(results[0][2] - results[1][2]) <= 1e-5 * max(1.0, abs(results[1][2]))
