@@ -168,6 +168,7 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     c->feat = fout;
   }
   c->act_floats_per_sample = aoff;
+  c->relu1_words_per_sample = (int64_t)c->layer[0].OH * c->layer[0].OW;
   c->actor_w_off = poff;  add_tensor(c, "actor_output_weights", poff, 2, c->feat, num_actions, 0, 0, c->feat);
   c->actor_b_off = poff;  add_tensor(c, "actor_output_biases", poff, 1, num_actions, 0, 0, 0, c->feat);
   c->critic_w_off = poff; add_tensor(c, "critic_output_weights", poff, 2, c->feat, 1, 0, 0, c->feat);
@@ -466,8 +467,10 @@ int paacb_tensor_info(const paacb_ctx* ctx, int index, char* name, int name_cap,
 }
 
 int64_t paacb_forward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
-  // activations as fp32, or as two bf16 planes per tensor (PAACB_MATH_BF16X3): the same bytes
-  return ctx ? ctx->act_floats_per_sample * batch : PAACB_EINVAL;
+  // activations as fp32, or as two bf16 planes per tensor (PAACB_MATH_BF16X3): the same bytes; then the ReLU bit mask of the
+  // first conv layer (one word per output position; written by conv1's forward, read by conv2's data gradient)
+  if (ctx == nullptr) return PAACB_EINVAL;
+  return (ctx->act_floats_per_sample + (ctx->math == PAACB_MATH_BF16X3 ? ctx->relu1_words_per_sample : 0)) * batch;
 }
 int64_t paacb_backward_workspace_floats(const paacb_ctx* ctx, int64_t batch) {
   return ctx ? ctx->act_floats_per_sample * batch : PAACB_EINVAL;

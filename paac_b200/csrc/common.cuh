@@ -85,6 +85,7 @@ struct paacb_ctx {
   paacb::LayerGeom layer[4];
   int feat;                     // hidden fc width F
   int64_t act_floats_per_sample;   // sum of activation sizes of all layers
+  int64_t relu1_words_per_sample;  // forward workspace, after the activations: one 32-bit word per conv1 output position, bit c = (channel c > 0)
   int64_t actor_w_off, actor_b_off, critic_w_off, critic_b_off;
   int64_t param_count;
   int n_tensors;

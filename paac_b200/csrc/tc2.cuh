@@ -39,6 +39,17 @@ __host__ __device__ inline Planes layer_planes(void* ws, int64_t off_floats_per_
   p.lo += s.first * elems_per_sample * 2;
   return p;
 }
+// ReLU bit mask of conv1's output, after all activation planes of the forward workspace: per sample two planes of
+// uint16 [OH1 * OW1] (400 words of 32 bits per sample in all) -- plane h holds, for every output position, the 16 flags
+// "channel 16 h + c > 0" at bit relu1_bit_pos(c) (NIPS, 16 channels: plane 0 only).  conv1's forward epilogue has the values
+// in registers and writes them (a warp's 32 positions are 64 contiguous bytes of one plane); conv2's data gradient reads
+// 4 bytes per pixel pair and plane instead of two 64-byte hi-plane rows and can hold the NEXT tile's words in two registers.
+// Bit position of channel c (0..15) inside a plane's uint16: the writer gathers the "non-zero" flags of its eight packed
+// bf16x2 words with three instructions per word (tc2_conv1.cuh), which leaves channel 2j at bit 7 - j and 2j + 1 at bit 15 - j.
+__host__ __device__ constexpr int relu1_bit_pos(int c) { return 8 * (c & 1) + 7 - (c >> 1); }
+inline uint32_t* relu1_bits(void* ws, const paacb_ctx* ctx, const WsSlice& s) {
+  return reinterpret_cast<uint32_t*>(ws) + ctx->act_floats_per_sample * s.cap + s.first * ctx->relu1_words_per_sample;
+}
 constexpr int64_t kStateElems = (int64_t)PAACB_OBS * PAACB_OBS * PAACB_STACK;   // 28,224
 
 // ---- launchers (tc2_*.cu) ---------------------------------------------------------------------------

@@ -290,6 +290,7 @@ int launch_conv_dgrad_bf16(const paacb_ctx* ctx, int l, const void* fwd_ws, void
   p.out_hi = dx.hi;
   p.out_lo = dx.lo;
   p.mask_hi = xa.hi;
+  if (l == 1) p.mask_bits = relu1_bits(const_cast<void*>(fwd_ws), ctx, WsSlice{batch, 0});     // conv1's ReLU mask as bit words
   p.dbias = grads + gp.b_off;
   const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)batch};
   const uint64_t strides[3] = {(uint64_t)g.N * 2, (uint64_t)g.OW * g.N * 2, (uint64_t)g.OH * g.OW * g.N * 2};

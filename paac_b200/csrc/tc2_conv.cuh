@@ -18,7 +18,7 @@ struct Geo;
 // conv2 forward: [b,20,20,32] 4x4 stride 2 -> [b,9,9,64].  Unit = 2 pixels x 32 channels = 128 B; 2 row-parity planes.
 template <>
 struct Geo<G_FWD2> {
-  static constexpr bool DGRAD = false, A_LO = true, STAGED = false;
+  static constexpr bool DGRAD = false, A_LO = true, STAGED = false, MASK_BITS = false;
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 2, WU = 10, HQ = 10, BOX_ROWS = 15, SLOT = 19456, NSLOTS = 5;
   static constexpr int NACC = 1, BN = 64, KS = 16, KB = 8, OH = 9, OW = 9;
   static constexpr int CH = 64, PIX = 1;
@@ -28,7 +28,7 @@ struct Geo<G_FWD2> {
 // conv3 forward: [b,9,9,64] 3x3 stride 1 -> [b,7,7,64].  Unit = 1 pixel x 64 channels = 128 B.
 template <>
 struct Geo<G_FWD3> {
-  static constexpr bool DGRAD = false, A_LO = true, STAGED = false;
+  static constexpr bool DGRAD = false, A_LO = true, STAGED = false, MASK_BITS = false;
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 9, HQ = 9, BOX_ROWS = 18, SLOT = 21504, NSLOTS = 3;
   static constexpr int NACC = 1, BN = 64, KS = 36, KB = 9, OH = 7, OW = 7;
   static constexpr int CH = 64, PIX = 1;
@@ -39,7 +39,7 @@ struct Geo<G_FWD3> {
 // zero-padded dZ (TMA out-of-bounds fill), tap (kh, kw) reads position q + (2-kh)*11 + (2-kw).
 template <>
 struct Geo<G_DG3> {
-  static constexpr bool DGRAD = true, A_LO = true, STAGED = false;
+  static constexpr bool DGRAD = true, A_LO = true, STAGED = false, MASK_BITS = false;
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 9, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 4;
   static constexpr int NACC = 1, BN = 64, KS = 36, KB = 9, OH = 9, OW = 9;       // OH/OW: valid rows/cols of the enumeration
   static constexpr int PAD = 2, S = 1, XH = 9, XW = 9;
@@ -55,7 +55,7 @@ struct Geo<G_DG3> {
 // swizzled shared-memory tile instead and the TMA engine stores the tile.
 template <>
 struct Geo<G_DG2> {
-  static constexpr bool DGRAD = true, A_LO = true, STAGED = true;
+  static constexpr bool DGRAD = true, A_LO = true, STAGED = true, MASK_BITS = true;      // mask = conv1's ReLU bit words
   static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 1, WU = 11, HQ = 10, BOX_ROWS = 11, SLOT = 16384, NSLOTS = 4;
   static constexpr int NACC = 4, BN = 32, KS = 16, KB = 4, OH = 10, OW = 10;
   static constexpr int PAD = 1, S = 2, XH = 20, XW = 20;
@@ -69,7 +69,7 @@ struct Geo<G_DG2> {
 // kw >> 1, 32-byte half kw & 1.
 template <>
 struct Geo<G_FWD2N> {
-  static constexpr bool DGRAD = false, A_LO = true, STAGED = false;
+  static constexpr bool DGRAD = false, A_LO = true, STAGED = false, MASK_BITS = false;
   static constexpr int UB = 64, SWZ = SWZ_64B, PARTS = 2, WU = 10, HQ = 10, BOX_ROWS = 15, SLOT = 10240, NSLOTS = 6;
   static constexpr int NACC = 1, BN = 32, KS = 8, KB = 4, OH = 9, OW = 9;
   static constexpr int CH = 32, PIX = 1;
@@ -82,7 +82,7 @@ struct Geo<G_FWD2N> {
 // and a thread's 32 columns are one 64-byte run of each output plane (direct 256-bit stores, no staging tile).
 template <>
 struct Geo<G_DG2N> {
-  static constexpr bool DGRAD = true, A_LO = true, STAGED = false;
+  static constexpr bool DGRAD = true, A_LO = true, STAGED = false, MASK_BITS = true;     // mask = conv1's ReLU bit words
   static constexpr int UB = 64, SWZ = SWZ_64B, PARTS = 1, WU = 11, HQ = 10, BOX_ROWS = 11, SLOT = 8192, NSLOTS = 6;
   static constexpr int NACC = 2, BN = 32, KS = 8, KB = 2, OH = 10, OW = 10;
   static constexpr int PAD = 1, S = 2, XH = 20, XW = 20;
@@ -102,6 +102,7 @@ struct ConvKParams {
   uint8_t* out_hi;         // output planes (bf16)
   uint8_t* out_lo;
   const uint8_t* mask_hi;  // dgrad: hi plane of the activation whose ReLU is differentiated (same shape as the output)
+  const uint32_t* mask_bits;   // conv2's data gradient: the same mask as bit planes, uint16 [b][2][XH * XW] (tc2.cuh: relu1_bits)
   int dbg;                 // PAACB_DBG ablations (timing experiments only): 256 no A_lo MMAs, 512 no stores, 1024 no patch loads, 4096 conv2 dgrad: lo plane through the staging tile, 8192 conv2 dgrad: both planes by direct stores (measured: no gain once the staging tile is gone)
   float* dbias;            // dgrad: += column sums of the output (the bias gradient of the layer that produced that activation)
 };
@@ -297,33 +298,28 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
       const int ph = (warp - 2) >> 2;                                       // this warp's output-row parity: classes (ph, 0), (ph, 1)
       const bool io = (tid == 64 + 128 * ph);                               // issues the TMA stores of this group's tile
       float bsum = 0.f;
-      // The ReLU-mask words of this thread's two output pixels (2 x 64 B = one 128-byte line) are loaded at the top of the
-      // tile, before the wait for the MMAs; the line of the NEXT tile is requested into L2 at the same time, so the load
-      // is an L2 hit.  (Version 1 loaded them cold: a DRAM round trip per tile.  Version 2 carried them one tile ahead in
-      // registers: 32 registers this kernel does not have -- the spill put a local-memory load on the critical path right
-      // after the MMA barrier, 18 % of all stall samples.)
-      uint4 mk[2][4];
-      auto mask_ptr = [&](int tile, int pw) {
-        const int64_t ob = (((int64_t)tile * Ge::XH + Ge::S * qh + ph) * Ge::XW + Ge::S * qw + pw) * BN;
-        return reinterpret_cast<const uint4*>(p.mask_hi + ob * 2);
+      // The ReLU mask of this thread's two output pixels is TWO 32-bit words (bit c = channel c > 0, written by conv1's
+      // forward epilogue), carried one tile ahead in two registers.  History: (1) the 64-byte hi-plane rows of both pixels
+      // loaded cold at the top of the tile: a DRAM round trip per tile; (2) the rows carried one tile ahead in registers: 32
+      // registers this kernel does not have -- the spill put a local-memory load on the critical path right after the MMA
+      // barrier, 18 % of all stall samples; (3) rows loaded at the top of the tile behind an L2 prefetch issued a tile earlier:
+      // still 11 % of the samples on the first use of the mask (the kernel is epilogue-bound, so nothing hides an L2 hit),
+      // -17 % with the loads switched off (profiles/r02_ablations_dgrad.json); (4) bits.
+      // (plane h of sample `tile`: uint16 [XH * XW]; this thread's two pixels are adjacent: one 32-bit load per plane)
+      const uint16_t* bits16 = reinterpret_cast<const uint16_t*>(p.mask_bits);
+      const int pxo = (Ge::S * qh + ph) * Ge::XW + Ge::S * qw;
+      auto load_bits = [&](int tile) {
+        const uint16_t* b = bits16 + (int64_t)tile * (2 * Ge::XH * Ge::XW) + pxo;
+        return make_uint2(__ldg(reinterpret_cast<const uint32_t*>(b)), __ldg(reinterpret_cast<const uint32_t*>(b + Ge::XH * Ge::XW)));
       };
-      if (ok && cta < p.num_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_ptr(cta, 0)));
+      uint2 mb_next = make_uint2(0u, 0u);
+      if (ok && cta < p.num_tiles && !(PAACB_DBGV(p.dbg) & 16384)) mb_next = load_bits(cta);
       int tl = 0;
       for (int tile = cta; tile < p.num_tiles; tile += ncta, ++tl) {
         const int ab = tl & 1;
         const uint32_t aph = (uint32_t)((tl >> 1) & 1);
-#pragma unroll
-        for (int pw = 0; pw < 2; ++pw)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mk[pw][j] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok && !(PAACB_DBGV(p.dbg) & 16384)) {
-#pragma unroll
-          for (int pw = 0; pw < 2; ++pw) {
-            ldg256(mask_ptr(tile, pw), mk[pw][0], mk[pw][1]);
-            ldg256(mask_ptr(tile, pw) + 2, mk[pw][2], mk[pw][3]);
-          }
-        }
-        if (ok && tile + ncta < p.num_tiles) asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_ptr(tile + ncta, 0)));
+        const uint2 mb = mb_next;
+        if (ok && tile + ncta < p.num_tiles && !(PAACB_DBGV(p.dbg) & 16384)) mb_next = load_bits(tile + ncta);
         mbar_wait(&tfull_bar[ab], aph);
         tc_fence_after();
         float o[2][32];
@@ -334,18 +330,11 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
           tmem_ld32(tcol, v);
           tmem_ld32(tcol + (uint32_t)Cfg::NT, v2);
           tmem_ld_wait();
+          // pixel pw: channels 0-15 in half pw of mb.x, channels 16-31 in half pw of mb.y (0 for rows that are no output pixels)
+          const uint32_t word = ((pw ? mb.x >> 16 : mb.x) & 0xffffu) | (pw ? mb.y & 0xffff0000u : mb.y << 16);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t mw[4] = {mk[pw][c].x, mk[pw][c].y, mk[pw][c].z, mk[pw][c].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int e = c * 8 + j * 2;
-              // bf16 > 0  <=>  the 16 bits, as a signed integer in the top half of a word, are > 0
-              const bool p0 = ok && ((int32_t)(mw[j] << 16) > 0), p1 = ok && ((int32_t)(mw[j] & 0xffff0000u) > 0);
-              o[pw][e] = p0 ? __uint_as_float(v[e]) + __uint_as_float(v2[e]) : 0.f;
-              o[pw][e + 1] = p1 ? __uint_as_float(v[e + 1]) + __uint_as_float(v2[e + 1]) : 0.f;
-            }
-          }
+          for (int e = 0; e < 32; ++e)
+            o[pw][e] = ((word >> (16 * (e / 16) + relu1_bit_pos(e % 16))) & 1u) ? __uint_as_float(v[e]) + __uint_as_float(v2[e]) : 0.f;
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[ab]);                                       // accumulator drained: the MMAs of tile tl + 2 may start
@@ -455,8 +444,19 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
       }
       // dgrad: the ReLU-mask words of the whole tile row do not depend on the accumulator: fetch them before waiting
       // for the MMAs so that their DRAM latency overlaps the mainloop (they were the top stall of the first version)
-      uint4 mk[Ge::DGRAD ? NACC : 1][Ge::DGRAD ? BN / 32 : 1][4];
-      if constexpr (Ge::DGRAD) {
+      uint4 mk[(Ge::DGRAD && !Ge::MASK_BITS) ? NACC : 1][(Ge::DGRAD && !Ge::MASK_BITS) ? BN / 32 : 1][4];
+      uint32_t mbits[Ge::MASK_BITS ? NACC : 1];   // MASK_BITS (PIX == 2, CH = 16): the 16 flags of the two pixels of an accumulator row
+      if constexpr (Ge::DGRAD && Ge::MASK_BITS) {
+        static_assert(!Ge::MASK_BITS || Ge::STAGED || (Ge::PIX == 2 && Ge::CH == 16 && BN == 32), "bit masks: two pixels of 16 channels per row");
+#pragma unroll
+        for (int acc = 0; acc < NACC; ++acc) {
+          const int ih = Ge::S * qh + acc, iw = Ge::S * qw;
+          mbits[acc] = 0u;
+          if (ok && !(PAACB_DBGV(p.dbg) & 16384))      // plane 0 of sample `tile`: pixels iw, iw + 1 are one aligned 32-bit word
+            mbits[acc] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.mask_bits) +
+                                                                 (int64_t)tile * (2 * Ge::XH * Ge::XW) + ih * Ge::XW + iw));
+        }
+      } else if constexpr (Ge::DGRAD) {
 #pragma unroll
         for (int acc = 0; acc < NACC; ++acc) {
           // accumulator -> output pixel: PIX == 1: class (acc / 2, acc % 2) of a stride-2 layer; PIX == 2: row parity acc, the
@@ -544,7 +544,12 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
           float o[32];
-          if constexpr (Ge::DGRAD) {
+          if constexpr (Ge::DGRAD && Ge::MASK_BITS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {      // column j = pixel j / CH, channel j % CH; rows that are no output pixels carry 0 bits
+              o[j] = ((mbits[acc] >> (16 * (j / Ge::CH) + relu1_bit_pos(j % Ge::CH))) & 1u) ? __uint_as_float(v[j]) : 0.f;
+            }
+          } else if constexpr (Ge::DGRAD) {
             uint32_t mw[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

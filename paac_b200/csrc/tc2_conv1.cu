@@ -93,16 +93,19 @@ int prepare_conv1_fwd_bf16(const paacb_ctx* ctx, const float* params, const uint
                            const WsSlice& slice, Conv1Params* p) {
   const LayerGeom& g = ctx->layer[0];
   const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
-  if (g.N == 16) return prepare_conv1<16>(ctx, params, states, out.hi, out.lo, nullptr, batch, p);
-  return prepare_conv1<32>(ctx, params, states, out.hi, out.lo, nullptr, batch, p);
+  const int rc = (g.N == 16) ? prepare_conv1<16>(ctx, params, states, out.hi, out.lo, nullptr, batch, p)
+                             : prepare_conv1<32>(ctx, params, states, out.hi, out.lo, nullptr, batch, p);
+  if (rc == PAACB_OK) p->relu_bits = reinterpret_cast<uint16_t*>(relu1_bits(fwd_ws, ctx, slice));
+  return rc;
 }
 
 template <int NC, bool F32OUT>
 static int launch_conv1_inst(const paacb_ctx* ctx, const float* params, const uint8_t* states, uint8_t* out_hi, uint8_t* out_lo,
-                             float* out_f32, int64_t batch, cudaStream_t st) {
+                             float* out_f32, uint16_t* relu_bits, int64_t batch, cudaStream_t st) {
   Conv1Params p;
   const int prc = prepare_conv1<NC>(ctx, params, states, out_hi, out_lo, out_f32, batch, &p);
   if (prc != PAACB_OK) return prc;
+  p.relu_bits = relu_bits;
   constexpr int SMEM = kC1_SMEM_FIXED + C1<NC>::WBYTES;
   static DeviceOnce attr_set;   // kernel attributes are per device: one bit per device index
   if (!attr_set.done(ctx->device)) {
@@ -129,9 +132,10 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
                         const WsSlice& slice, cudaStream_t st) {
   const LayerGeom& g = ctx->layer[0];
   const Planes out = layer_planes(fwd_ws, g.out_act_off, (int64_t)g.OH * g.OW * g.N, slice);
+  uint16_t* bits = reinterpret_cast<uint16_t*>(relu1_bits(fwd_ws, ctx, slice));
   if (g.N == 16)      // NIPS: 16 channels = one 32-byte sector per position and plane
-    return launch_conv1_inst<16, false>(ctx, params, states, out.hi, out.lo, nullptr, batch, st);
-  return launch_conv1_inst<32, false>(ctx, params, states, out.hi, out.lo, nullptr, batch, st);
+    return launch_conv1_inst<16, false>(ctx, params, states, out.hi, out.lo, nullptr, bits, batch, st);
+  return launch_conv1_inst<32, false>(ctx, params, states, out.hi, out.lo, nullptr, bits, batch, st);
 }
 
 // NIPS (16 output channels), tf32 pipeline: fp32 activations out.  The int8 digit scheme is exact to 2^-19 of the largest
@@ -139,7 +143,7 @@ int launch_conv1_fwd_i8(const paacb_ctx* ctx, const float* params, const uint8_t
 int launch_conv1_fwd_i8_f32(const paacb_ctx* ctx, const float* params, const uint8_t* states, float* y, int64_t batch,
                             cudaStream_t st) {
   if (ctx->layer[0].N != 16 || ctx->wq_i8 == nullptr) return PAACB_EUNSUPPORTED;
-  return launch_conv1_inst<16, true>(ctx, params, states, nullptr, nullptr, y, batch, st);
+  return launch_conv1_inst<16, true>(ctx, params, states, nullptr, nullptr, y, nullptr, batch, st);
 }
 
 }  // namespace paacb

@@ -45,6 +45,7 @@ struct Conv1Params {
   int dbg;                 // PAACB_DBG ablations (timing experiments only): 1 no stores, 2 no epilogue arithmetic, 4 no MMAs, 8 no A loads
   uint8_t* out_hi;
   uint8_t* out_lo;
+  uint16_t* relu_bits;     // [b][2 planes][400 positions] uint16, plane h bit relu1_bit_pos(c) = (channel 16 h + c > 0); nullptr: not wanted (tc2.cuh)
 };
 
 // D[tmem] (+)= A[smem] * B[smem], kind::i8 (uint8 x int8 -> int32), K = 32 per instruction
@@ -214,6 +215,23 @@ __device__ __forceinline__ void conv1_i8_body(const Conv1Params& p, const int ct
       if constexpr (PIPE) pipe_publish(io, note, lane);       // the PREVIOUS tile's stores have had a tile's worth of time to land
       if (ok && !(PAACB_DBGV(p.dbg) & 1)) {                 // 16 channels = one full 32-byte sector per plane
         const uint32_t oh = g - n * (uint32_t)kC1_HQ;
+        if constexpr (!F32OUT) {
+          if (p.relu_bits != nullptr) {
+            // the ReLU mask conv2's data gradient needs, as bits.  The outputs are >= +0, so "hi > 0" is "the bf16 half is not
+            // zero", and w + 0x7fff7fff sets bit 15 / bit 31 exactly when the low / high half of w is non-zero (a positive bf16
+            // is <= 0x7f80: no carry between the halves).  Word j's two flags are shifted to bits 15 - j / 31 - j and OR-ed:
+            // three instructions per pair of channels in this ALU-bound epilogue; relu1_bit_pos() is the resulting layout.
+            const int64_t px = (int64_t)n * (2 * kC1_OH * kC1_OW) + oh * kC1_OW + ju;      // plane 0 of sample n
+#pragma unroll
+            for (int h = 0; h < HPT; ++h) {
+              uint32_t acc = 0u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc |= ((hw[h][j] + 0x7fff7fffu) >> j) & (0x80008000u >> j);
+              const uint32_t bits = ((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u);
+              p.relu_bits[px + (half0 + h) * (kC1_OH * kC1_OW)] = (uint16_t)bits;
+            }
+          }
+        }
 #pragma unroll
         for (int h = 0; h < HPT; ++h) {
           const int64_t oe = (((int64_t)n * kC1_OH + oh) * kC1_OW + ju) * NC + (half0 + h) * 16;      // element index
