@@ -219,7 +219,7 @@ __device__ __forceinline__ void stream_gemm_body(const StreamParams& p, const in
           const int n0 = nt * BN + c * 32;
 #pragma unroll
           for (int j = 0; j < 4; ++j) mk[c][j] = make_uint4(0u, 0u, 0u, 0u);
-          if (ok && n0 < p.N) {
+          if (ok && n0 < p.N && !(PAACB_DBGV(p.dbg) & 16384)) {
             const uint8_t* mp = p.mask_hi + ((int64_t)m * p.ldo + n0) * 2;
             ldg256(mp, mk[c][0], mk[c][1]);
             ldg256(mp + 32, mk[c][2], mk[c][3]);
