@@ -464,6 +464,21 @@ def run_b200(args):
             'note': "RolloutEngine(train_forward='reuse'): act(t) stores its activations in the training workspace "
                     '(paacb_policy_forward_at) and the update skips the redundant training forward; bit-identical results'}
         eng.set_train_forward('batched')
+        # the reference's DEFAULT size (train.py:95-96, BASELINE.json configs[0], [1], [3]: 32 environments per GPU): one cycle
+        # is ~60 small launches, so the engine replays act / update as CUDA graphs (tools/small_batch.py has the full table)
+        if rank == 0 and world == 1:
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location('small_batch', os.path.join(ROOT, 'tools', 'small_batch.py'))
+                sb = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(sb)
+                r32 = sb.engine_numbers(args.arch, 32, 100, True, math=args.math)
+                variants['envs_32_graph_replay'] = {
+                    'value': r32['env_steps_per_s'], 'unit': UNIT, 'ms_per_step': r32['ms_per_cycle'], 'update_ms': r32['update_ms'],
+                    'note': '32 environments x t_max 5 on one GPU (the reference default -ec 32), act / update replayed as CUDA '
+                            'graphs, device-resident raw frames; %d kernel launches issued per cycle' % r32['kernel_launches_issued_per_cycle']}
+            except Exception as e:                      # a variant, never the headline: report and go on
+                variants['envs_32_graph_replay'] = {'error': str(e)[:200]}
 
     # ---- end-to-end arm: host buffers in, actions / loss out ---------------------------------------------
     e2e = None
