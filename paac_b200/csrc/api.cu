@@ -135,6 +135,10 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     c->opt_two_pass = (tp != nullptr) ? atoi(tp) : 0;
     const char* hg = getenv("PAACB_K1_HOST_GRID");      // tuning knob for tools/experiments/pcie_probe.py
     c->k1_host_grid = (hg != nullptr && atoi(hg) > 0) ? atoi(hg) : 96;
+    const char* kp = getenv("PAACB_K1_PIPE");
+    c->k1_pipe = (kp != nullptr) ? atoi(kp) : 1;
+    const char* kh = getenv("PAACB_K1_HINTS");
+    c->k1_hints = (kh != nullptr) ? atoi(kh) : 3;
   }
   int h = PAACB_OBS, w = PAACB_OBS, ch = PAACB_STACK;
   int64_t poff = 0, aoff = 0;

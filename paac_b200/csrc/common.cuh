@@ -127,6 +127,8 @@ struct paacb_ctx {
   mutable uintptr_t k1_cache_key[kK1Cache];
   mutable int k1_cache_host[kK1Cache];
   int k1_host_grid;             // PAACB_K1_HOST_GRID (default 96)
+  int k1_pipe;                  // PAACB_K1_PIPE (default 1): device-resident frames go through the persistent copy pipeline
+  int k1_hints;                 // PAACB_K1_HINTS (default 3): bit 0 = inputs read evict-first, bit 1 = new stack written evict-last
   // layer-pipelined forward (tc2_pipe.cu): hand-off counters (one buffer per stream in use), role sizes, sticky error word
   static constexpr int kPipeBufs = 4;
   static constexpr int64_t kPipeMaxBatch = 32768;

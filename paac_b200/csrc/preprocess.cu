@@ -12,7 +12,7 @@
 // (prev >> 8) | (new << 24) per pixel word (drop the oldest frame, append the newest as channel 3).
 // HBM traffic per env-step: 26,880 B frames + 28,224 B previous stack read, 28,224 B written.
 #include <stdlib.h>
-#include "common.cuh"
+#include "tc2.cuh"
 
 namespace paacb {
 
@@ -96,6 +96,204 @@ preprocess_u8_kernel(const uint8_t* __restrict__ frames, int pairs, const uint8_
     const int idx = tid + i * kThreads;
     if (idx < kStateVec) next4[idx] = acc[i];
   }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1, device-resident frames: the same arithmetic as a persistent, warp-specialised copy pipeline (round 2).
+// The kernel above alternates a load phase and a gather phase per CTA and leans on 4-8 resident CTAs per SM to keep
+// HBM busy: 0.60 of the copy peak on moved bytes inside a step (4,096 environments = 3.5-7 waves of short CTAs), 0.77 at
+// 16,384.  Here ONE CTA per SM keeps kK1Stages environments in flight through the TMA engine:
+//   warp 0 (producer)  per environment THREE TMA operations completing on the stage's `full` mbarrier: one 28,224-byte bulk
+//                      copy of the previous stack and two tensor boxes of the frame rows.  Pillow's NEAREST table for
+//                      210 -> 84 rows is row(2k) = 5k + 1, row(2k + 1) = 5k + 3: the even and the odd
+//                      selected rows are each a uniform 800-byte pitch that also runs across frames (33,600 = 42 x 800),
+//                      so ONE rank-3 tensor map per parity {160 B, 42 rows, frames} with a box of {160, 42, 2} lands the
+//                      42 rows of both frames of a pair.  (First version: 168 bulk copies of 160 B per environment --
+//                      2.4x SLOWER than the kernel above, ~60 cycles of TMA issue per copy; measured, tools/gpu_round2_t.sh.)
+//   warps 2-9          wait `full`, turn the stage's stack into the next stack IN PLACE ((prev >> 8) | max(f0, f1) << 24 per
+//                      pixel word; column table and row offsets live in registers for the whole kernel),
+//                      fence.proxy.async, arrive on `done`
+//   warp 1 (storer)    wait `done`, ONE 28,224-byte bulk store shared -> global, wait until the engine has read the stage,
+//                      arrive on `empty`
+// No thread touches global memory on the fast path (resets -- rare, 4 pairs per environment -- are gathered straight from
+// global memory by the consumer warps into the same stage).  L2 policy (PAACB_K1_HINTS): bit 0 = the frame rows and the
+// old stack are read evict-first (never used again), bit 1 = the new stack is written evict-last.
+// The launcher falls back to the kernel above when the row table is not the affine pattern.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kK1Stages = 4;
+constexpr int kStackBytes = kStateVec * 16;                            // 28,224
+constexpr int kRowsBytes = 2 * PAACB_OBS * PAACB_FRAME_W;              // 26,880 = two boxes of 13,440
+constexpr int kBoxBytes = kRowsBytes / 2;                              // one parity: [frame][42][160]
+constexpr int kBoxFrame = kBoxBytes / 2;                               // 6,720
+constexpr int kStageBytes = (kRowsBytes + kStackBytes + 127) / 128 * 128;   // 55,168: [even box][odd box][stack]
+constexpr int kK1Consumers = 256;
+constexpr int kK1PipeThreads = 64 + kK1Consumers;
+constexpr int kK1PipeSmem = kK1Stages * kStageBytes + 3 * kK1Stages * 8 + 16;
+static_assert(PAACB_FRAME_H * PAACB_FRAME_W == 42 * 800 && PAACB_OBS == 84, "row-parity tensor maps assume 210 x 160 -> 84 rows");
+
+struct K1PipeParams {
+  CUtensorMap tm_even, tm_odd;
+  const uint8_t* frames;
+  const uint8_t* reset;
+  const uint8_t* prev;
+  uint8_t* next;
+  int64_t n_envs;
+  int pairs, hints;
+  StepScalars sc;
+  ResizeTables tabs;
+};
+
+__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 normal, 1 evict-first, 2 evict-last
+  uint64_t pol;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kK1PipeThreads, 1) preprocess_u8_pipe_kernel(const __grid_constant__ K1PipeParams p) {
+  extern __shared__ __align__(128) uint8_t k1_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(k1_smem + kK1Stages * kStageBytes);
+  uint64_t* done = full + kK1Stages;
+  uint64_t* empty = done + kK1Stages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kK1Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&done[s], kK1Consumers);
+      mbar_init(&empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ---- producer ----
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tm_even);
+      tma_prefetch_desc(&p.tm_odd);
+      const uint64_t pol = l2_policy((p.hints & 1) ? 1 : 0);
+      int k = 0;
+      for (int64_t env = blockIdx.x; env < p.n_envs; env += gridDim.x, ++k) {
+        const int s = k % kK1Stages;
+        const uint32_t ph = (uint32_t)(k / kK1Stages) & 1u;
+        if (k >= kK1Stages) mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* stage = k1_smem + s * kStageBytes;
+        mbar_arrive_expect_tx(&full[s], kRowsBytes + kStackBytes);
+        const int frame0 = (int)(env * p.pairs * 2);
+        tma_load_3d_hint(stage, &p.tm_even, 0, 0, frame0, &full[s], pol);
+        tma_load_3d_hint(stage + kBoxBytes, &p.tm_odd, 0, 0, frame0, &full[s], pol);
+        bulk_g2s_hint(stage + kRowsBytes, p.prev + env * (int64_t)kStackBytes, kStackBytes, &full[s], pol);
+      }
+    }
+  } else if (warp == 1) {
+    // ---- storer ----
+    if (lane == 0) {
+      const uint64_t pol = l2_policy((p.hints & 2) ? 2 : 0);
+      int k = 0;
+      for (int64_t env = blockIdx.x; env < p.n_envs; env += gridDim.x, ++k) {
+        const int s = k % kK1Stages;
+        const uint32_t ph = (uint32_t)(k / kK1Stages) & 1u;
+        mbar_wait(&done[s], ph);
+        bulk_s2g_hint(p.next + env * (int64_t)kStackBytes, k1_smem + s * kStageBytes + kRowsBytes, kStackBytes, pol);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&empty[s]);
+      }
+      tma_store_wait_all();
+    }
+  } else {
+    // ---- consumers ----
+    const int ctid = tid - 64;
+    const StepScalars& sc = p.sc;
+    int roff[kVecPerThread];          // byte offset of the thread's plane row inside the stage (frame 0 of its parity box)
+    uint32_t cols[kVecPerThread];     // the four source columns of its four pixels, one byte each
+#pragma unroll
+    for (int i = 0; i < kVecPerThread; ++i) {
+      const int idx = ctid + i * kK1Consumers;
+      const int y = idx < kStateVec ? idx / (PAACB_OBS / 4) : 0;
+      const int x0 = idx < kStateVec ? (idx - y * (PAACB_OBS / 4)) * 4 : 0;
+      roff[i] = (y & 1) * kBoxBytes + (y >> 1) * PAACB_FRAME_W;
+      cols[i] = (uint32_t)p.tabs.col[x0] | ((uint32_t)p.tabs.col[x0 + 1] << 8) | ((uint32_t)p.tabs.col[x0 + 2] << 16) |
+                ((uint32_t)p.tabs.col[x0 + 3] << 24);
+    }
+    int k = 0;
+    for (int64_t env = blockIdx.x; env < p.n_envs; env += gridDim.x, ++k) {
+      const int s = k % kK1Stages;
+      const uint32_t ph = (uint32_t)(k / kK1Stages) & 1u;
+      // the step's scalars and the reset flag: loaded before the wait, consumed after it
+      bool rst = false;
+      if (p.pairs >= PAACB_STACK) {
+        if (p.reset != nullptr) rst = p.reset[env] != 0;
+        if (sc.over_in != nullptr && sc.over_is_reset) rst = rst || (sc.over_in[env] != 0.f);
+      }
+      if (ctid == 0 && sc.over_in != nullptr) {
+        sc.over_out[env] = sc.over_in[env];
+        sc.rewards_out[env] = sc.rewards_in[env];
+      }
+      uint8_t* stage = k1_smem + s * kStageBytes;
+      uint4* st4 = reinterpret_cast<uint4*>(stage + kRowsBytes);
+      mbar_wait(&full[s], ph);
+      if (!rst) {
+#pragma unroll
+        for (int i = 0; i < kVecPerThread; ++i) {
+          const int idx = ctid + i * kK1Consumers;
+          if (idx < kStateVec) {
+            uint4 v = shr8(st4[idx]);
+            const uint8_t* a = stage + roff[i];
+            const uint8_t* b = a + kBoxFrame;
+            const uint32_t c0 = cols[i] & 0xffu, c1 = (cols[i] >> 8) & 0xffu, c2 = (cols[i] >> 16) & 0xffu, c3 = cols[i] >> 24;
+            v.x |= (uint32_t)max(a[c0], b[c0]) << 24;
+            v.y |= (uint32_t)max(a[c1], b[c1]) << 24;
+            v.z |= (uint32_t)max(a[c2], b[c2]) << 24;
+            v.w |= (uint32_t)max(a[c3], b[c3]) << 24;
+            st4[idx] = v;
+          }
+        }
+      } else {
+        // reset: a fresh stack from the environment's four pairs (oldest first), gathered from global memory
+#pragma unroll 1
+        for (int i = 0; i < kVecPerThread; ++i) {
+          const int idx = ctid + i * kK1Consumers;
+          if (idx < kStateVec) {
+            const int y = idx / (PAACB_OBS / 4);
+            const int src_row = (int)p.tabs.row[y] * PAACB_FRAME_W;
+            uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+            const uint32_t c0 = cols[i] & 0xffu, c1 = (cols[i] >> 8) & 0xffu, c2 = (cols[i] >> 16) & 0xffu, c3 = cols[i] >> 24;
+            for (int q = 0; q < PAACB_STACK; ++q) {
+              const uint8_t* g0 = p.frames + ((env * p.pairs + q) * 2) * (int64_t)kFrameBytes + src_row;
+              const uint8_t* g1 = g0 + kFrameBytes;
+              w0 |= (uint32_t)max(__ldg(g0 + c0), __ldg(g1 + c0)) << (8 * q);
+              w1 |= (uint32_t)max(__ldg(g0 + c1), __ldg(g1 + c1)) << (8 * q);
+              w2 |= (uint32_t)max(__ldg(g0 + c2), __ldg(g1 + c2)) << (8 * q);
+              w3 |= (uint32_t)max(__ldg(g0 + c3), __ldg(g1 + c3)) << (8 * q);
+            }
+            st4[idx] = make_uint4(w0, w1, w2, w3);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&done[s]);
+    }
   }
 }
 
@@ -221,6 +419,36 @@ int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, co
   if (is_host) {
     unsigned narrow = (unsigned)ctx->k1_host_grid;
     if (n > narrow) grid = narrow;
+  }
+  bool affine = true;       // row(2k) = row(0) + 5k, row(2k + 1) = row(1) + 5k: what the two row-parity tensor maps can express
+  for (int y = 0; y < PAACB_OBS; ++y) affine = affine && ((int)ctx->tabs.row[y] == (int)ctx->tabs.row[y & 1] + 5 * (y >> 1));
+  if (!is_host && ctx->k1_pipe && affine && (((uintptr_t)frames | (uintptr_t)prev | (uintptr_t)next) & 15) == 0 &&
+      n * pairs * 2 < (1LL << 31)) {
+    // device-resident frames: the persistent copy pipeline, one CTA per SM
+    static DeviceOnce attr_once;
+    if (!attr_once.done(ctx->device)) {
+      cudaError_t e = cudaFuncSetAttribute(preprocess_u8_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1PipeSmem);
+      if (e != cudaSuccess) {
+        set_error("launch_preprocess: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return PAACB_ECUDA;
+      }
+      attr_once.mark(ctx->device);
+    }
+    K1PipeParams p;
+    memset(&p, 0, sizeof(p));
+    const uint64_t dims[3] = {(uint64_t)PAACB_FRAME_W, 42u, (uint64_t)(n * pairs * 2)};
+    const uint64_t strides[2] = {5u * PAACB_FRAME_W, (uint64_t)kFrameBytes};
+    const uint32_t box[3] = {(uint32_t)PAACB_FRAME_W, 42u, 2u};
+    int rc = encode_tmap(&p.tm_even, frames + (int)ctx->tabs.row[0] * PAACB_FRAME_W, 1, 3, dims, strides, box, 0);
+    if (rc == PAACB_OK) rc = encode_tmap(&p.tm_odd, frames + (int)ctx->tabs.row[1] * PAACB_FRAME_W, 1, 3, dims, strides, box, 0);
+    if (rc != PAACB_OK) return rc;
+    p.frames = frames; p.reset = reset; p.prev = prev; p.next = next;
+    p.n_envs = n; p.pairs = pairs; p.hints = ctx->k1_hints; p.sc = sc; p.tabs = ctx->tabs;
+    const unsigned pgrid = n < (int64_t)ctx->num_sms ? (unsigned)n : (unsigned)ctx->num_sms;
+    PAACB_LAUNCH_BEGIN(ctx, K_PREPROCESS, st);
+    preprocess_u8_pipe_kernel<<<pgrid, kK1PipeThreads, kK1PipeSmem, st>>>(p);
+    PAACB_LAUNCH_END(ctx, K_PREPROCESS, st);
+    return PAACB_OK;
   }
   PAACB_LAUNCH_BEGIN(ctx, K_PREPROCESS, st);
   preprocess_u8_kernel<<<grid, kThreads, 0, st>>>(frames, pairs, reset, prev, next, ctx->tabs, n, sc);

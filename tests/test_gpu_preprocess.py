@@ -120,3 +120,39 @@ def test_planar_ring_prototype_equals_k1():
             _lib.check(net._lib.paacb_stack_from_planes(net.ctx, _lib.ptr(ring), R, t % R, _lib.ptr(got), N, G.stream()), 'gather')
             torch.cuda.synchronize()
             assert np.array_equal(got.cpu().numpy(), state), t
+
+
+def test_copy_pipeline_equals_cta_per_env_kernel(monkeypatch):
+    """Device-resident frames go through the persistent copy pipeline (one CTA per SM, 4 stages); the CTA-per-environment
+    kernel (PAACB_K1_PIPE=0: what pinned host frames use) must write the same bytes.  1,500 environments = more than 148 x 4:
+    every stage of the ring is refilled, 20 % of the environments reset from their four pairs, in place and out of place,
+    with and without the L2 policies; 700 environments also against the oracle."""
+    from paac_b200 import _lib
+    n = 1500
+    gen = torch.Generator(device='cuda'); gen.manual_seed(11)
+    frames = torch.randint(0, 256, (n, 4, 2, 210, 160), dtype=torch.uint8, device='cuda', generator=gen)
+    prev = torch.randint(0, 256, (n, 84, 84, 4), dtype=torch.uint8, device='cuda', generator=gen)
+    reset = (torch.rand((n,), device='cuda', generator=gen) < 0.2).to(torch.uint8)
+    nets = {}
+    for name, env in (('pipe', {'PAACB_K1_PIPE': '1', 'PAACB_K1_HINTS': '3'}), ('pipe_nohint', {'PAACB_K1_PIPE': '1', 'PAACB_K1_HINTS': '0'}),
+                      ('cta', {'PAACB_K1_PIPE': '0'})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        nets[name] = G.make_net('NIPS', 4)
+    outs = {}
+    for name, net in nets.items():
+        o = torch.empty_like(prev)
+        _lib.check(net._lib.paacb_preprocess_u8(net.ctx, _lib.ptr(frames), 4, _lib.ptr(reset), _lib.ptr(prev), _lib.ptr(o), n, G.stream()))
+        # single-slot view of the same buffer (pairs = 1: stride of one pair, no resets), in place
+        f1 = frames[:, 0].contiguous()
+        b = prev.clone()
+        _lib.check(net._lib.paacb_preprocess_u8(net.ctx, _lib.ptr(f1), 1, None, _lib.ptr(b), _lib.ptr(b), n, G.stream()))
+        torch.cuda.synchronize()
+        outs[name] = (o, b)
+    for name in ('pipe', 'pipe_nohint'):
+        assert torch.equal(outs[name][0], outs['cta'][0]), name
+        assert torch.equal(outs[name][1], outs['cta'][1]), name
+    assert int(reset.sum()) > 100
+    m = 700
+    want = opre.step_states(prev[:m].cpu().numpy(), frames[:m].cpu().numpy(), reset[:m].cpu().numpy(), ROW, COL)
+    assert np.array_equal(outs['pipe'][0][:m].cpu().numpy(), want)
