@@ -55,6 +55,8 @@ def parse():
     ap.add_argument('--no_variants', action='store_true')
     ap.add_argument('--no_overlap_allreduce', action='store_true', help='N > 1: one all-reduce after the whole backward')
     ap.add_argument('--e2e_slices', type=int, default=2, help='environment slices pipelined in the end-to-end arm')
+    ap.add_argument('--dev_slices', type=int, default=1,
+                    help='device-resident arm: contiguous environment slices, each rolled out on its own stream (1 = whole batch on one stream)')
     ap.add_argument('--ref_envs', type=int, default=64, help='--impl reference: envs per step (bounded sample)')
     args = ap.parse_args()
     if args.math == 'auto':
@@ -68,6 +70,9 @@ def workload_config(args, n_gpus):
                             'Nature' if args.arch == 'NATURE' else 'NIPS', args.envs, T_MAX, NUM_ACTIONS),
             'arch': args.arch, 'envs_per_gpu': args.envs, 't_max': T_MAX, 'num_actions': NUM_ACTIONS,
             'env_steps_per_step': args.envs * T_MAX * n_gpus,
+            'rollout_schedule': ('whole batch on one stream' if args.dev_slices <= 1 else
+                                 '%d contiguous environment slices, one stream each (act -> observe per slice in order; one update '
+                                 'on the whole batch)' % args.dev_slices),
             'parallelism': 'envs sharded over %d GPU(s); flat fp32 gradient all-reduced per update (NCCL; the fc + heads tail '
                            'under the conv weight-gradient kernels, the conv head after them)' % n_gpus,
             'l2': 'inputs larger than L2: each env step reads a different %d-deep rotating frame buffer of %.0f MB and '
@@ -315,6 +320,37 @@ def run_b200(args):
             eng.observe_frames(t, buf.data_ptr(), 1, None, rewards[t], over[t])
         eng.update(lr)
 
+    def make_step_sliced(S):
+        # The rollout as S contiguous environment slices (what the runners' workers own, runners.py:17-18), each on its own
+        # stream: every environment still sees act -> step -> observe in order and the update is the whole batch, so the
+        # results are the same bits (tests/test_gpu_engine.py: sliced == whole-batch); the kernels of one slice fill the
+        # SMs the other slice's kernels leave idle while they start up and drain.
+        bounds = [(c * N // S, (c + 1) * N // S) for c in range(S)]
+        streams = [torch.cuda.Stream(dev) for _ in bounds]
+        ev_done = [torch.cuda.Event() for _ in bounds]
+        ev_upd = torch.cuda.Event()
+
+        def step():
+            main = torch.cuda.current_stream(dev)
+            ev_upd.record(main)
+            for c, (lo, hi) in enumerate(bounds):
+                streams[c].wait_event(ev_upd)
+                with torch.cuda.stream(streams[c]):
+                    for t in range(T):
+                        eng.act(t, lo, hi)
+                        buf = pool[(counter[0] + t) % len(pool)]
+                        eng.observe_frames(t, buf.data_ptr() + lo * FRAME_PAIR_BYTES, 1, None, rewards[t], over[t], lo, hi)
+                    eng.bootstrap(lo, hi)
+                    ev_done[c].record(streams[c])
+            counter[0] += T
+            for e in ev_done:
+                main.wait_event(e)
+            eng.update(lr)
+        return step
+
+    if args.dev_slices > 1:
+        step_device = make_step_sliced(min(args.dev_slices, N))
+
     def barrier():
         if world > 1:
             torch.distributed.barrier()
@@ -429,7 +465,14 @@ def run_b200(args):
         kind = k['name'].rsplit('_', 1)[-1]
         units = units_total.get(k['name'], fwd_samples if kind == 'fwd' else B * args.steps)
         if bf16_math and k['name'] in dram_table:
-            k['traffic'] = dram_table[k['name']]['dram_bytes_per_unit'] * units / k['launches']
+            dt = dram_table[k['name']]
+            k['traffic'] = dt['dram_bytes_per_unit'] * units / k['launches']
+            # what ncu saw for ONE launch of this kernel at the captured batch (cold, serialised): DRAM rate against the same
+            # HBM peak and tensor-pipe activity -- which of the two roofs the kernel is really near
+            cap_units = dj.get('envs' if k['name'] == 'preprocess_u8' else 'batch')
+            if cap_units and dt.get('duration_us'):
+                k['ncu_dram_frac'] = dt['dram_bytes_per_unit'] * cap_units / (dt['duration_us'] * 1e-6) / 1e9 / hbm_peak
+                k['ncu_tensor_pipe_active'] = dt.get('tensor_pipe_active_pct', 0.0) / 100.0
     accounted = sum(k['ms'] for k in kernels)
     for k in kernels:
         k['share_of_step'] = k['ms'] / ms_total

@@ -209,6 +209,8 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     // but 13-60 % SLOWER than one launch per layer (profiles/r02_pipe_tune.json; DESIGN.md section 3.3 says why), so the
     // product path launches the layers one by one.  Role sizes: CTAs of conv1 / conv2 / conv3 out of the device's SMs, the fc
     // layer takes the rest; PAACB_PIPE_SPLIT="a,b,c" overrides the split, PAACB_PIPE_MIN_BATCH the smallest batch that uses it.
+    const char* c3 = getenv("PAACB_CONV3_PACKED");
+    c->conv3_packed = (c3 != nullptr) ? atoi(c3) : 1;
     const char* e = getenv("PAACB_PDL");
     c->pdl_on = (e == nullptr) ? 1 : atoi(e);
     e = getenv("PAACB_PIPE");

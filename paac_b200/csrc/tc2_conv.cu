@@ -260,6 +260,29 @@ static int conv_fwd_bf16(const paacb_ctx* ctx, int l, const float* params, const
   // (each case leaves its do-while with `break` when the layer's geometry is not the one it was written for)
   if (l == 1) do PAACB_FWD_CASE(G_FWD2) while (0);
   if (l == 1) do PAACB_FWD_CASE(G_FWD2N) while (0);
+  if (l == 2 && ctx->conv3_packed) do {
+    // conv3, two whole samples per tile (Geo<G_FWD3P>): the source planes as (channels, x, y, sample); one box = the 7 input
+    // rows kh .. kh + 6 of two samples; a box that runs past the last sample is zero-filled
+    using Ge = Geo<G_FWD3P>;
+    if (g.C * 2 != Ge::UB || g.W != Ge::WU || g.H != Ge::HQ || g.N != Ge::BN || g.K != Ge::KB * 64 || s != 1 || g.R != Ge::PARTS ||
+        g.S != 3 || g.OH != Ge::OH || g.OW != Ge::OW)
+      break;
+    const uint64_t pdims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)batch};
+    const uint64_t pstr[3] = {(uint64_t)g.C * 2, (uint64_t)g.W * g.C * 2, (uint64_t)g.H * g.W * g.C * 2};
+    const uint32_t pbox[4] = {(uint32_t)g.C, (uint32_t)g.W, (uint32_t)Ge::OH, (uint32_t)GeoPack<G_FWD3P>::SAMPLES};
+    static_assert(Ge::BOX_ROWS == Ge::OH * GeoPack<G_FWD3P>::SAMPLES, "box bytes");
+    rc = encode_tmap_bf16(&p.tmA[0], in_hi, 4, pdims, pstr, pbox, Ge::UB);
+    if (rc == PAACB_OK) rc = encode_tmap_bf16(&p.tmA[1], in_lo, 4, pdims, pstr, pbox, Ge::UB);
+    if (rc == PAACB_OK) rc = weight_maps(ctx, ctx->wb_f_hi, ctx->wb_f_lo, g, (uint64_t)g.K, (uint64_t)g.N, Ge::BN, p.tmW);
+    if (rc != PAACB_OK) return rc;
+    p.num_tiles = (int)((batch + GeoPack<G_FWD3P>::SAMPLES - 1) / GeoPack<G_FWD3P>::SAMPLES);
+    if (prep != nullptr) {
+      *prep = p;
+      *prep_geo = G_FWD3P;
+      return PAACB_OK;
+    }
+    return launch_convk<G_FWD3P>(ctx, p, K_FWD0 + l, st);
+  } while (0);
   if (l == 2) do PAACB_FWD_CASE(G_FWD3) while (0);
 #undef PAACB_FWD_CASE
   return PAACB_EUNSUPPORTED;

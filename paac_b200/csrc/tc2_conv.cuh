@@ -10,7 +10,8 @@ namespace paacb {
 // geometry of the five patch-resident GEMMs of the Nature network
 // ------------------------------------------------------------------------------------------------
 enum { G_FWD2 = 1, G_FWD3 = 2, G_DG3 = 3, G_DG2 = 4,        // Nature; conv1 forward has its own int8 kernel (tc2_conv1.cu)
-       G_FWD2N = 5, G_DG2N = 6 };                           // NIPS conv2 (networks.py:146): 64-byte units, SWIZZLE_64B
+       G_FWD2N = 5, G_DG2N = 6,                             // NIPS conv2 (networks.py:146): 64-byte units, SWIZZLE_64B
+       G_FWD3P = 7 };                                       // conv3 forward, two whole samples per tile (below)
 
 template <int G>
 struct Geo;
@@ -35,6 +36,26 @@ struct Geo<G_FWD3> {
   __host__ __device__ static constexpr int aoff(int t) { return (((t / 4) / 3) * 9 + ((t / 4) % 3)) * 128 + (t % 4) * 32; }
   __host__ __device__ static constexpr int jw(int, int t) { return t; }
 };
+// conv3 forward, PACKED (round 2): the geometry above enumerates the 9 x 9 INPUT grid, of which 7 x 7 positions are outputs
+// (60 % of the MMA rows).  A row group of an MMA operand is 8 consecutive 128-byte units and the groups lie at a uniform
+// stride (the descriptor's SBO, any multiple of 16 bytes: probe A_k128_sbo1152) -- so group g = output row (sample g / 7,
+// oh = g % 7), its 8 units = ow 0..7 (7 outputs), stride 9 units, over a patch copy that holds ONLY the 7 input rows
+// kh .. kh + 6 of each sample: the TMA box {64 ch, 9, 7 rows from kh, 2 samples} lands exactly that, densely.  One copy per
+// filter row kh (PARTS = 3; the 2nd and 3rd are L2 hits), tap (kh, kw) = copy kh at a byte offset of kw units.  A tile = two
+// whole samples = 14 of 16 groups x 7 of 8 units: 77 % of the MMA rows, 0.5 instead of 0.63 tiles per sample.
+template <>
+struct Geo<G_FWD3P> {
+  static constexpr bool DGRAD = false, A_LO = true, STAGED = false, MASK_BITS = false;
+  static constexpr int UB = 128, SWZ = SWZ_128B, PARTS = 3, WU = 9, HQ = 9, BOX_ROWS = 14, SLOT = 16384, NSLOTS = 5;
+  static constexpr int NACC = 1, BN = 64, KS = 12, KB = 9, OH = 7, OW = 7;
+  static constexpr int CH = 64, PIX = 1;
+  __host__ __device__ static constexpr int aoff(int t) { return (t / 4) * 128 + (t % 4) * 32; }
+  __host__ __device__ static constexpr int jw(int part, int t) { return part * 12 + t; }
+};
+// PACKED geometries: samples per tile; row-group stride of the A descriptor in units
+template <int G> struct GeoPack { static constexpr int SAMPLES = 0; };
+template <> struct GeoPack<G_FWD3P> { static constexpr int SAMPLES = 2; };
+
 // conv3 data-gradient: dZ3 [b,7,7,64] -> dX [b,9,9,64]; one sample per tile, positions enumerated 11 wide over the
 // zero-padded dZ (TMA out-of-bounds fill), tap (kh, kw) reads position q + (2-kh)*11 + (2-kw).
 template <>
@@ -156,6 +177,7 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
   using Cfg = ConvKCfg<G>;
   constexpr int NSLOTS = Ge::NSLOTS, BN = Ge::BN, NACC = Ge::NACC;
   static_assert(!PIPE || !Ge::DGRAD, "the pipelined hand-off is a forward feature");
+  constexpr int PACK = GeoPack<G>::SAMPLES;       // > 0: whole samples per tile, one patch copy per filter row
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
   uint8_t* wsm = smem + Cfg::RING_BYTES;
@@ -215,22 +237,28 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
           // the tile's positions [128 tile, 128 tile + 128) belong to these samples of the layer above (WU * HQ positions each);
           // rows the box reads beyond them feed only positions that are discarded
           constexpr int PPS = Ge::WU * Ge::HQ;
-          const int n0 = (tile * 128) / PPS;
-          int n1 = (tile * 128 + 127) / PPS;
+          const int n0 = PACK > 0 ? PACK * tile : (tile * 128) / PPS;
+          int n1 = PACK > 0 ? PACK * tile + PACK - 1 : (tile * 128 + 127) / PPS;
           if (n1 > p.batch - 1) n1 = p.batch - 1;
           pipe_wait(io, n0, n1, io.up_target);
         }
         // (requesting the boxes of the tile after next into L2 with cp.async.bulk.prefetch.tensor was measured: 3 % slower)
+        // slot order: (part, piece) with the piece fastest; PACKED: piece slowest, so that the MMAs run in the same order as in
+        // the input-grid geometry (all taps of A_hi, then all taps of A_lo) and the accumulators hold the same bits
+        constexpr int NPIECE = Ge::A_LO ? 2 : 1;
 #pragma unroll 1
-        for (int part = 0; part < Ge::PARTS; ++part) {
-#pragma unroll 1
-          for (int piece = 0; piece < (Ge::A_LO ? 2 : 1); ++piece) {
+        for (int it = 0; it < Ge::PARTS * NPIECE; ++it) {
+          const int part = PACK > 0 ? it % Ge::PARTS : it / NPIECE;
+          const int piece = PACK > 0 ? it / Ge::PARTS : it % NPIECE;
+          {
             mbar_wait(&empty_bar[slot], phase ^ 1u);
             if (PAACB_DBGV(p.dbg) & 1024) { mbar_arrive(&full_bar[slot]); if (++slot == NSLOTS) { slot = 0; phase ^= 1u; } continue; }
             mbar_arrive_expect_tx(&full_bar[slot], Cfg::BOX_BYTES);
             uint8_t* dst = ring + slot * Ge::SLOT;
             if constexpr (Ge::DGRAD) {
               tma_load_4d(dst, &p.tmA[piece], 0, -Ge::PAD, -Ge::PAD, tile, &full_bar[slot]);
+            } else if constexpr (PACK > 0) {
+              tma_load_4d(dst, &p.tmA[piece], 0, 0, part, PACK * tile, &full_bar[slot]);     // input rows part .. part + OH - 1
             } else {
               const int row0 = (int)(((int64_t)tile * 128) / Ge::WU);
               tma_load_4d(dst, &p.tmA[piece], 0, 0, part, row0, &full_bar[slot]);
@@ -245,7 +273,7 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc_full = make_idesc_bf16(2 * Cfg::NT, 0, 0);
     constexpr uint32_t idesc_half = make_idesc_bf16(Cfg::NT, 0, 0);
-    const uint64_t adesc0 = make_smem_desc(0, 16, 8 * Ge::UB, Ge::SWZ);
+    const uint64_t adesc0 = make_smem_desc(0, 16, (PACK > 0 ? Ge::WU : 8) * Ge::UB, Ge::SWZ);
     const uint64_t bdesc0 = make_smem_desc(0, 16, 1024, SWZ_128B);
     const uint32_t ring_a = smem_u32(ring);
     const uint32_t w_a = smem_u32(wsm);
@@ -259,12 +287,14 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
       mbar_wait(&tempty_bar[ab], aph ^ 1u);
       tc_fence_after();
       uint32_t rel = 0;
-      if constexpr (!Ge::DGRAD) rel = (uint32_t)(((int64_t)tile * 128) % Ge::WU) * Ge::UB;
+      if constexpr (!Ge::DGRAD && PACK == 0) rel = (uint32_t)(((int64_t)tile * 128) % Ge::WU) * Ge::UB;
       const uint32_t d0 = tmem_base + (uint32_t)(ab * 2 * Cfg::NT);
+      constexpr int NPIECE = Ge::A_LO ? 2 : 1;
 #pragma unroll
-      for (int part = 0; part < Ge::PARTS; ++part) {
-#pragma unroll
-        for (int piece = 0; piece < (Ge::A_LO ? 2 : 1); ++piece) {
+      for (int it = 0; it < Ge::PARTS * NPIECE; ++it) {
+        const int part = PACK > 0 ? it % Ge::PARTS : it / NPIECE;       // same slot order as the producer
+        const int piece = PACK > 0 ? it / Ge::PARTS : it % NPIECE;
+        {
           mbar_wait(&full_bar[slot], phase);
           tc_fence_after();
           if (leader) {
@@ -432,6 +462,13 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
         qh = r / Ge::WU;
         qw = r - qh * Ge::WU;
         ok = (qh < Ge::OH) && (qw < Ge::OW);
+      } else if constexpr (PACK > 0) {
+        const int g = r >> 3, ju = r & 7;                             // row group = (sample, output row), unit = output column
+        const int n = PACK * tile + g / Ge::OH;
+        const int oh = g % Ge::OH;
+        ok = (g < PACK * Ge::OH) && (ju < Ge::OW) && (n < p.batch);
+        pix = ((int64_t)n * Ge::OH + oh) * Ge::OW + ju;
+        n_fwd = n;
       } else {
         const uint32_t q = (uint32_t)tile * 128u + (uint32_t)r;      // < 2^31 (checked by the launcher)
         const uint32_t prow = q / (uint32_t)Ge::WU;

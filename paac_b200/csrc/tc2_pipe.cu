@@ -22,6 +22,7 @@ struct PipeParams {
   Conv1Params c1;
   ConvKParams c2;
   ConvKParams c3;        // Nature only
+  int c3_geo;            // G_FWD3 (input-grid tiles) or G_FWD3P (two samples per tile): the geometry the stand-alone launch would use
   StreamParams fc;
   int s1, s2, s3;        // CTAs of conv1, conv2, conv3 (NIPS: s3 = 0); the fc layer takes the rest of the grid
   uint32_t* cnt1;        // [batch]               conv1 output positions stored, per sample        (complete: 400)
@@ -38,7 +39,8 @@ struct PipeCfg {
   static constexpr int G2 = NATURE ? G_FWD2 : G_FWD2N;
   static constexpr int SMEM_C1 = kC1_SMEM_FIXED + C1<NC1>::WBYTES;
   static constexpr int SMEM_C2 = ConvKCfg<G2>::SMEM_BYTES;
-  static constexpr int SMEM_C3 = NATURE ? ConvKCfg<G_FWD3>::SMEM_BYTES : 0;
+  static constexpr int SMEM_C3 = NATURE ? (ConvKCfg<G_FWD3>::SMEM_BYTES > ConvKCfg<G_FWD3P>::SMEM_BYTES ? ConvKCfg<G_FWD3>::SMEM_BYTES
+                                                                                                         : ConvKCfg<G_FWD3P>::SMEM_BYTES) : 0;
   static constexpr int SMEM_FC = StreamCfg<kFcBN, ST_FWD>::SMEM_BYTES;
   static constexpr int M1 = SMEM_C1 > SMEM_C2 ? SMEM_C1 : SMEM_C2;
   static constexpr int M2 = SMEM_C3 > SMEM_FC ? SMEM_C3 : SMEM_FC;
@@ -62,7 +64,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) forward_pipe_kernel(const __g
   } else if (NATURE && b < p.s1 + p.s2 + p.s3) {
     if constexpr (NATURE) {
       const PipeIO io = {p.cnt2, (uint32_t)(Geo<G_FWD2>::OH * Geo<G_FWD2>::OW), p.cnt3, 7, p.err};
-      convk_body<G_FWD3, true>(p.c3, b - p.s1 - p.s2, p.s3, smem_raw, io);
+      if (p.c3_geo == G_FWD3P) convk_body<G_FWD3P, true>(p.c3, b - p.s1 - p.s2, p.s3, smem_raw, io);
+      else convk_body<G_FWD3, true>(p.c3, b - p.s1 - p.s2, p.s3, smem_raw, io);
     }
   } else {
     const int first = p.s1 + p.s2 + p.s3;
@@ -121,7 +124,8 @@ int launch_forward_pipe_bf16(const paacb_ctx* ctx, const float* params, const ui
   if (rc == PAACB_OK && geo != (nature ? G_FWD2 : G_FWD2N)) rc = PAACB_EUNSUPPORTED;
   if (rc == PAACB_OK && nature) {
     rc = prepare_conv_fwd_bf16(ctx, 2, params, fwd_ws, batch, slice, &p.c3, &geo);
-    if (rc == PAACB_OK && geo != G_FWD3) rc = PAACB_EUNSUPPORTED;
+    if (rc == PAACB_OK && geo != G_FWD3 && geo != G_FWD3P) rc = PAACB_EUNSUPPORTED;
+    p.c3_geo = geo;
   }
   if (rc == PAACB_OK) rc = prepare_fc_fwd_bf16(ctx, L - 1, params, fwd_ws, batch, slice, &p.fc);
   if (rc != PAACB_OK) return rc;
