@@ -242,7 +242,8 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
           if (n1 > p.batch - 1) n1 = p.batch - 1;
           pipe_wait(io, n0, n1, io.up_target);
         }
-        // (requesting the boxes of the tile after next into L2 with cp.async.bulk.prefetch.tensor was measured: 3 % slower)
+        // (requesting the boxes of the tile after next into L2 with cp.async.bulk.prefetch.tensor was measured: 3 % slower; the
+        // packed conv3 geometry with the NEXT tile's two samples prefetched: 0.603 -> 0.617 ms per step, tools/gpu_round2_x.sh)
         // slot order: (part, piece) with the piece fastest; PACKED: piece slowest, so that the MMAs run in the same order as in
         // the input-grid geometry (all taps of A_hi, then all taps of A_lo) and the accumulators hold the same bits
         constexpr int NPIECE = Ge::A_LO ? 2 : 1;
