@@ -136,7 +136,9 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     const char* hg = getenv("PAACB_K1_HOST_GRID");      // tuning knob for tools/experiments/pcie_probe.py
     c->k1_host_grid = (hg != nullptr && atoi(hg) > 0) ? atoi(hg) : 96;
     const char* kp = getenv("PAACB_K1_PIPE");
-    c->k1_pipe = (kp != nullptr) ? atoi(kp) : 1;
+    c->k1_pipe = (kp != nullptr) ? atoi(kp) : 2;
+    const char* kg = getenv("PAACB_K1_PIPE_HOST_GRID");
+    c->k1_pipe_host_grid = (kg != nullptr && atoi(kg) > 0) ? atoi(kg) : 32;
     const char* kh = getenv("PAACB_K1_HINTS");
     c->k1_hints = (kh != nullptr) ? atoi(kh) : 3;
   }

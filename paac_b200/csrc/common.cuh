@@ -127,7 +127,9 @@ struct paacb_ctx {
   mutable uintptr_t k1_cache_key[kK1Cache];
   mutable int k1_cache_host[kK1Cache];
   int k1_host_grid;             // PAACB_K1_HOST_GRID (default 96)
-  int k1_pipe;                  // PAACB_K1_PIPE (default 1): device-resident frames go through the persistent copy pipeline
+  int k1_pipe;                  // PAACB_K1_PIPE (default 2): 0 = CTA-per-environment kernel only, 1 = device-resident frames go through the persistent
+                                // copy pipeline, 2 = pinned host frames too (on k1_pipe_host_grid CTAs: PCIe needs few loads in flight)
+  int k1_pipe_host_grid;        // PAACB_K1_PIPE_HOST_GRID (default 32)
   int k1_hints;                 // PAACB_K1_HINTS (default 3): bit 0 = inputs read evict-first, bit 1 = new stack written evict-last
   // layer-pipelined forward (tc2_pipe.cu): hand-off counters (one buffer per stream in use), role sizes, sticky error word
   static constexpr int kPipeBufs = 4;

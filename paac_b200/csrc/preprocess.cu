@@ -422,8 +422,14 @@ int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, co
   }
   bool affine = true;       // row(2k) = row(0) + 5k, row(2k + 1) = row(1) + 5k: what the two row-parity tensor maps can express
   for (int y = 0; y < PAACB_OBS; ++y) affine = affine && ((int)ctx->tabs.row[y] == (int)ctx->tabs.row[y & 1] + 5 * (y >> 1));
-  if (!is_host && ctx->k1_pipe && affine && (((uintptr_t)frames | (uintptr_t)prev | (uintptr_t)next) & 15) == 0 &&
-      n * pairs * 2 < (1LL << 31)) {
+  // (a CTA of the pipeline needs at least two environments to overlap anything: batches up to one environment per SM -- the
+  // reference's default 32 -- keep the CTA-per-environment kernel)
+  // PAACB_K1_PIPE=2 (default): pinned host frames go through the pipeline too, on PAACB_K1_PIPE_HOST_GRID CTAs -- the TMA engine's
+  // row reads cross PCIe at 43.1 GB/s against 42.0 for the threads' 16-byte loads (tools/experiments/pcie_probe.py), 32 SMs are
+  // held instead of 96, and the end-to-end cycle went 16.37 -> 15.8-15.95 ms (tools/gpu_round2_y.sh)
+  const bool pipe_host = is_host && ctx->k1_pipe == 2;
+  if ((!is_host || pipe_host) && ctx->k1_pipe && affine && n > (int64_t)ctx->num_sms &&
+      (((uintptr_t)frames | (uintptr_t)prev | (uintptr_t)next) & 15) == 0 && n * pairs * 2 < (1LL << 31)) {
     // device-resident frames: the persistent copy pipeline, one CTA per SM
     static DeviceOnce attr_once;
     if (!attr_once.done(ctx->device)) {
@@ -444,7 +450,7 @@ int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, co
     if (rc != PAACB_OK) return rc;
     p.frames = frames; p.reset = reset; p.prev = prev; p.next = next;
     p.n_envs = n; p.pairs = pairs; p.hints = ctx->k1_hints; p.sc = sc; p.tabs = ctx->tabs;
-    const unsigned pgrid = n < (int64_t)ctx->num_sms ? (unsigned)n : (unsigned)ctx->num_sms;
+    const unsigned pgrid = (unsigned)((pipe_host && ctx->k1_pipe_host_grid < ctx->num_sms) ? ctx->k1_pipe_host_grid : ctx->num_sms);
     PAACB_LAUNCH_BEGIN(ctx, K_PREPROCESS, st);
     preprocess_u8_pipe_kernel<<<pgrid, kK1PipeThreads, kK1PipeSmem, st>>>(p);
     PAACB_LAUNCH_END(ctx, K_PREPROCESS, st);

@@ -50,7 +50,20 @@ def k1():
                                             C.c_void_p(st.cuda_stream)), 'k1')
 ms = timeit(k1)
 print('c) zero-copy K1 (grid 96): %.3f ms  %.1f GB/s over PCIe' % (ms, sel_bytes / ms / 1e6))
-for g in (32, 64, 148, 296, 592):
+for pipe, g in ((1, 32), (1, 148), (1, 592), (2, 8), (2, 16), (2, 32), (2, 64), (2, 148)):
+    # the knobs are read when a context is created: a fresh network per setting
+    os.environ['PAACB_K1_PIPE'] = str(pipe)
     os.environ['PAACB_K1_HOST_GRID'] = str(g)
-    ms = timeit(k1)
-    print('   zero-copy K1 grid %d: %.3f ms  %.1f GB/s' % (g, ms, sel_bytes / ms / 1e6))
+    os.environ['PAACB_K1_PIPE_HOST_GRID'] = str(g)
+    net = NaturePolicyVNetwork(conf)
+    try:
+        ms = timeit(k1)
+        print('   %s grid %d: %.3f ms  %.1f GB/s' % ('zero-copy K1 (CTA per env)' if pipe == 1 else 'zero-copy K1 through the TMA pipeline', g, ms, sel_bytes / ms / 1e6))
+        if pipe == 2:
+            ref = nxt.clone()
+            os.environ['PAACB_K1_PIPE'] = '1'
+            net = NaturePolicyVNetwork(conf); k1(); torch.cuda.synchronize()
+            print('      same bytes as the CTA-per-env kernel:', bool(torch.equal(ref, nxt)))
+    except Exception as e:
+        print('   pipe=%d grid %d failed: %s' % (pipe, g, str(e)[:200]))
+        break
