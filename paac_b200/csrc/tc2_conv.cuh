@@ -243,7 +243,9 @@ __device__ __forceinline__ void convk_body(const ConvKParams& p, const int cta, 
           pipe_wait(io, n0, n1, io.up_target);
         }
         // (requesting the boxes of the tile after next into L2 with cp.async.bulk.prefetch.tensor was measured: 3 % slower; the
-        // packed conv3 geometry with the NEXT tile's two samples prefetched: 0.603 -> 0.617 ms per step, tools/gpu_round2_x.sh)
+        // packed conv3 geometry with the NEXT tile's two samples prefetched: 0.603 -> 0.617 ms per step, tools/gpu_round2_x.sh;
+        // prefetch.global.L2 of the tile after next by the idle epilogue threads, one per 128-byte line: conv2 0.76-0.79 -> 0.79-0.83,
+        // conv3 unchanged, tools/gpu_round2_z.sh -- these kernels do not wait for first-touch DRAM latency)
         // slot order: (part, piece) with the piece fastest; PACKED: piece slowest, so that the MMAs run in the same order as in
         // the input-grid geometry (all taps of A_hi, then all taps of A_lo) and the accumulators hold the same bits
         constexpr int NPIECE = Ge::A_LO ? 2 : 1;

@@ -3,11 +3,11 @@ sample (per env for the preprocessing kernel) of every hot-path kernel, keyed by
 usage: python tools/ncu_dram_table.py gpurun_out/x.ncu-rep BATCH ENVS > profiles/r01_ncu_dram_bytes.json"""
 import csv, io, json, re, subprocess, sys
 
-NAMES = [(r'conv1_i8_kernel', 'conv1_fwd'), (r'convk_kernel<1>', 'conv2_fwd'), (r'convk_kernel<2>', 'conv3_fwd'),
+NAMES = [(r'conv1_i8_kernel', 'conv1_fwd'), (r'convk_kernel<1>', 'conv2_fwd'), (r'convk_kernel<2>', 'conv3_fwd'), (r'convk_kernel<7>', 'conv3_fwd'),
          (r'convk_kernel<3>', 'conv3_dgrad'), (r'convk_kernel<4>', 'conv2_dgrad'), (r'stream_gemm_kernel<128, 0>', 'fc4_fwd'),
          (r'stream_gemm_kernel<128, 1>', 'fc4_dgrad'), (r'stream_gemm_kernel<128, 2>', 'fc4_wgrad'),
          (r'wgrad2_kernel<0>', 'conv1_wgrad'), (r'wgrad2_kernel<1>', 'conv2_wgrad'), (r'wgrad2_kernel<2>', 'conv3_wgrad'),
-         (r'preprocess_u8_kernel', 'preprocess_u8'), (r'heads_fwd', 'heads_fwd'), (r'heads_bwd', 'heads_bwd')]
+         (r'preprocess_u8_pipe_kernel', 'preprocess_u8'), (r'preprocess_u8_kernel', 'preprocess_u8'), (r'heads_fwd', 'heads_fwd'), (r'heads_bwd', 'heads_bwd')]
 
 
 def gb(value, unit):
