@@ -213,6 +213,8 @@ int paacb_create(paacb_ctx** out, int arch, int num_actions, int device) {
     // layer takes the rest; PAACB_PIPE_SPLIT="a,b,c" overrides the split, PAACB_PIPE_MIN_BATCH the smallest batch that uses it.
     const char* c3 = getenv("PAACB_CONV3_PACKED");
     c->conv3_packed = (c3 != nullptr) ? atoi(c3) : 1;
+    const char* rk = getenv("PAACB_SM_RESERVE_KERNELS");
+    c->sm_reserve_kernels = (rk != nullptr) ? atoi(rk) : 3;
     const char* e = getenv("PAACB_PDL");
     c->pdl_on = (e == nullptr) ? 1 : atoi(e);
     e = getenv("PAACB_PIPE");

@@ -144,6 +144,7 @@ struct paacb_ctx {
   mutable void* pipe_stream[kPipeBufs];
   int conv3_packed;             // PAACB_CONV3_PACKED (default 1): conv3 forward with two whole samples per tile (tc2_conv.cuh: Geo<G_FWD3P>)
   int pdl_on;                   // PAACB_PDL (default 1): programmatic dependent launch between the kernels of one forward / backward
+  int sm_reserve_kernels;       // PAACB_SM_RESERVE_KERNELS (default 3): how many of the conv weight-gradient kernels, in launch order, leave them
   int sm_reserve;               // paacb_set_sm_reserve: SMs the persistent conv weight-gradient kernels leave free (multi-GPU)
   int dbg;                      // PAACB_DBG: ablation switches of the tcgen05 kernels for timing experiments (0 in production)
 };

@@ -430,7 +430,11 @@ static int launch_wg2(const paacb_ctx* ctx, const Wg2Params& p, cudaStream_t st)
   }
   // multi-GPU: the gradient tail is being all-reduced while these kernels run; one persistent CTA per SM with the maximum
   // shared-memory carve-out would leave the collective's CTAs nowhere to go until a whole kernel retires
-  const int sms = ctx->num_sms - ctx->sm_reserve > 0 ? ctx->num_sms - ctx->sm_reserve : 1;
+  // (the collective is launched when the first of these kernels is: only the first sm_reserve_kernels of them -- conv3, conv2,
+  // conv1 in launch order -- leave the SMs free, PAACB_SM_RESERVE_KERNELS)
+  const int order = (ctx->n_layers - 2) - Wg<L>::LAYER;
+  const int reserve = (order < ctx->sm_reserve_kernels) ? ctx->sm_reserve : 0;
+  const int sms = ctx->num_sms - reserve > 0 ? ctx->num_sms - reserve : 1;
   const unsigned grid = (unsigned)(p.stages_total < sms ? p.stages_total : sms);
   PAACB_LAUNCH_BEGIN(ctx, K_WGRAD0 + Wg<L>::LAYER, st);
   launch_kernel(wgrad2_kernel<L>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, ctx->pdl_on != 0, p);

@@ -77,10 +77,27 @@ class RolloutEngine(object):
         self.overlap_allreduce = bool(overlap_allreduce)
         self.tail_off = int(self.lib.paacb_grad_tail_offset(self.ctx))
         self._pending = []
+        self.tail_group = self.group
         if self.world > 1 and self.overlap_allreduce and hasattr(self.lib, 'paacb_set_sm_reserve'):
-            # the tail's all-reduce runs under the conv weight-gradient kernels: leave its CTAs a few SMs (PAACB_SM_RESERVE)
+            # The tail's all-reduce runs under the conv weight-gradient kernels, which are persistent CTAs with the maximum
+            # shared-memory carve-out: they leave PAACB_SM_RESERVE SMs free, and the collective must FIT there.  NCCL's default on
+            # NVSwitch is up to 24 NVLS channels = 24 CTAs that all have to be resident before any of them makes progress: with 8 SMs
+            # free, 8 of them spin until the first weight-gradient kernel retires, the other 16 then take SMs from the NEXT kernel,
+            # whose last 16 CTAs wait for the collective and run alone afterwards (measured at 8 GPUs: conv2's weight gradient
+            # 0.31 -> 0.47 ms, the whole cost of the N = 8 step over the N = 1 step).  So the tail goes through its own
+            # communicator limited to as many CTAs as SMs are reserved (ProcessGroupNCCL max_ctas; 6.4 MB on 8 CTAs: 94 us
+            # against 71 us on 24, tools/experiments/allreduce_probe.py); the small conv-head reduction after the backward
+            # keeps the default communicator.
             import os
-            _lib.check(self.lib.paacb_set_sm_reserve(self.ctx, int(os.environ.get('PAACB_SM_RESERVE', '8'))), 'paacb_set_sm_reserve')
+            reserve = int(os.environ.get('PAACB_SM_RESERVE', '8'))
+            _lib.check(self.lib.paacb_set_sm_reserve(self.ctx, reserve), 'paacb_set_sm_reserve')
+            max_ctas = int(os.environ.get('PAACB_TAIL_MAX_CTAS', str(reserve)))
+            if max_ctas > 0 and torch.distributed.get_backend(self.group) == 'nccl':
+                opts = torch.distributed.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = max_ctas
+                opts.config.min_ctas = 1
+                ranks = torch.distributed.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
+                self.tail_group = torch.distributed.new_group(ranks=ranks, pg_options=opts)
 
         d, N, T, A, B = self.dev, self.N, self.T, self.A, self.B
         f32 = dict(dtype=torch.float32, device=d)
@@ -357,7 +374,7 @@ class RolloutEngine(object):
                            'paacb_backward_part')
                 if part == _lib.BWD_TAIL:
                     self._pending = [torch.distributed.all_reduce(self.grads[self.tail_off:], op=torch.distributed.ReduceOp.SUM,
-                                                                  group=self.group, async_op=True)]
+                                                                  group=self.tail_group, async_op=True)]
             return
         _lib.check(self.lib.paacb_backward(self.ctx, p(self.net.params), p(flat_states), B, p(self.fwd_ws),
                                            p(self.dlogits), p(self.dv), p(self.bwd_ws), p(self.grads), st),
