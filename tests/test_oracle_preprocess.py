@@ -68,3 +68,18 @@ def test_max_pool_is_elementwise_and_commutative():
     b = opre.process_frame_pool(pair[::-1], row, col)
     assert (a == b).all()
     assert (a == np.maximum(pair[0], pair[1])[row[:, None], col[None, :]]).all()
+
+
+def test_row_table_is_two_uniform_pitches():
+    """K1's copy pipeline lands the selected frame rows with two rank-3 TMA boxes (csrc/preprocess.cu): that needs Pillow's
+    NEAREST row table for 210 -> 84 to be row(2k) = 5k + 1, row(2k + 1) = 5k + 3 -- each parity a uniform 5-row (800-byte)
+    pitch that also runs across frames (210 = 42 * 5) -- and the last selected row of a frame to lie inside it.  (The launcher
+    checks the pattern on the tables it is given and falls back to the CTA-per-environment kernel otherwise.)"""
+    from paac_b200.resize_tables import ROW, COL
+    rows = [int(r) for r in ROW]
+    assert len(rows) == 84 and len(COL) == 84
+    assert rows[0::2] == [5 * k + 1 for k in range(42)]
+    assert rows[1::2] == [5 * k + 3 for k in range(42)]
+    assert 210 == 42 * 5 and max(rows) < 210
+    # the same table from its definition (SURVEY App. A): floor((i + 0.5) * 210 / 84), in integers
+    assert rows == [((2 * i + 1) * 210) // 168 for i in range(84)]
