@@ -396,10 +396,11 @@ int launch_stack_from_planes(const paacb_ctx* ctx, const uint8_t* ring, int ring
 int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, const uint8_t* reset,
                       const uint8_t* prev, uint8_t* next, int64_t n, const StepScalars& sc, cudaStream_t st) {
   if (n == 0) return PAACB_OK;
-  // Frames in pinned, mapped HOST memory (the runners' buffers, read zero-copy): the kernel is PCIe-bound and needs only
-  // ~100 KB of loads in flight, so it runs as a narrow grid-stride grid (one CTA on a subset of the SMs) that leaves
-  // room for the persistent tensor-core kernels of the next environment slice to run beside it.  Device-resident frames:
-  // HBM-bound, one CTA per environment.
+  // Two kernels.  More than one environment per SM: the persistent TMA copy pipeline (above) -- one CTA per SM for device-resident
+  // frames (HBM-bound), PAACB_K1_PIPE_HOST_GRID CTAs for frames in pinned, mapped HOST memory (the runners' buffers, read
+  // zero-copy: PCIe-bound, few loads in flight are enough, and the other SMs stay free for the tensor-core kernels of the next
+  // environment slice).  Small batches, or a row table that is not the two-pitch pattern: the CTA-per-environment kernel
+  // (host frames: as a narrow grid-stride grid, PAACB_K1_HOST_GRID).
   unsigned grid = (unsigned)n;
   // is the frame buffer host memory?  The answer is cached per 2 MB-aligned address range the caller has used (a runner's
   // buffer is registered once and then read every step: no driver query on the hot path)
@@ -430,7 +431,6 @@ int launch_preprocess(const paacb_ctx* ctx, const uint8_t* frames, int pairs, co
   const bool pipe_host = is_host && ctx->k1_pipe == 2;
   if ((!is_host || pipe_host) && ctx->k1_pipe && affine && n > (int64_t)ctx->num_sms &&
       (((uintptr_t)frames | (uintptr_t)prev | (uintptr_t)next) & 15) == 0 && n * pairs * 2 < (1LL << 31)) {
-    // device-resident frames: the persistent copy pipeline, one CTA per SM
     static DeviceOnce attr_once;
     if (!attr_once.done(ctx->device)) {
       cudaError_t e = cudaFuncSetAttribute(preprocess_u8_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1PipeSmem);
